@@ -1,0 +1,166 @@
+/* newman_b200.h — C-ABI of the B200-native Mandelbrot hot path (libnewman_b200.so).
+ *
+ * The reference (axnjaxn/newman) has no FFI: its de-facto boundary is the C++ surface
+ * `class Mandelbrot` (reference mandelbrot.h:22-53) + `RenderGrid` (grid.h:6-25). This header is the
+ * thin C shim underneath our drop-in for that class (include/newman_b200/mandelbrot.h): plain
+ * pointers and sizes, int status codes, no exceptions, no torch/C++ types. Every entry point names
+ * the reference code it replaces.
+ *
+ * Conventions
+ *   - All `nm_*` functions return NM_OK (0) or a negative NM_E* code; nm_last_error() gives text.
+ *   - One nm_ctx per host thread and per GPU. Calls on one ctx are stream-ordered on its stream.
+ *   - "h/d pointer": source/destination buffers may be HOST or DEVICE memory (cudaMemcpyDefault
+ *     decides by pointer attributes), so a multi-GPU caller can hand over NCCL-received buffers.
+ *   - Output records are the reference's `RenderGrid::EscapeValue` (grid.h:8-16): 8 bytes,
+ *     {int32 iterations; float32 smoothing}, row-major.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry returns NM_ENODEV.
+ */
+#ifndef NEWMAN_B200_H
+#define NEWMAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define NM_API __attribute__((visibility("default")))
+#else
+#define NM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NM_OK 0
+#define NM_EINVAL (-1)  /* bad argument */
+#define NM_ENODEV (-2)  /* no CUDA device / driver */
+#define NM_ECUDA (-3)   /* CUDA runtime error (see nm_last_error) */
+#define NM_ENOMEM (-4)
+#define NM_ESTATE (-5)  /* call order violated (e.g. launch without a frame) */
+#define NM_ERANGE (-6)  /* tables not representable (non-finite coefficient; reference would SIGFPE) */
+#define NM_ECANCELLED (-7)
+
+typedef struct nm_ctx nm_ctx;
+
+/* grid.h:8-16 */
+typedef struct nm_escape {
+  int32_t iterations;
+  float smoothing;
+} nm_escape;
+
+/* ---- context ------------------------------------------------------------------------------ */
+NM_API int nm_create(int device, nm_ctx** out);
+NM_API void nm_destroy(nm_ctx* ctx);
+NM_API const char* nm_last_error(const nm_ctx* ctx); /* ctx may be NULL: last error of nm_create */
+NM_API const char* nm_version(void);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream. */
+NM_API int nm_set_stream(nm_ctx* ctx, void* cuda_stream);
+NM_API int nm_sync(nm_ctx* ctx);
+/* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
+NM_API int nm_cancel(nm_ctx* ctx);
+
+/* ---- K1: plain-double escape ----------------------------------------------------------------
+ * Replaces Mandelbrot::getIterationsHW + inCardioid + getSmoothingMagnitude
+ * (mandelbrot.cpp:231-254, 63-71, 133-136) for every pixel of rows x cols.
+ * c_re[nc], c_im[nr]: pixel coordinates, already descended (truncated) by the host exactly as
+ * computeRow does (mandelbrot.cpp:271, 275, 234). Separable because the pixel map is.
+ * The cardioid/bulb test runs in double on the device; pixels whose margin is too small to decide
+ * in double are iterated anyway and reported in the "ambiguous" list so the host can repeat the
+ * reference's mpf test for just those (nm_frame_ambiguous). */
+NM_API int nm_frame_hw(nm_ctx* ctx, const double* c_re, int nc, const double* c_im, int nr, int N);
+
+/* ---- K2+K3: series skip + perturbation ------------------------------------------------------
+ * Replaces Mandelbrot::getIterations (mandelbrot.cpp:144-229): phases 1-2 (series scan, binary
+ * search) verbatim in double, phase 3 as the FP64 perturbation iteration against the orbit.
+ * Tables are produced by the host with the reference's own arbitrary-precision recurrences
+ * (findProbe/computeOrbit/computeSeries, mandelbrot.cpp:73-131) and descended once. */
+typedef struct nm_deep_tables {
+  int32_t M;            /* orbit length = X.size() (mandelbrot.cpp:106) */
+  int32_t N;            /* iteration limit */
+  int32_t has_escape;   /* 1: x_hi holds M+1 entries, entry M = the escaped iterate the reference drops */
+  int32_t reserved;
+  double tol;           /* error_tolerance (isUnstable, mandelbrot.cpp:138-142) */
+  double glitch_tol;    /* glitch rule |X_n+d_n|^2 < glitch_tol*|X_n|^2 (same squared-magnitude form) */
+  const double* x_hi;   /* [2*(M+has_escape)] re,im interleaved: truncated doubles of X[i] */
+  const double* x_lo;   /* [2*M] truncated doubles of X[i]-x_hi[i] (phase-2 'X[mid]+d[mid]' in mpf) */
+  const double* a;      /* [2*M] descended A[i] (mandelbrot.cpp:166) */
+  const double* b;      /* [2*M] descended B[i] */
+  const double* c;      /* [2*M] descended C[i] */
+} nm_deep_tables;
+
+#define NM_CARDIOID_NONE 0 /* no pixel of the view is inside cardioid/bulb (mandelbrot.cpp:149) */
+#define NM_CARDIOID_ALL 1  /* every pixel is */
+#define NM_CARDIOID_MASK 2 /* per-pixel byte mask supplied */
+
+#define NM_MODE_REQUEUE 0 /* glitched pixels are flagged and listed for a secondary reference */
+#define NM_MODE_REBASE 1  /* final pass: no glitch flagging; rebase onto orbit start when |z|<|d| */
+
+/* Starts a deep frame over the whole raster (pix_list == NULL) or over the listed pixel ids
+ * (secondary-reference rounds; ids are r*nc+c). eps_re[nc], eps_im[nr] are the truncated doubles of
+ * (pixel - X[0]) formed in mpf as mandelbrot.cpp:155-159. */
+NM_API int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, int nc,
+                  const double* eps_im, int nr, int cardioid_mode, const uint8_t* cardioid_mask,
+                  const int32_t* pix_list, int64_t n_list, int mode);
+
+/* Enqueue all kernels of the current frame on the ctx stream (asynchronous). */
+NM_API int nm_launch(nm_ctx* ctx);
+
+/* After nm_launch: sizes/contents of the host-assist lists (these calls synchronise).
+ *  ambiguous: pixel ids whose double cardioid test was undecidable (K1 only).
+ *  requeue:   pixel ids flagged as glitched (K3, NM_MODE_REQUEUE), with the iteration of the flag.
+ * Buffers may be NULL to query the count. */
+NM_API int64_t nm_frame_ambiguous(nm_ctx* ctx, int32_t* pix, int64_t cap);
+NM_API int64_t nm_frame_requeue(nm_ctx* ctx, int32_t* pix, int32_t* at_iter, int64_t cap);
+/* Overwrite one pixel's record (host verdict for an ambiguous pixel). */
+NM_API int nm_poke(nm_ctx* ctx, int64_t pix, nm_escape v);
+
+/* Copy rows [r0, r1) of the finished raster to dst (h/d pointer, (r1-r0)*nc records).
+ * Applies the float32-rounding fix-ups first (see DESIGN.md "smoothing"): the handful of pixels
+ * whose smoothing value sits within the device libm's error of a float32 rounding boundary are
+ * re-evaluated with the host libm the reference uses (mandelbrot.cpp:133-136). */
+NM_API int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst);
+
+typedef struct nm_stats {
+  uint64_t pixels;          /* samples in the frame (or list) */
+  uint64_t executed_iters;  /* z<-z^2+c (K1) or delta updates (K3) actually performed */
+  uint64_t series_evals;    /* exact isUnstable evaluations performed by K2 */
+  uint64_t skipped_pixels;  /* cardioid/bulb pixels */
+  uint64_t glitched;        /* pixels flagged for re-queue */
+  uint64_t rebased;         /* rebase events (orbit exhausted, or |z|<|d| in NM_MODE_REBASE) */
+  uint64_t fixups;          /* smoothing values re-evaluated on the host */
+  uint64_t kernel_launches; /* kernels of ours launched for this frame */
+  uint64_t sweeps;          /* K3 passes over the orbit */
+  float ms_k1, ms_k2, ms_k3, ms_k4; /* device time per stage (CUDA events on the ctx stream) */
+} nm_stats;
+NM_API int nm_frame_stats(nm_ctx* ctx, nm_stats* out);
+
+/* One-call forms with HOST buffers = what Mandelbrot::precompute()+computeRow() drive:
+ * upload, launch, host-assist, download. These are the "e2e" calls bench.py times. */
+NM_API int nm_render_hw(nm_ctx* ctx, const double* c_re, int nc, const double* c_im, int nr, int N,
+                 nm_escape* out);
+NM_API int nm_render_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, int nc,
+                   const double* eps_im, int nr, int cardioid_mode, const uint8_t* cardioid_mask,
+                   const int32_t* pix_list, int64_t n_list, int mode, nm_escape* out);
+
+/* ---- K4: colour resolve ---------------------------------------------------------------------
+ * Replaces FractalViewer::getColor/colorLine/recolor (viewer.cpp:84-124): palette lookup, smooth
+ * interpolation, sc x sc RGB-space box average, clip. pal_rgb: 3*n_pal bytes from
+ * MultiWaveGenerator::cache (multiwave.cpp:75-116). Reads the raster of the current frame; writes
+ * (nr/sc) x (nc/sc) x 3 interleaved bytes to rgb_out (h/d pointer). */
+NM_API int nm_resolve(nm_ctx* ctx, const uint8_t* pal_rgb, int n_pal, int N, int sc, int smooth,
+               uint8_t* rgb_out);
+/* Same, on a caller-supplied raster (h/d pointer) instead of the current frame. */
+NM_API int nm_resolve_grid(nm_ctx* ctx, const nm_escape* grid, int nr, int nc, const uint8_t* pal_rgb,
+                    int n_pal, int N, int sc, int smooth, uint8_t* rgb_out);
+
+/* ---- measurement helpers --------------------------------------------------------------------
+ * FP64-pipe peak probe: runs `iters` dependent-chain DFMA (kind 0), DADD (1), DMUL (2) per thread
+ * over a full-chip grid and returns instructions/s. Used by bench.py for the roofline denominator
+ * (MEASURED_PEAKS.json carries no FP64 entry). */
+NM_API int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms);
+NM_API int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes, char* name, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,130 @@
+// newman_b200/mandelbrot.h — source-compatible drop-in for newman's fractal engine headers
+// (reference mandelbrot.h:22-53, grid.h:6-25, complex.h:6-35), backed by the B200 CUDA path.
+//
+// A caller written against the reference (viewer.cpp:76, 157-184, 186-253, 441-453) compiles
+// unchanged when this directory precedes the reference's on the include path: same class names,
+// same public fields (`error_tolerance, N, center, sz`), same member functions with the same
+// argument meaning, same value semantics (copyable / movable; GPU state sits behind a shared
+// handle). `grid.h` and `complex.h` in this directory forward here.
+//
+// What differs underneath:
+//   * precompute() does the reference's host-side arbitrary-precision work (probe search, orbit,
+//     series: mandelbrot.cpp:73-131, multi-threaded over probes) AND renders the whole raster on
+//     the GPU through the C-ABI in <newman_b200.h>; computeRow(r) then only validates the frame.
+//   * the per-pixel arbitrary-precision continuation (mandelbrot.cpp:209-224) is replaced by an
+//     FP64 perturbation iteration with glitch detection and secondary reference orbits.
+//   * there is no CPU fallback: without a CUDA device precompute()/computeRow() throw
+//     std::runtime_error.
+#ifndef NEWMAN_B200_MANDELBROT_H
+#define NEWMAN_B200_MANDELBROT_H
+
+#include <gmpxx.h>
+
+#include <memory>
+#include <vector>
+
+// ---- value types (complex.h) ------------------------------------------------------------------
+struct LPComplex {
+  double re, im;
+  constexpr LPComplex() : re(0.0), im(0.0) {}
+  constexpr LPComplex(double r, double i) : re(r), im(i) {}
+};
+struct HPComplex {
+  mpf_class re, im;
+};
+// Operation order is part of the contract (complex.h:19-31): the device kernels issue the same ops.
+constexpr LPComplex operator+(const LPComplex& p, const LPComplex& q) { return LPComplex(p.re + q.re, p.im + q.im); }
+constexpr LPComplex operator*(const LPComplex& p, const LPComplex& q) {
+  return LPComplex(p.re * q.re - p.im * q.im, p.re * q.im + p.im * q.re);
+}
+constexpr LPComplex sq(const LPComplex& p) { return LPComplex(p.re * p.re - p.im * p.im, 2.0 * p.re * p.im); }
+constexpr double sqMag(const LPComplex& p) { return p.re * p.re + p.im * p.im; }
+inline LPComplex descend(const HPComplex& p) { return LPComplex(p.re.get_d(), p.im.get_d()); }  // truncating
+
+// ---- output raster (grid.h) ---------------------------------------------------------------------
+class RenderGrid {
+public:
+  struct EscapeValue {
+    int iterations;
+    float smoothing;
+    EscapeValue(int it = 0, float sm = 0.0f) : iterations(it), smoothing(sm) {}
+  };
+  int nr, nc;
+  std::vector<EscapeValue> values;  // row-major nr x nc, 8 bytes per sample == nm_escape
+
+  RenderGrid() : nr(0), nc(0) {}
+  RenderGrid(int rows, int cols) : nr(rows), nc(cols), values((size_t)rows * cols) {}
+  EscapeValue& at(int r, int c) { return values[(size_t)r * nc + c]; }
+  const EscapeValue& at(int r, int c) const { return values[(size_t)r * nc + c]; }
+};
+
+namespace newman_b200 {
+class Engine;  // GPU context + last frame; shared between copies of a Mandelbrot
+struct FrameInfo {
+  bool hardware = false;
+  int precision_bits = 64, orbit_len = 0, probe_row = -1, probe_col = -1;
+  int references = 0;               // reference orbits used (1 + secondary rounds)
+  unsigned long long executed_iters = 0, series_evals = 0, skipped_pixels = 0, glitched = 0, rebased = 0,
+                     fixups = 0, kernel_launches = 0, ambiguous = 0;
+  double host_precompute_s = 0, device_ms = 0, frame_s = 0;
+};
+}  // namespace newman_b200
+
+class Mandelbrot {
+protected:
+  RenderGrid grid;
+  std::shared_ptr<newman_b200::Engine> engine_;
+  struct Signature;  // view parameters the current raster was rendered for
+  std::shared_ptr<Signature> rendered_;
+  newman_b200::FrameInfo info_;
+
+  void setPrecision();  // mandelbrot.cpp:37-56
+  bool frameCurrent() const;
+  void renderFrame();
+
+public:
+  double error_tolerance;
+  int N;
+  HPComplex center, sz;
+
+  // Extensions (defaults reproduce the reference wherever the reference is defined).
+  double glitch_tolerance;  // K3 glitch rule |X_n+d_n|^2 < glitch_tolerance*|X_n|^2
+  int max_secondary;        // secondary reference rounds before the final rebasing pass
+  int device;               // CUDA device ordinal
+  int host_threads;         // probe-search threads (0 = hardware concurrency)
+
+  Mandelbrot();
+  Mandelbrot(int nr, int nc);
+
+  void loadLegacy(const char* fn);  // 5-line view file (viewer.cpp:12-23)
+
+  inline int rows() const { return grid.nr; }
+  inline int cols() const { return grid.nc; }
+
+  bool useHardware();
+  void precompute();
+  void computeRow(int r);
+
+  HPComplex pointAt(int r, int c, int sc = 1) const;
+  void translate(int dr, int dc, int sc = 1);
+  void zoom(float scale);
+  void zoomAt(float scale, int r, int c, int sc = 1);
+
+  const RenderGrid::EscapeValue& at(int r, int c);
+  RenderGrid::EscapeValue at(int r, int c, int sc);  // sc x sc average in iteration space
+
+  void scaleUp(int sc);
+  void scaleDown(int sc);
+
+  void load(const char* fn);  // empty in the reference (mandelbrot.cpp:362-364); here: loadLegacy format
+  void save(const char* fn);
+
+  // Not in the reference: introspection for tests/bench, and the fused colour resolve
+  // (viewer.cpp:84-124) on the raster that is already resident on the GPU.
+  const newman_b200::FrameInfo& frameInfo() const { return info_; }
+  const RenderGrid& raster() const { return grid; }
+  void resolveRGB(const unsigned char* pal_rgb, int n_pal, int sc, bool smooth, unsigned char* rgb_out);
+  void setPrecisionNow() { setPrecision(); }
+};
+
+#endif

@@ -1,0 +1,330 @@
+// See hp_host.h. C++11, GMP C API only (explicit precisions => re-entrant, safe under std::thread).
+#include "hp_host.h"
+
+#include <atomic>
+#include <cmath>
+#include <thread>
+
+#include "../../include/newman_b200.h"
+
+namespace newman_b200 {
+
+namespace {
+
+const double kBailout2 = 1024.0 * 1024.0;  // mandelbrot.cpp:58-59
+
+struct Mp {  // RAII mpf at an explicit precision
+  mpf_t v;
+  explicit Mp(mp_bitcnt_t prec) { mpf_init2(v, prec); }
+  ~Mp() { mpf_clear(v); }
+  Mp(const Mp&) = delete;
+  Mp& operator=(const Mp&) = delete;
+};
+
+// `k * s` as gmpxx evaluates int * mpf: mpf_mul_ui on |k|, then mpf_neg
+inline void mul_int(mpf_ptr out, mpf_srcptr s, long k) {
+  if (k >= 0) mpf_mul_ui(out, s, (unsigned long)k);
+  else { mpf_mul_ui(out, s, 0UL - (unsigned long)k); mpf_neg(out, out); }
+}
+
+// Pixel map (mandelbrot.cpp:86-87, 271, 275): re = center.re + (c - cols/2)*sz.re,
+// im = center.im + (rows/2 - r - 1)*sz.im. `tmp` and `out` at the working precision.
+inline void pixel_re(const ViewHP& v, int c, mpf_ptr tmp, mpf_ptr out) {
+  mul_int(tmp, v.sz_re, (long)(c - v.nc / 2));
+  mpf_add(out, v.center_re, tmp);
+}
+inline void pixel_im(const ViewHP& v, int r, mpf_ptr tmp, mpf_ptr out) {
+  mul_int(tmp, v.sz_im, (long)(v.nr / 2 - r - 1));
+  mpf_add(out, v.center_im, tmp);
+}
+
+// One reference-orbit step with the reference's expression order (mandelbrot.cpp:102-103):
+//   re' = re*re - im*im + x0.re ;  im' = 2.0*(re*im) + x0.im     (2.0 enters as a 64-bit mpf)
+struct OrbitStep {
+  Mp t1, t2, t3, two;
+  explicit OrbitStep(mp_bitcnt_t prec) : t1(prec), t2(prec), t3(prec), two(64) { mpf_set_d(two.v, 2.0); }
+  void operator()(mpf_ptr nre, mpf_ptr nim, mpf_srcptr re, mpf_srcptr im, mpf_srcptr x0re, mpf_srcptr x0im) {
+    mpf_mul(t1.v, re, re);
+    mpf_mul(t2.v, im, im);
+    mpf_sub(t3.v, t1.v, t2.v);
+    mpf_mul(t1.v, re, im);  // before nre is written: nre may alias re
+    mpf_add(nre, t3.v, x0re);
+    mpf_mul(t2.v, two.v, t1.v);
+    mpf_add(nim, t2.v, x0im);
+  }
+};
+
+inline bool bailed(mpf_srcptr re, mpf_srcptr im) {  // bailedOut, mandelbrot.cpp:61
+  double r = mpf_get_d(re), i = mpf_get_d(im);
+  return r * r + i * i > kBailout2;
+}
+
+// X.size() of computeOrbit (mandelbrot.cpp:97-110) without storing the orbit.
+int orbit_length(const ViewHP& v, mpf_srcptr x0re, mpf_srcptr x0im) {
+  Mp re(v.prec), im(v.prec), nre(v.prec), nim(v.prec);
+  OrbitStep step(v.prec);
+  mpf_set(re.v, x0re);
+  mpf_set(im.v, x0im);
+  for (int i = 1; i < v.N; i++) {
+    step(nre.v, nim.v, re.v, im.v, x0re, x0im);
+    if (bailed(nre.v, nim.v)) return i;
+    mpf_swap(re.v, nre.v);
+    mpf_swap(im.v, nim.v);
+  }
+  return v.N;
+}
+
+int pick_threads(int threads) {
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  if (threads < 1) threads = 1;
+  if (threads > 256) threads = 256;
+  return threads;
+}
+
+// inCardioid (mandelbrot.cpp:63-71) on an mpf point; optionally returns the two margins as doubles.
+bool in_cardioid(mp_bitcnt_t prec, mpf_srcptr zre, mpf_srcptr zim, double* margin1, double* margin2) {
+  Mp fourth(prec), xmf(prec), y2(prec), q(prec), t(prec), lhs(prec), rhs(prec), one(64);
+  mpf_set_d(fourth.v, 0.25);
+  mpf_set_d(one.v, 1.0);
+  mpf_sub(xmf.v, zre, fourth.v);
+  mpf_mul(y2.v, zim, zim);
+  mpf_mul(t.v, xmf.v, xmf.v);
+  mpf_add(q.v, t.v, y2.v);
+  mpf_add(t.v, q.v, xmf.v);
+  mpf_mul(lhs.v, q.v, t.v);
+  mpf_mul(rhs.v, fourth.v, y2.v);
+  bool in1 = mpf_cmp(lhs.v, rhs.v) < 0;
+  if (margin1) { mpf_sub(t.v, lhs.v, rhs.v); *margin1 = mpf_get_d(t.v); }
+  if (in1 && !margin2) return true;
+  mpf_add(q.v, zre, one.v);
+  mpf_mul(t.v, q.v, q.v);
+  mpf_add(lhs.v, t.v, y2.v);
+  mpf_mul(rhs.v, fourth.v, fourth.v);
+  bool in2 = mpf_cmp(lhs.v, rhs.v) < 0;
+  if (margin2) { mpf_sub(t.v, lhs.v, rhs.v); *margin2 = mpf_get_d(t.v); }
+  return in1 || in2;
+}
+
+}  // namespace
+
+int precision_bits_for(mpf_srcptr sz_re) {
+  const double log_alpha = log2(1.0e-20);
+  const int beta = 64;
+  signed long int e;
+  mpf_get_d_2exp(&e, sz_re);
+  int bits = (int)(beta - e + log_alpha);
+  if (bits < 64) bits = 64;
+  return bits;
+}
+
+void pixel_coords(const ViewHP& v, std::vector<double>& c_re, std::vector<double>& c_im) {
+  Mp tmp(v.prec), p(v.prec);
+  c_re.resize(v.nc);
+  c_im.resize(v.nr);
+  for (int c = 0; c < v.nc; c++) { pixel_re(v, c, tmp.v, p.v); c_re[c] = mpf_get_d(p.v); }
+  for (int r = 0; r < v.nr; r++) { pixel_im(v, r, tmp.v, p.v); c_im[r] = mpf_get_d(p.v); }
+}
+
+bool in_cardioid_pixel(const ViewHP& v, int r, int c) {
+  Mp tmp(v.prec), re(v.prec), im(v.prec);
+  pixel_re(v, c, tmp.v, re.v);
+  pixel_im(v, r, tmp.v, im.v);
+  return in_cardioid(v.prec, re.v, im.v, nullptr, nullptr);
+}
+
+int classify_cardioid(const ViewHP& v, int threads, std::vector<uint8_t>& mask) {
+  // The two margins are polynomials in (x, y) with |grad| < 200 wherever they are small, so if both
+  // exceed 200 * (view extent) at the centre sample every sample of the view decides like it.
+  Mp tmp(v.prec), re(v.prec), im(v.prec);
+  pixel_re(v, v.nc / 2, tmp.v, re.v);
+  pixel_im(v, v.nr / 2, tmp.v, im.v);
+  double m1 = 0, m2 = 0;
+  bool inside = in_cardioid(v.prec, re.v, im.v, &m1, &m2);
+  double extent = fabs(mpf_get_d(v.sz_re)) * v.nc + fabs(mpf_get_d(v.sz_im)) * v.nr;
+  if (fabs(m1) > 200.0 * extent && fabs(m2) > 200.0 * extent) return inside ? NM_CARDIOID_ALL : NM_CARDIOID_NONE;
+
+  mask.assign((size_t)v.nr * v.nc, 0);
+  threads = pick_threads(threads);
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    Mp t(v.prec), pre(v.prec), pim(v.prec);
+    for (;;) {
+      int r = next.fetch_add(1);
+      if (r >= v.nr) break;
+      pixel_im(v, r, t.v, pim.v);
+      for (int c = 0; c < v.nc; c++) {
+        pixel_re(v, c, t.v, pre.v);
+        mask[(size_t)r * v.nc + c] = in_cardioid(v.prec, pre.v, pim.v, nullptr, nullptr) ? 1 : 0;
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int i = 1; i < threads; i++) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  return NM_CARDIOID_MASK;
+}
+
+void find_probe(const ViewHP& v, int threads, int& row, int& col, int& length) {
+  // candidate order of mandelbrot.cpp:77-83
+  std::vector<std::pair<int, int>> cand;
+  for (int c = 0; c < v.nc; c += 2) {
+    cand.emplace_back(v.nr / 4, c);
+    cand.emplace_back(v.nr / 2, c);
+    cand.emplace_back(3 * v.nr / 4, c);
+  }
+  for (int r = 0; r < v.nr; r += 2) cand.emplace_back(r, v.nc / 2);
+  const int n = (int)cand.size();
+  std::vector<int> len(n, -1);
+  // A probe that never escapes (length N) cannot be beaten by a later one (strict '>' at :90), so
+  // candidates after the first such probe need not be evaluated.
+  std::atomic<int> next(0), first_full(n);
+  threads = pick_threads(threads);
+  if (threads > n) threads = n;
+  auto work = [&]() {
+    Mp tmp(v.prec), pre(v.prec), pim(v.prec);
+    for (;;) {
+      int i = next.fetch_add(1);
+      if (i >= n) break;
+      if (i > first_full.load()) continue;
+      pixel_re(v, cand[i].second, tmp.v, pre.v);
+      pixel_im(v, cand[i].first, tmp.v, pim.v);
+      int L = orbit_length(v, pre.v, pim.v);
+      len[i] = L;
+      if (L >= v.N) {
+        int cur = first_full.load();
+        while (i < cur && !first_full.compare_exchange_weak(cur, i)) {}
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int i = 1; i < threads; i++) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  int best = 0;
+  for (int i = 1; i < n; i++)
+    if (len[i] > len[best]) best = i;  // first longest wins
+  row = cand[best].first;
+  col = cand[best].second;
+  length = len[best];
+}
+
+void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out) {
+  const mp_bitcnt_t P = v.prec;
+  out.probe_row = row;
+  out.probe_col = col;
+  Mp tmp(P), x0re(P), x0im(P);
+  pixel_re(v, col, tmp.v, x0re.v);
+  pixel_im(v, row, tmp.v, x0im.v);
+
+  // ---- computeOrbit (mandelbrot.cpp:97-110), keeping the escaped iterate the reference drops ----
+  struct Pair { mpf_t re, im; };
+  std::vector<Pair> X;
+  X.reserve(1024);
+  auto push = [&](mpf_srcptr re, mpf_srcptr im) {
+    X.emplace_back();
+    mpf_init2(X.back().re, P); mpf_init2(X.back().im, P);
+    mpf_set(X.back().re, re); mpf_set(X.back().im, im);
+  };
+  push(x0re.v, x0im.v);
+  {
+    OrbitStep step(P);
+    Mp nre(P), nim(P);
+    out.has_escape = false;
+    for (int i = 1; i < v.N; i++) {
+      step(nre.v, nim.v, X[i - 1].re, X[i - 1].im, x0re.v, x0im.v);
+      push(nre.v, nim.v);
+      if (bailed(nre.v, nim.v)) { out.has_escape = true; break; }
+    }
+  }
+  const int M = (int)X.size() - (out.has_escape ? 1 : 0);
+  out.M = M;
+
+  // ---- descend X: hi = trunc(X), lo = trunc(X - hi) -----------------------------------------------
+  out.x_hi.resize(2 * (size_t)X.size());
+  out.x_lo.resize(2 * (size_t)M);
+  {
+    Mp d64(64), rem(P);
+    for (size_t i = 0; i < X.size(); i++) {
+      double hr = mpf_get_d(X[i].re), hi = mpf_get_d(X[i].im);
+      out.x_hi[2 * i] = hr;
+      out.x_hi[2 * i + 1] = hi;
+      if ((int)i < M) {
+        mpf_set_d(d64.v, hr); mpf_sub(rem.v, X[i].re, d64.v); out.x_lo[2 * i] = mpf_get_d(rem.v);
+        mpf_set_d(d64.v, hi); mpf_sub(rem.v, X[i].im, d64.v); out.x_lo[2 * i + 1] = mpf_get_d(rem.v);
+      }
+    }
+  }
+
+  // ---- computeSeries (mandelbrot.cpp:112-131), descending as we go --------------------------------
+  // Note the reference's recurrences use the NEW A[i] in B[i] and the new A[i], B[i] in C[i].
+  out.a.resize(2 * (size_t)M); out.b.resize(2 * (size_t)M); out.c.resize(2 * (size_t)M);
+  {
+    Mp ar(P), ai(P), br(P), bi(P), cr(P), ci(P), nar(P), nai(P), nbr(P), nbi(P), ncr(P), nci(P);
+    Mp p1(P), p2(P), s(P), u(P), two(64), one(64);
+    mpf_set_d(two.v, 2.0);
+    mpf_set_d(one.v, 1.0);
+    mpf_set_d(ar.v, 1.0);  // A[0] = 1, B[0] = C[0] = 0
+    auto store = [&](int i) {
+      out.a[2 * i] = mpf_get_d(ar.v); out.a[2 * i + 1] = mpf_get_d(ai.v);
+      out.b[2 * i] = mpf_get_d(br.v); out.b[2 * i + 1] = mpf_get_d(bi.v);
+      out.c[2 * i] = mpf_get_d(cr.v); out.c[2 * i + 1] = mpf_get_d(ci.v);
+    };
+    store(0);
+    for (int i = 1; i < M; i++) {
+      mpf_srcptr xr = X[i - 1].re, xi = X[i - 1].im;
+      // A[i].re = 2.0 * (xr*ar - xi*ai) + 1.0
+      mpf_mul(p1.v, xr, ar.v); mpf_mul(p2.v, xi, ai.v); mpf_sub(s.v, p1.v, p2.v);
+      mpf_mul(u.v, two.v, s.v); mpf_add(nar.v, u.v, one.v);
+      // A[i].im = 2.0 * (xr*ai + xi*ar)
+      mpf_mul(p1.v, xr, ai.v); mpf_mul(p2.v, xi, ar.v); mpf_add(s.v, p1.v, p2.v);
+      mpf_mul(nai.v, two.v, s.v);
+      // B[i].re = 2.0 * (xr*br - xi*bi) + A.re*A.re - A.im*A.im        (new A)
+      mpf_mul(p1.v, xr, br.v); mpf_mul(p2.v, xi, bi.v); mpf_sub(s.v, p1.v, p2.v);
+      mpf_mul(u.v, two.v, s.v);
+      mpf_mul(p1.v, nar.v, nar.v); mpf_add(s.v, u.v, p1.v);
+      mpf_mul(p2.v, nai.v, nai.v); mpf_sub(nbr.v, s.v, p2.v);
+      // B[i].im = 2.0 * (xr*bi + xi*br + A.re*A.im)
+      mpf_mul(p1.v, xr, bi.v); mpf_mul(p2.v, xi, br.v); mpf_add(s.v, p1.v, p2.v);
+      mpf_mul(p1.v, nar.v, nai.v); mpf_add(u.v, s.v, p1.v);
+      mpf_mul(nbi.v, two.v, u.v);
+      // C[i].re = 2.0 * (xr*cr - xi*ci + A.re*B.re - A.im*B.im)         (new A, new B)
+      mpf_mul(p1.v, xr, cr.v); mpf_mul(p2.v, xi, ci.v); mpf_sub(s.v, p1.v, p2.v);
+      mpf_mul(p1.v, nar.v, nbr.v); mpf_add(u.v, s.v, p1.v);
+      mpf_mul(p2.v, nai.v, nbi.v); mpf_sub(s.v, u.v, p2.v);
+      mpf_mul(ncr.v, two.v, s.v);
+      // C[i].im = 2.0 * (xr*ci + xi*cr + A.re*B.im + A.im*B.re)
+      mpf_mul(p1.v, xr, ci.v); mpf_mul(p2.v, xi, cr.v); mpf_add(s.v, p1.v, p2.v);
+      mpf_mul(p1.v, nar.v, nbi.v); mpf_add(u.v, s.v, p1.v);
+      mpf_mul(p2.v, nai.v, nbr.v); mpf_add(s.v, u.v, p2.v);
+      mpf_mul(nci.v, two.v, s.v);
+      mpf_swap(ar.v, nar.v); mpf_swap(ai.v, nai.v);
+      mpf_swap(br.v, nbr.v); mpf_swap(bi.v, nbi.v);
+      mpf_swap(cr.v, ncr.v); mpf_swap(ci.v, nci.v);
+      store(i);
+    }
+  }
+  out.finite = true;
+  for (size_t i = 0; i < out.a.size() && out.finite; i++)
+    if (!std::isfinite(out.a[i]) || !std::isfinite(out.b[i]) || !std::isfinite(out.c[i])) out.finite = false;
+
+  // ---- eps arrays: trunc((pixel - X[0])) per column / per row (mandelbrot.cpp:155-159) ------------
+  out.eps_re.resize(v.nc);
+  out.eps_im.resize(v.nr);
+  {
+    Mp p(P), y(P);
+    for (int c = 0; c < v.nc; c++) {
+      pixel_re(v, c, tmp.v, p.v);
+      mpf_sub(y.v, p.v, X[0].re);
+      out.eps_re[c] = mpf_get_d(y.v);
+    }
+    for (int r = 0; r < v.nr; r++) {
+      pixel_im(v, r, tmp.v, p.v);
+      mpf_sub(y.v, p.v, X[0].im);
+      out.eps_im[r] = mpf_get_d(y.v);
+    }
+  }
+  for (auto& x : X) { mpf_clear(x.re); mpf_clear(x.im); }
+}
+
+}  // namespace newman_b200

@@ -1,0 +1,683 @@
+// Device layer of libnewman_b200.so: context, HBM residency of the per-frame tables, kernel
+// orchestration and the C-ABI declared in include/newman_b200.h.
+//
+// HBM layout per frame (all grow-only allocations owned by the ctx):
+//   raster   out[nr*nc]            8 B/sample  {int32 iterations, float32 smoothing}  (grid.h:8-16)
+//   K1       c_re[nc], c_im[nr]    separable pixel coordinates (doubles)
+//   K2/K3    Z[Jmax+1]   16 B      Z[0]=0, Z[j]=X[j-1] (+ the escaped iterate X[M] when known)
+//            gb[Jmax+1]   8 B      glitch bound glitch_tol*|Z[j]|^2,  ghi[] = its high word (4 B)
+//            Xlo[M]      16 B      low parts of X (phase-2 truncated add)
+//            A,B,C[M]    16 B each descended series coefficients
+//            eps_re[nc], eps_im[nr]
+//            init_d[W] 16 B, init_j[W] 4 B, fresh_ids[W] 4 B     K2 -> K3 hand-over, chunk-sorted
+//            q[2][W], rq[2][W]   32 B PixState      level ping-pong queues, rebase queues
+//            rq_pix[W], rq_iter[W]                   glitch re-queue list
+// No CPU fallback exists: without a device every entry returns NM_ENODEV.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "k1_escape.cuh"
+#include "k2_series.cuh"
+#include "k3_perturb.cuh"
+#include "k4_resolve.cuh"
+
+using namespace nm;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct nm_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own = nullptr, stream = nullptr, side = nullptr;
+  std::string err;
+
+  int kind = 0;  // 0 none, 1 hw, 2 deep
+  int nr = 0, nc = 0, N = 0;
+  long long pixels = 0, W = 0;
+  bool have_list = false;
+  bool launched = false, finished = false;
+
+  DevBuf out, cre, cim, ctr, ambig, fix, fixapply;
+  unsigned long long ambig_cap = 0, fix_cap = 0;
+  // deep
+  DevBuf Z, ghi, gb, xlo, a, b, c, mask, list, init_d, init_j, hist, offs, cursor, fresh, q[2], rq[2], qctr,
+      rq_pix, rq_iter, pal, rgb, gridtmp;
+  int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
+  double tol = 0, gtol = 0;
+
+  nm_stats stats;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  unsigned long long* h_ctr = nullptr;  // pinned mirror of the counters
+  unsigned long long* h_flag = nullptr; // pinned cancel flag source
+  double log_bailout = 0;
+  int occ_k1 = 0, occ_k3[2] = {0, 0};
+};
+
+namespace {
+
+int fail(nm_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define NM_CUDA(ctx, call)                                                                     \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(ctx, e__ == cudaErrorMemoryAllocation ? NM_ENOMEM : NM_ECUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e__));                                                    \
+  } while (0)
+
+__global__ void k_glitch_bounds(const double2* Z, double* gb, int32_t* ghi, int n, int pad_n, double gtol,
+                                int zero_last) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= pad_n) return;
+  double v = 0.0;
+  if (j > 0 && j < n && !(zero_last && j == n - 1)) {
+    double2 z = Z[j];
+    v = (z.x * z.x + z.y * z.y) * gtol;
+  }
+  gb[j] = v;
+  ghi[j] = __double2hiint(v);
+}
+
+__global__ void k_apply_fixups(nm_escape* out, const int32_t* pix, const float* val, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[pix[i]].smoothing = val[i];
+}
+
+__global__ void k_poke(nm_escape* out, long long pix, nm_escape v) { out[pix] = v; }
+
+int set_device(nm_ctx* ctx) {
+  NM_CUDA(ctx, cudaSetDevice(ctx->device));
+  return NM_OK;
+}
+
+int reset_frame_counters(nm_ctx* ctx) {
+  NM_CUDA(ctx, cudaMemsetAsync(ctx->ctr.p, 0, CTR_COUNT * sizeof(unsigned long long), ctx->stream));
+  return NM_OK;
+}
+
+int size_lists(nm_ctx* ctx) {
+  ctx->ambig_cap = (unsigned long long)ctx->W;
+  ctx->fix_cap = (unsigned long long)(ctx->W / 16 + 65536);
+  NM_CUDA(ctx, ctx->ambig.ensure(ctx->ambig_cap * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->fix.ensure(ctx->fix_cap * sizeof(FixupRec)));
+  return NM_OK;
+}
+
+// Host re-evaluation of the smoothing values the device could not round safely
+// (reference mandelbrot.cpp:133-136, same expression, host libm).
+float host_smoothing(double r2) {
+  const double bailout = 1024.0;
+  return (float)(1.0 - log2(0.5 * log(r2) / log(bailout)));
+}
+
+int finish_frame(nm_ctx* ctx) {
+  if (!ctx->launched) return fail(ctx, NM_ESTATE, "no frame launched");
+  if (ctx->finished) return NM_OK;
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, CTR_COUNT * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long nfix = ctx->h_ctr[CTR_FIXUP];
+  if (nfix > ctx->fix_cap) return fail(ctx, NM_ESTATE, "smoothing fix-up list overflow (%llu > %llu)", nfix, ctx->fix_cap);
+  if (ctx->h_ctr[CTR_AMBIG] > ctx->ambig_cap) return fail(ctx, NM_ESTATE, "ambiguous list overflow");
+  if (nfix) {
+    std::vector<FixupRec> recs(nfix);
+    NM_CUDA(ctx, cudaMemcpyAsync(recs.data(), ctx->fix.p, nfix * sizeof(FixupRec), cudaMemcpyDeviceToHost, ctx->stream));
+    NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int32_t> pix(nfix);
+    std::vector<float> val(nfix);
+    for (size_t i = 0; i < nfix; i++) { pix[i] = recs[i].pix; val[i] = host_smoothing(recs[i].r2); }
+    NM_CUDA(ctx, ctx->fixapply.ensure(nfix * 8));
+    int32_t* dpix = ctx->fixapply.as<int32_t>();
+    float* dval = (float*)(dpix + nfix);
+    NM_CUDA(ctx, cudaMemcpyAsync(dpix, pix.data(), nfix * 4, cudaMemcpyHostToDevice, ctx->stream));
+    NM_CUDA(ctx, cudaMemcpyAsync(dval, val.data(), nfix * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_apply_fixups<<<(unsigned)((nfix + 255) / 256), 256, 0, ctx->stream>>>(ctx->out.as<nm_escape>(), dpix, dval, (int)nfix);
+    ctx->stats.kernel_launches++;
+    NM_CUDA(ctx, cudaGetLastError());
+    NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->stats.pixels = (uint64_t)ctx->W;
+  ctx->stats.executed_iters = ctx->h_ctr[CTR_EXECUTED];
+  ctx->stats.series_evals = ctx->h_ctr[CTR_SERIES];
+  ctx->stats.skipped_pixels = ctx->h_ctr[CTR_SKIPPED];
+  ctx->stats.glitched = ctx->h_ctr[CTR_REQUEUE];
+  ctx->stats.rebased = ctx->h_ctr[CTR_REBASED];
+  ctx->stats.fixups = nfix;
+  float ms = 0;
+  if (ctx->kind == 1) {
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2]);
+    ctx->stats.ms_k1 = ms;
+  } else {
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_k2 = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_k3 = ms;
+  }
+  ctx->finished = true;
+  if (ctx->h_ctr[CTR_CANCEL]) return fail(ctx, NM_ECANCELLED, "frame cancelled");
+  return NM_OK;
+}
+
+int launch_hw(nm_ctx* ctx) {
+  K1Params p;
+  p.c_re = ctx->cre.as<double>();
+  p.c_im = ctx->cim.as<double>();
+  p.nr = ctx->nr; p.nc = ctx->nc; p.N = ctx->N;
+  p.out = ctx->out.as<nm_escape>();
+  p.ctr = ctx->ctr.as<unsigned long long>();
+  p.ambig = ctx->ambig.as<int32_t>();
+  p.ambig_cap = ctx->ambig_cap;
+  p.fix = ctx->fix.as<FixupRec>();
+  p.fix_cap = ctx->fix_cap;
+  p.log_bailout = ctx->log_bailout;
+  long long warps_needed = (ctx->pixels + 31) / 32;
+  long long blocks = (warps_needed + (K1_THREADS / 32) - 1) / (K1_THREADS / 32);
+  long long maxb = (long long)ctx->sm_count * ctx->occ_k1;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  k1_escape<<<(unsigned)blocks, K1_THREADS, 0, ctx->stream>>>(p);
+  ctx->stats.kernel_launches++;
+  NM_CUDA(ctx, cudaGetLastError());
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  return NM_OK;
+}
+
+template <int MODE>
+cudaError_t launch_level(nm_ctx* ctx, const K3Params& p, unsigned blocks, size_t smem) {
+  k3_level<MODE><<<blocks, K3_THREADS, smem, ctx->stream>>>(p);
+  return cudaGetLastError();
+}
+
+int launch_deep(nm_ctx* ctx) {
+  const int CH = ctx->CH;
+  const int K = ctx->K;
+  unsigned long long* qctr = ctx->qctr.as<unsigned long long>();
+  // qctr layout: qcount[K+2] | head[K+2] | rcount[2]
+  unsigned long long* qcount = qctr;
+  unsigned long long* head = qctr + (K + 2);
+  unsigned long long* rcount = qctr + 2 * (K + 2);
+
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (K + 2) * sizeof(unsigned), ctx->stream));
+
+  K2Params k2;
+  k2.A = ctx->a.as<double2>(); k2.B = ctx->b.as<double2>(); k2.C = ctx->c.as<double2>();
+  k2.Z = ctx->Z.as<double2>(); k2.Xlo = ctx->xlo.as<double2>();
+  k2.M = ctx->M; k2.N = ctx->N; k2.tol = ctx->tol;
+  k2.eps_re = ctx->cre.as<double>(); k2.eps_im = ctx->cim.as<double>(); k2.nc = ctx->nc;
+  k2.pix_list = ctx->have_list ? ctx->list.as<int32_t>() : nullptr;
+  k2.W = ctx->W;
+  k2.cardioid_mode = ctx->cardioid_mode;
+  k2.mask = ctx->mask.as<uint8_t>();
+  k2.init_d = ctx->init_d.as<double2>(); k2.init_j = ctx->init_j.as<int32_t>();
+  k2.hist = ctx->hist.as<unsigned>(); k2.CH = CH;
+  k2.out = ctx->out.as<nm_escape>();
+  k2.ctr = ctx->ctr.as<unsigned long long>();
+  k2.fix = ctx->fix.as<FixupRec>(); k2.fix_cap = ctx->fix_cap;
+  k2.log_bailout = ctx->log_bailout;
+  long long b2 = (ctx->W + K2_THREADS - 1) / K2_THREADS;
+  long long maxb2 = (long long)ctx->sm_count * 8;
+  if (b2 > maxb2) b2 = maxb2;
+  if (b2 < 1) b2 = 1;
+  k2_series<<<(unsigned)b2, K2_THREADS, 0, ctx->stream>>>(k2);
+  NM_CUDA(ctx, cudaGetLastError());
+  k2_scan<<<1, 32, 0, ctx->stream>>>(ctx->hist.as<unsigned>(), ctx->offs.as<unsigned>(), ctx->cursor.as<unsigned>(), K + 1);
+  NM_CUDA(ctx, cudaGetLastError());
+  k2_scatter<<<(unsigned)b2, 256, 0, ctx->stream>>>(ctx->init_j.as<int32_t>(), ctx->W, CH, ctx->cursor.as<unsigned>(),
+                                                    ctx->fresh.as<int32_t>());
+  NM_CUDA(ctx, cudaGetLastError());
+  ctx->stats.kernel_launches += 3;
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+
+  K3Params p;
+  p.Z = ctx->Z.as<double2>(); p.ghi = ctx->ghi.as<int32_t>(); p.gb = ctx->gb.as<double>();
+  p.Jmax = ctx->Jmax; p.N = ctx->N; p.CH = CH;
+  p.eps_re = ctx->cre.as<double>(); p.eps_im = ctx->cim.as<double>(); p.nc = ctx->nc;
+  p.init_d = ctx->init_d.as<double2>(); p.init_j = ctx->init_j.as<int32_t>();
+  p.pix_list = k2.pix_list;
+  p.fresh_ids = ctx->fresh.as<int32_t>();
+  p.out = ctx->out.as<nm_escape>();
+  p.ctr = ctx->ctr.as<unsigned long long>();
+  p.fix = ctx->fix.as<FixupRec>(); p.fix_cap = ctx->fix_cap;
+  p.rq_pix = ctx->rq_pix.as<int32_t>(); p.rq_iter = ctx->rq_iter.as<int32_t>();
+  p.log_bailout = ctx->log_bailout;
+
+  const size_t smem = (size_t)(CH + 4) * (sizeof(double2) + sizeof(int32_t));
+  const int occ = ctx->occ_k3[ctx->mode == NM_MODE_REBASE ? 1 : 0];
+  const unsigned blocks = (unsigned)(ctx->sm_count * occ);
+
+  for (int sweep = 0;; ++sweep) {
+    const int par = sweep & 1;
+    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 2 * (K + 2) * sizeof(unsigned long long), ctx->stream));
+    NM_CUDA(ctx, cudaMemsetAsync(&rcount[par ^ 1], 0, sizeof(unsigned long long), ctx->stream));
+    for (int k = 0; k < K; ++k) {
+      p.k = k;
+      if (k == 0) {
+        p.cur = ctx->rq[par].as<PixState>();
+        p.cur_count = sweep == 0 ? nullptr : &rcount[par];
+      } else {
+        p.cur = ctx->q[k & 1].as<PixState>();
+        p.cur_count = &qcount[k];
+      }
+      p.next = ctx->q[(k + 1) & 1].as<PixState>();
+      p.next_count = &qcount[k + 1];
+      p.restart = ctx->rq[par ^ 1].as<PixState>();
+      p.restart_count = &rcount[par ^ 1];
+      p.head = &head[k];
+      p.fresh_off = sweep == 0 ? ctx->offs.as<unsigned>() : nullptr;
+      cudaError_t e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE>(ctx, p, blocks, smem)
+                                                  : launch_level<NM_MODE_REQUEUE>(ctx, p, blocks, smem);
+      if (e != cudaSuccess) return fail(ctx, NM_ECUDA, "k3_level launch: %s", cudaGetErrorString(e));
+      ctx->stats.kernel_launches++;
+    }
+    ctx->stats.sweeps++;
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, &rcount[par ^ 1], sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr + 1, &ctx->ctr.as<unsigned long long>()[CTR_CANCEL], sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctr[0] == 0 || ctx->h_ctr[1] != 0) break;
+  }
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  return NM_OK;
+}
+
+int run_resolve(nm_ctx* ctx, const nm_escape* dgrid, int nr, int nc, const uint8_t* pal_rgb, int n_pal, int N, int sc,
+                int smooth, uint8_t* rgb_out) {
+  if (sc < 1 || nr % sc || nc % sc || n_pal < 1 || !pal_rgb || !rgb_out) return fail(ctx, NM_EINVAL, "nm_resolve: bad arguments");
+  NM_CUDA(ctx, ctx->pal.ensure((size_t)3 * n_pal));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->pal.p, pal_rgb, (size_t)3 * n_pal, cudaMemcpyDefault, ctx->stream));
+  size_t obytes = (size_t)(nr / sc) * (nc / sc) * 3;
+  NM_CUDA(ctx, ctx->rgb.ensure(obytes));
+  K4Params p;
+  p.grid = dgrid; p.nr = nr; p.nc = nc; p.pal = ctx->pal.as<uint8_t>();
+  p.n_pal = n_pal; p.N = N; p.sc = sc; p.smooth = smooth; p.rgb = ctx->rgb.as<uint8_t>();
+  long long total = (long long)(nr / sc) * (nc / sc);
+  long long blocks = (total + 255) / 256;
+  long long maxb = (long long)ctx->sm_count * 16;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  k4_resolve<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
+  NM_CUDA(ctx, cudaGetLastError());
+  cudaEvent_t evend = ctx->ev[1];
+  if (ctx->kind != 0) {  // ev[1] belongs to the frame; use a scratch event
+    NM_CUDA(ctx, cudaEventCreate(&evend));
+  }
+  NM_CUDA(ctx, cudaEventRecord(evend, ctx->stream));
+  ctx->stats.kernel_launches++;
+  NM_CUDA(ctx, cudaMemcpyAsync(rgb_out, ctx->rgb.p, obytes, cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[3], evend);
+  ctx->stats.ms_k4 = ms;
+  if (evend != ctx->ev[1]) cudaEventDestroy(evend);
+  return NM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* nm_version(void) { return "newman_b200 0.1 (sm_100a)"; }
+
+const char* nm_last_error(const nm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int nm_create(int device, nm_ctx** out) {
+  if (!out) return NM_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, NM_ENODEV, "no CUDA device (%s); newman_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, NM_EINVAL, "device %d out of range (0..%d)", device, ndev - 1);
+  nm_ctx* ctx = new nm_ctx();
+  ctx->device = device;
+#define NM_CREATE_CUDA(call)                                                       \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      int rc = fail(nullptr, NM_ECUDA, "%s: %s", #call, cudaGetErrorString(e__));  \
+      delete ctx;                                                                  \
+      return rc;                                                                   \
+    }                                                                              \
+  } while (0)
+  NM_CREATE_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  NM_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    int rc = fail(nullptr, NM_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    delete ctx;
+    return rc;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  NM_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking));
+  NM_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  ctx->stream = ctx->own;
+  for (int i = 0; i < 4; i++) NM_CREATE_CUDA(cudaEventCreate(&ctx->ev[i]));
+  NM_CREATE_CUDA(ctx->ctr.ensure(CTR_COUNT * sizeof(unsigned long long)));
+  NM_CREATE_CUDA(cudaMemset(ctx->ctr.p, 0, CTR_COUNT * sizeof(unsigned long long)));
+  NM_CREATE_CUDA(cudaMallocHost((void**)&ctx->h_ctr, CTR_COUNT * sizeof(unsigned long long)));
+  NM_CREATE_CUDA(cudaMallocHost((void**)&ctx->h_flag, sizeof(unsigned long long)));
+  *ctx->h_flag = 1ULL;
+  ctx->log_bailout = log(1024.0);
+  const size_t smem = (size_t)(ctx->CH + 4) * (sizeof(double2) + sizeof(int32_t));
+  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_level<NM_MODE_REQUEUE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_level<NM_MODE_REBASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k1, k1_escape, K1_THREADS, 0));
+  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3[0], k3_level<NM_MODE_REQUEUE>, K3_THREADS, smem));
+  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3[1], k3_level<NM_MODE_REBASE>, K3_THREADS, smem));
+#undef NM_CREATE_CUDA
+  if (ctx->occ_k1 < 1) ctx->occ_k1 = 1;
+  if (ctx->occ_k3[0] < 1) ctx->occ_k3[0] = 1;
+  if (ctx->occ_k3[1] < 1) ctx->occ_k3[1] = 1;
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  *out = ctx;
+  return NM_OK;
+}
+
+void nm_destroy(nm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->own);
+  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi,
+                    &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->init_d, &ctx->init_j,
+                    &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+  if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  if (ctx->own) cudaStreamDestroy(ctx->own);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  delete ctx;
+}
+
+int nm_set_stream(nm_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return NM_EINVAL;
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
+  return NM_OK;
+}
+
+int nm_sync(nm_ctx* ctx) {
+  if (!ctx) return NM_EINVAL;
+  if (set_device(ctx)) return NM_ECUDA;
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_cancel(nm_ctx* ctx) {
+  if (!ctx) return NM_EINVAL;
+  // side stream: must not queue behind the frame it is cancelling
+  NM_CUDA(ctx, cudaMemcpyAsync(&ctx->ctr.as<unsigned long long>()[CTR_CANCEL], ctx->h_flag, sizeof(unsigned long long),
+                               cudaMemcpyHostToDevice, ctx->side));
+  return NM_OK;
+}
+
+int nm_frame_hw(nm_ctx* ctx, const double* c_re, int nc, const double* c_im, int nr, int N) {
+  if (!ctx) return NM_EINVAL;
+  if (!c_re || !c_im || nr < 1 || nc < 1 || N < 0 || (long long)nr * nc > 0x7fffffffLL)
+    return fail(ctx, NM_EINVAL, "nm_frame_hw: bad arguments");
+  if (int rc = set_device(ctx)) return rc;
+  ctx->kind = 1; ctx->nr = nr; ctx->nc = nc; ctx->N = N;
+  ctx->pixels = (long long)nr * nc; ctx->W = ctx->pixels; ctx->have_list = false;
+  ctx->launched = ctx->finished = false;
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  NM_CUDA(ctx, ctx->out.ensure((size_t)ctx->pixels * sizeof(nm_escape)));
+  NM_CUDA(ctx, ctx->cre.ensure((size_t)nc * sizeof(double)));
+  NM_CUDA(ctx, ctx->cim.ensure((size_t)nr * sizeof(double)));
+  if (int rc = size_lists(ctx)) return rc;
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->cre.p, c_re, (size_t)nc * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->cim.p, c_im, (size_t)nr * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  return NM_OK;
+}
+
+int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, int nc, const double* eps_im, int nr,
+                  int cardioid_mode, const uint8_t* cardioid_mask, const int32_t* pix_list, int64_t n_list, int mode) {
+  if (!ctx) return NM_EINVAL;
+  if (!t || !eps_re || !eps_im || nr < 1 || nc < 1 || (long long)nr * nc > 0x7fffffffLL)
+    return fail(ctx, NM_EINVAL, "nm_frame_deep: bad arguments");
+  if (t->M < 1 || t->N < t->M || !t->x_hi || !t->x_lo || !t->a || !t->b || !t->c)
+    return fail(ctx, NM_EINVAL, "nm_frame_deep: bad tables (M=%d N=%d)", t->M, t->N);
+  if (!t->has_escape && t->M != t->N)
+    return fail(ctx, NM_EINVAL, "nm_frame_deep: orbit shorter than N needs its escaped iterate (has_escape)");
+  if (cardioid_mode == NM_CARDIOID_MASK && !cardioid_mask) return fail(ctx, NM_EINVAL, "cardioid mask missing");
+  if (mode != NM_MODE_REQUEUE && mode != NM_MODE_REBASE) return fail(ctx, NM_EINVAL, "bad mode");
+  if (pix_list && (ctx->kind != 2 || ctx->nr != nr || ctx->nc != nc))
+    return fail(ctx, NM_ESTATE, "a pixel-list frame needs a previous full deep frame of the same size");
+  if (int rc = set_device(ctx)) return rc;
+
+  ctx->kind = 2; ctx->nr = nr; ctx->nc = nc; ctx->N = t->N;
+  ctx->pixels = (long long)nr * nc;
+  ctx->have_list = pix_list != nullptr;
+  ctx->W = pix_list ? (long long)n_list : ctx->pixels;
+  ctx->launched = ctx->finished = false;
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  ctx->M = t->M; ctx->has_escape = t->has_escape ? 1 : 0;
+  ctx->Jmax = t->M + ctx->has_escape;
+  ctx->K = (ctx->Jmax + ctx->CH - 1) / ctx->CH;
+  ctx->tol = t->tol; ctx->gtol = t->glitch_tol;
+  ctx->mode = mode; ctx->cardioid_mode = cardioid_mode;
+  const int M = t->M, J1 = ctx->Jmax + 1, K = ctx->K;
+  const size_t Wn = (size_t)(ctx->W > 0 ? ctx->W : 1);
+
+  NM_CUDA(ctx, ctx->out.ensure((size_t)ctx->pixels * sizeof(nm_escape)));
+  NM_CUDA(ctx, ctx->cre.ensure((size_t)nc * sizeof(double)));
+  NM_CUDA(ctx, ctx->cim.ensure((size_t)nr * sizeof(double)));
+  if (int rc = size_lists(ctx)) return rc;
+  NM_CUDA(ctx, ctx->Z.ensure((size_t)(J1 + 8) * sizeof(double2)));
+  NM_CUDA(ctx, ctx->gb.ensure((size_t)(J1 + 8) * sizeof(double)));
+  NM_CUDA(ctx, ctx->ghi.ensure((size_t)(J1 + 8) * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->xlo.ensure((size_t)M * sizeof(double2)));
+  NM_CUDA(ctx, ctx->a.ensure((size_t)M * sizeof(double2)));
+  NM_CUDA(ctx, ctx->b.ensure((size_t)M * sizeof(double2)));
+  NM_CUDA(ctx, ctx->c.ensure((size_t)M * sizeof(double2)));
+  NM_CUDA(ctx, ctx->init_d.ensure(Wn * sizeof(double2)));
+  NM_CUDA(ctx, ctx->init_j.ensure(Wn * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->fresh.ensure(Wn * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->hist.ensure((size_t)(K + 2) * sizeof(unsigned)));
+  NM_CUDA(ctx, ctx->offs.ensure((size_t)(K + 2) * sizeof(unsigned)));
+  NM_CUDA(ctx, ctx->cursor.ensure((size_t)(K + 2) * sizeof(unsigned)));
+  for (int i = 0; i < 2; i++) {
+    NM_CUDA(ctx, ctx->q[i].ensure(Wn * sizeof(PixState)));
+    NM_CUDA(ctx, ctx->rq[i].ensure(Wn * sizeof(PixState)));
+  }
+  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(2 * (K + 2) + 2) * sizeof(unsigned long long)));
+  NM_CUDA(ctx, ctx->rq_pix.ensure(Wn * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->rq_iter.ensure(Wn * sizeof(int32_t)));
+
+  cudaStream_t s = ctx->stream;
+  NM_CUDA(ctx, cudaMemsetAsync(ctx->Z.p, 0, (size_t)(J1 + 8) * sizeof(double2), s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->Z.as<double2>() + 1, t->x_hi, (size_t)(M + ctx->has_escape) * sizeof(double2), cudaMemcpyDefault, s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->xlo.p, t->x_lo, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->a.p, t->a, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->b.p, t->b, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->c.p, t->c, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->cre.p, eps_re, (size_t)nc * sizeof(double), cudaMemcpyDefault, s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->cim.p, eps_im, (size_t)nr * sizeof(double), cudaMemcpyDefault, s));
+  if (cardioid_mode == NM_CARDIOID_MASK) {
+    NM_CUDA(ctx, ctx->mask.ensure((size_t)ctx->pixels));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->mask.p, cardioid_mask, (size_t)ctx->pixels, cudaMemcpyDefault, s));
+  }
+  if (pix_list) {
+    NM_CUDA(ctx, ctx->list.ensure(Wn * sizeof(int32_t)));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->list.p, pix_list, (size_t)ctx->W * sizeof(int32_t), cudaMemcpyDefault, s));
+  }
+  {
+    int pad_n = J1 + 8;
+    k_glitch_bounds<<<(pad_n + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->ghi.as<int32_t>(), J1,
+                                                        pad_n, ctx->gtol, ctx->has_escape);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+  }
+  return NM_OK;
+}
+
+int nm_launch(nm_ctx* ctx) {
+  if (!ctx) return NM_EINVAL;
+  if (ctx->kind == 0) return fail(ctx, NM_ESTATE, "nm_launch: no frame set up");
+  if (int rc = set_device(ctx)) return rc;
+  if (int rc = reset_frame_counters(ctx)) return rc;
+  ctx->finished = false;
+  int rc = ctx->kind == 1 ? launch_hw(ctx) : (ctx->W > 0 ? launch_deep(ctx) : NM_OK);
+  if (rc == NM_OK && ctx->kind == 2 && ctx->W == 0) {
+    cudaEventRecord(ctx->ev[0], ctx->stream); cudaEventRecord(ctx->ev[1], ctx->stream); cudaEventRecord(ctx->ev[2], ctx->stream);
+  }
+  if (rc == NM_OK) ctx->launched = true;
+  return rc;
+}
+
+int64_t nm_frame_ambiguous(nm_ctx* ctx, int32_t* pix, int64_t cap) {
+  if (!ctx) return NM_EINVAL;
+  if (int rc = finish_frame(ctx)) return rc;
+  int64_t n = (int64_t)ctx->h_ctr[CTR_AMBIG];
+  if (pix && n) {
+    int64_t m = n < cap ? n : cap;
+    NM_CUDA(ctx, cudaMemcpy(pix, ctx->ambig.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  return n;
+}
+
+int64_t nm_frame_requeue(nm_ctx* ctx, int32_t* pix, int32_t* at_iter, int64_t cap) {
+  if (!ctx) return NM_EINVAL;
+  if (int rc = finish_frame(ctx)) return rc;
+  int64_t n = (int64_t)ctx->h_ctr[CTR_REQUEUE];
+  int64_t m = n < cap ? n : cap;
+  if (pix && m) NM_CUDA(ctx, cudaMemcpy(pix, ctx->rq_pix.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (at_iter && m) NM_CUDA(ctx, cudaMemcpy(at_iter, ctx->rq_iter.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return n;
+}
+
+int nm_poke(nm_ctx* ctx, int64_t pix, nm_escape v) {
+  if (!ctx) return NM_EINVAL;
+  if (pix < 0 || pix >= ctx->pixels) return fail(ctx, NM_EINVAL, "nm_poke: pixel out of range");
+  k_poke<<<1, 1, 0, ctx->stream>>>(ctx->out.as<nm_escape>(), pix, v);
+  NM_CUDA(ctx, cudaGetLastError());
+  return NM_OK;
+}
+
+int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst) {
+  if (!ctx) return NM_EINVAL;
+  if (r0 < 0 || r1 > ctx->nr || r0 > r1 || !dst) return fail(ctx, NM_EINVAL, "nm_read_rows: bad range");
+  if (int rc = finish_frame(ctx)) return rc;
+  NM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->out.as<nm_escape>() + (size_t)r0 * ctx->nc,
+                               (size_t)(r1 - r0) * ctx->nc * sizeof(nm_escape), cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_frame_stats(nm_ctx* ctx, nm_stats* out) {
+  if (!ctx || !out) return NM_EINVAL;
+  if (ctx->launched) { if (int rc = finish_frame(ctx)) return rc; }
+  *out = ctx->stats;
+  return NM_OK;
+}
+
+int nm_render_hw(nm_ctx* ctx, const double* c_re, int nc, const double* c_im, int nr, int N, nm_escape* out) {
+  if (int rc = nm_frame_hw(ctx, c_re, nc, c_im, nr, N)) return rc;
+  if (int rc = nm_launch(ctx)) return rc;
+  return nm_read_rows(ctx, 0, nr, out);
+}
+
+int nm_render_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, int nc, const double* eps_im, int nr,
+                   int cardioid_mode, const uint8_t* cardioid_mask, const int32_t* pix_list, int64_t n_list, int mode,
+                   nm_escape* out) {
+  if (int rc = nm_frame_deep(ctx, t, eps_re, nc, eps_im, nr, cardioid_mode, cardioid_mask, pix_list, n_list, mode)) return rc;
+  if (int rc = nm_launch(ctx)) return rc;
+  return nm_read_rows(ctx, 0, nr, out);
+}
+
+int nm_resolve(nm_ctx* ctx, const uint8_t* pal_rgb, int n_pal, int N, int sc, int smooth, uint8_t* rgb_out) {
+  if (!ctx) return NM_EINVAL;
+  if (int rc = finish_frame(ctx)) return rc;
+  return run_resolve(ctx, ctx->out.as<nm_escape>(), ctx->nr, ctx->nc, pal_rgb, n_pal, N, sc, smooth, rgb_out);
+}
+
+int nm_resolve_grid(nm_ctx* ctx, const nm_escape* grid, int nr, int nc, const uint8_t* pal_rgb, int n_pal, int N, int sc,
+                    int smooth, uint8_t* rgb_out) {
+  if (!ctx || !grid) return NM_EINVAL;
+  if (int rc = set_device(ctx)) return rc;
+  size_t bytes = (size_t)nr * nc * sizeof(nm_escape);
+  NM_CUDA(ctx, ctx->gridtmp.ensure(bytes));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->gridtmp.p, grid, bytes, cudaMemcpyDefault, ctx->stream));
+  int saved = ctx->kind;
+  ctx->kind = -1;
+  int rc = run_resolve(ctx, ctx->gridtmp.as<nm_escape>(), nr, nc, pal_rgb, n_pal, N, sc, smooth, rgb_out);
+  ctx->kind = saved;
+  return rc;
+}
+
+int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms_out) {
+  if (!ctx || kind < 0 || kind > 2 || iters < 1) return NM_EINVAL;
+  if (int rc = set_device(ctx)) return rc;
+  NM_CUDA(ctx, ctx->fixapply.ensure(64));
+  const unsigned blocks = (unsigned)ctx->sm_count * 8;
+  cudaEvent_t a, b;
+  NM_CUDA(ctx, cudaEventCreate(&a));
+  NM_CUDA(ctx, cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    NM_CUDA(ctx, cudaEventRecord(a, ctx->stream));
+    double* sink = ctx->fixapply.as<double>();
+    if (kind == 0) fp64_peak_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
+    else if (kind == 1) fp64_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
+    else fp64_peak_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
+    NM_CUDA(ctx, cudaGetLastError());
+    NM_CUDA(ctx, cudaEventRecord(b, ctx->stream));
+    NM_CUDA(ctx, cudaEventSynchronize(b));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  double inst = (double)blocks * 256.0 * (double)iters * 8.0;
+  if (inst_per_s) *inst_per_s = inst / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return NM_OK;
+}
+
+int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes, char* name, int cap) {
+  if (!ctx) return NM_EINVAL;
+  cudaDeviceProp prop;
+  NM_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (sm_clock_khz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device); *sm_clock_khz = khz; }
+  if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+  if (name && cap > 0) { strncpy(name, prop.name, cap - 1); name[cap - 1] = 0; }
+  return NM_OK;
+}
+
+}  // extern "C"
