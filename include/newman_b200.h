@@ -160,6 +160,59 @@ NM_API int nm_resolve_grid(nm_ctx* ctx, const nm_escape* grid, int nr, int nc, c
 NM_API int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms);
 NM_API int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes, char* name, int cap);
 
+/* ==== view level: the drop-in class through C ===================================================
+ * `nmv_view` wraps one `class Mandelbrot` (include/newman_b200/mandelbrot.h == reference
+ * mandelbrot.h:22-53), so bindings without a C++ toolchain (ctypes, cgo, JNI ...) drive the same
+ * object the viewer would. Strings are base-10 mpf literals. No C++ exception crosses this ABI:
+ * failures return a negative code and nmv_last_error() has the text. */
+typedef struct nmv_view nmv_view;
+
+typedef struct nmv_frame_info {
+  int32_t hardware, precision_bits, orbit_len, probe_row, probe_col, references;
+  uint64_t executed_iters, series_evals, skipped_pixels, glitched, rebased, fixups, kernel_launches, ambiguous;
+  double host_precompute_s, device_ms, frame_s;
+} nmv_frame_info;
+
+NM_API nmv_view* nmv_create(int nr, int nc);                      /* Mandelbrot(nr, nc), mandelbrot.cpp:8-17 */
+NM_API void nmv_destroy(nmv_view* v);
+NM_API const char* nmv_last_error(const nmv_view* v);
+/* SURVEY.md 8d construction order: N; sz from strings; zoom(1.0f) (-> setPrecision); centre; tolerance.
+ * sz_* / c_* may be NULL to keep the current value. */
+NM_API int nmv_set_view(nmv_view* v, int N, const char* sz_re, const char* sz_im, const char* c_re,
+                        const char* c_im, double tol);
+NM_API int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, int device, int host_threads);
+NM_API int nmv_rows(const nmv_view* v);
+NM_API int nmv_cols(const nmv_view* v);
+NM_API int nmv_use_hardware(nmv_view* v);                          /* mandelbrot.cpp:256-259 */
+NM_API int nmv_precision_bits(const nmv_view* v);                  /* what setPrecision chose, 37-51 */
+NM_API int nmv_precompute(nmv_view* v);                            /* mandelbrot.cpp:261-267 (+ GPU frame) */
+NM_API int nmv_compute_row(nmv_view* v, int r);                    /* mandelbrot.cpp:269-283 */
+NM_API int nmv_render(nmv_view* v, nm_escape* out);                /* precompute + every row, raster copied out */
+NM_API int nmv_read_grid(const nmv_view* v, nm_escape* out);       /* at(r,c) for all r,c: mandelbrot.cpp:318 */
+NM_API int nmv_write_grid(nmv_view* v, const nm_escape* in);
+NM_API int nmv_at_sc(nmv_view* v, int r, int c, int sc, nm_escape* out); /* mandelbrot.cpp:320-332 */
+NM_API int nmv_scale(nmv_view* v, int sc, int up);                 /* scaleUp / scaleDown, 334-360 */
+NM_API int nmv_zoom(nmv_view* v, float scale);                     /* 297-302 */
+NM_API int nmv_translate(nmv_view* v, int dr, int dc, int sc);     /* 292-295 */
+NM_API int nmv_zoom_at(nmv_view* v, float scale, int r, int c, int sc); /* 304-316 */
+NM_API int nmv_load_legacy(nmv_view* v, const char* fn);           /* 19-35 */
+NM_API int nmv_save(nmv_view* v, const char* fn);                  /* viewer.cpp:12-23 format */
+/* which: 0 centre.re, 1 centre.im, 2 sz.re, 3 sz.im; "<mantissa digits>@<exp>" as mpf_get_str */
+NM_API int nmv_view_string(const nmv_view* v, int which, char* buf, int cap);
+NM_API int nmv_frame_info_get(const nmv_view* v, nmv_frame_info* out);
+NM_API int nmv_resolve(nmv_view* v, const uint8_t* pal_rgb, int n_pal, int sc, int smooth, uint8_t* rgb_out);
+
+/* Host-only pieces of precompute() (no GPU needed): used by the CPU test-suite to pin the
+ * arbitrary-precision tables against the compiled reference.
+ * nmv_host_tables: row/col < 0 runs findProbe (mandelbrot.cpp:73-95), else uses that pixel as the
+ * reference point. Returns M (orbit length) or a negative code; the arrays are then read with
+ * nmv_host_table (which: 0 x_hi[2*(M+has_escape)], 1 x_lo[2M], 2 a, 3 b, 4 c, 5 eps_re[nc], 6 eps_im[nr]). */
+NM_API int nmv_host_tables(nmv_view* v, int row, int col, int* has_escape, int* probe_row, int* probe_col);
+NM_API int nmv_host_table(const nmv_view* v, int which, double* out);
+NM_API int nmv_host_coords(nmv_view* v, double* c_re, double* c_im);       /* mandelbrot.cpp:271, 275, 234 */
+NM_API int nmv_host_cardioid(nmv_view* v, uint8_t* mask_or_null);          /* returns NM_CARDIOID_* */
+NM_API int nmv_host_in_cardioid(nmv_view* v, int r, int c);                /* mandelbrot.cpp:63-71 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ bench. Importing it does not load CUDA; creating a Device or View does, and rais
 from ._lib import (CARDIOID_ALL, CARDIOID_MASK, CARDIOID_NONE, ESCAPE_DTYPE, MODE_REBASE, MODE_REQUEUE, NmError,
                    load)
 from .device import Device
+from .view import Mandelbrot
 
-__all__ = ["Device", "NmError", "load", "ESCAPE_DTYPE", "CARDIOID_NONE", "CARDIOID_ALL", "CARDIOID_MASK",
+__all__ = ["Device", "Mandelbrot", "NmError", "load", "ESCAPE_DTYPE", "CARDIOID_NONE", "CARDIOID_ALL", "CARDIOID_MASK",
            "MODE_REQUEUE", "MODE_REBASE"]

@@ -1,0 +1,316 @@
+// Drop-in `class Mandelbrot` (include/newman_b200/mandelbrot.h) over the device C-ABI.
+// Mirrors the reference's public behaviour (reference mandelbrot.cpp) for the view state, precision
+// policy, view transforms and multisample rescale; replaces the per-pixel work with one GPU frame.
+#include "../../include/newman_b200/mandelbrot.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/newman_b200.h"
+#include "hp_host.h"
+
+namespace newman_b200 {
+
+class Engine {
+public:
+  nm_ctx* ctx = nullptr;
+  int device;
+  explicit Engine(int dev) : device(dev) {
+    int rc = nm_create(dev, &ctx);
+    if (rc != NM_OK) throw std::runtime_error(std::string("newman_b200: ") + nm_last_error(nullptr));
+  }
+  ~Engine() { if (ctx) nm_destroy(ctx); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  void check(int rc, const char* what) {
+    if (rc != NM_OK) throw std::runtime_error(std::string("newman_b200: ") + what + ": " + nm_last_error(ctx));
+  }
+};
+
+}  // namespace newman_b200
+
+using newman_b200::DeepTablesHost;
+using newman_b200::ViewHP;
+
+static_assert(sizeof(RenderGrid::EscapeValue) == sizeof(nm_escape), "EscapeValue must be the 8-byte device record");
+
+struct Mandelbrot::Signature {
+  int N, nr, nc, max_secondary;
+  double tol, gtol;
+  mpf_class cre, cim, sre, sim;
+};
+
+namespace {
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+mp_bitcnt_t max_prec(const HPComplex& a, const HPComplex& b) {
+  mp_bitcnt_t p = a.re.get_prec();
+  if (a.im.get_prec() > p) p = a.im.get_prec();
+  if (b.re.get_prec() > p) p = b.re.get_prec();
+  if (b.im.get_prec() > p) p = b.im.get_prec();
+  return p;
+}
+}  // namespace
+
+Mandelbrot::Mandelbrot() : Mandelbrot(1, 1) {}
+
+Mandelbrot::Mandelbrot(int nr, int nc)
+    : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(16), device(0), host_threads(0) {
+  // default full view (mandelbrot.cpp:13-14)
+  center.re = -0.5;
+  center.im = 0.0;
+  sz.re = 4.0 / nc;
+  sz.im = 3.0 / nr;
+  setPrecision();
+}
+
+void Mandelbrot::setPrecision() {
+  const int bits = newman_b200::precision_bits_for(sz.re.get_mpf_t());
+  mpf_set_default_prec(bits);  // global, like the reference (mandelbrot.cpp:47): callers' temporaries follow it
+  center.re.set_prec(bits);
+  center.im.set_prec(bits);
+  sz.re.set_prec(bits);
+  sz.im.set_prec(bits);
+  rendered_.reset();  // the reference clears X/A/B/C here; our equivalent is dropping the frame
+}
+
+void Mandelbrot::loadLegacy(const char* fn) {
+  std::ifstream in(fn);
+  if (!in) return;  // the reference ignores a missing file too (mandelbrot.cpp:20-21)
+  std::string cre, cim, sre, sim;
+  int n = N;
+  in >> n >> cre >> cim >> sre >> sim;
+  if (!in) return;
+  N = n;
+  // parsed at the CURRENT precision of each field (mandelbrot.cpp:24-27), then rescaled from the
+  // 800x600 window the file format assumes (30-31)
+  center.re = cre.c_str();
+  center.im = cim.c_str();
+  sz.re = sre.c_str();
+  sz.im = sim.c_str();
+  sz.re = sz.re * (800.0 / cols());
+  sz.im = sz.im * (600.0 / rows());
+  setPrecision();
+}
+
+void Mandelbrot::load(const char* fn) { loadLegacy(fn); }
+
+void Mandelbrot::save(const char* fn) {
+  // the 5-line text format FractalViewer::save writes (viewer.cpp:12-23): N, centre, sz as they are
+  // (loadLegacy's 800/cols rescale is the identity for the viewer's 800x600 window)
+  FILE* fp = fopen(fn, "w");
+  if (!fp) return;
+  fprintf(fp, "%d\n", N);
+  const mpf_class* fields[4] = {&center.re, &center.im, &sz.re, &sz.im};
+  for (const mpf_class* f : fields) {
+    mpf_out_str(fp, 10, 0, f->get_mpf_t());
+    fprintf(fp, "\n");
+  }
+  fclose(fp);
+}
+
+bool Mandelbrot::useHardware() {
+  const double minpreview = 1.5e-16;  // mandelbrot.cpp:257
+  return sz.re.get_d() >= minpreview && sz.im.get_d() >= minpreview;
+}
+
+bool Mandelbrot::frameCurrent() const {
+  if (!rendered_) return false;
+  const Signature& s = *rendered_;
+  return s.N == N && s.nr == grid.nr && s.nc == grid.nc && s.max_secondary == max_secondary &&
+         s.tol == error_tolerance && s.gtol == glitch_tolerance && s.cre == center.re && s.cim == center.im &&
+         s.sre == sz.re && s.sim == sz.im;
+}
+
+void Mandelbrot::precompute() { renderFrame(); }
+
+void Mandelbrot::computeRow(int r) {
+  (void)r;
+  if (!frameCurrent()) renderFrame();  // rows of a current frame are already in `grid`
+}
+
+void Mandelbrot::renderFrame() {
+  const double t_begin = now_s();
+  if (!engine_ || engine_->device != device) engine_ = std::make_shared<newman_b200::Engine>(device);
+  newman_b200::Engine& eng = *engine_;
+  nm_ctx* ctx = eng.ctx;
+  info_ = newman_b200::FrameInfo();
+
+  ViewHP v;
+  v.center_re = center.re.get_mpf_t(); v.center_im = center.im.get_mpf_t();
+  v.sz_re = sz.re.get_mpf_t(); v.sz_im = sz.im.get_mpf_t();
+  v.nr = grid.nr; v.nc = grid.nc; v.N = N;
+  v.prec = max_prec(center, sz);
+  info_.precision_bits = (int)v.prec;
+  nm_escape* out = reinterpret_cast<nm_escape*>(grid.values.data());
+
+  auto absorb = [&](const nm_stats& st) {
+    info_.executed_iters += st.executed_iters; info_.series_evals += st.series_evals;
+    info_.skipped_pixels += st.skipped_pixels; info_.rebased += st.rebased; info_.fixups += st.fixups;
+    info_.kernel_launches += st.kernel_launches;
+    info_.device_ms += st.ms_k1 + st.ms_k2 + st.ms_k3;
+  };
+
+  if (useHardware()) {
+    info_.hardware = true;
+    std::vector<double> c_re, c_im;
+    newman_b200::pixel_coords(v, c_re, c_im);
+    info_.host_precompute_s = now_s() - t_begin;
+    eng.check(nm_frame_hw(ctx, c_re.data(), v.nc, c_im.data(), v.nr, N), "nm_frame_hw");
+    eng.check(nm_launch(ctx), "nm_launch");
+    int64_t n_amb = nm_frame_ambiguous(ctx, nullptr, 0);
+    if (n_amb < 0) eng.check((int)n_amb, "nm_frame_ambiguous");
+    if (n_amb > 0) {  // the reference's mpf test decides the samples double could not
+      std::vector<int32_t> amb((size_t)n_amb);
+      nm_frame_ambiguous(ctx, amb.data(), n_amb);
+      for (int32_t pix : amb)
+        if (newman_b200::in_cardioid_pixel(v, pix / v.nc, pix % v.nc)) {
+          nm_escape e; e.iterations = N; e.smoothing = 0.0f;
+          eng.check(nm_poke(ctx, pix, e), "nm_poke");
+        }
+      info_.ambiguous = (unsigned long long)n_amb;
+    }
+    eng.check(nm_read_rows(ctx, 0, v.nr, out), "nm_read_rows");
+    nm_stats st; nm_frame_stats(ctx, &st); absorb(st);
+    info_.references = 0;
+  } else {
+    std::vector<uint8_t> mask;
+    int cmode = newman_b200::classify_cardioid(v, host_threads, mask);
+    DeepTablesHost T;
+    if (cmode == NM_CARDIOID_ALL) {
+      // every sample returns (N, 0) at mandelbrot.cpp:149-153: no probe search, a one-entry orbit
+      ViewHP v1 = v;
+      v1.N = 1;
+      newman_b200::build_tables(v1, v.nr / 2, v.nc / 2, T);
+    } else {
+      int prow, pcol, plen;
+      newman_b200::find_probe(v, host_threads, prow, pcol, plen);
+      newman_b200::build_tables(v, prow, pcol, T);
+    }
+    info_.orbit_len = T.M; info_.probe_row = T.probe_row; info_.probe_col = T.probe_col;
+    info_.host_precompute_s = now_s() - t_begin;
+    std::vector<int32_t> rq_pix, rq_iter;
+    int round = 0;
+    for (;;) {
+      if (!T.finite)
+        throw std::runtime_error("newman_b200: series coefficients exceed double range (view beyond the reference's "
+                                 "depth limit, SURVEY.md finding 3)");
+      nm_deep_tables t;
+      t.M = T.M; t.N = N; t.has_escape = T.has_escape ? 1 : 0; t.reserved = 0;
+      t.tol = error_tolerance; t.glitch_tol = glitch_tolerance;
+      t.x_hi = T.x_hi.data(); t.x_lo = T.x_lo.data(); t.a = T.a.data(); t.b = T.b.data(); t.c = T.c.data();
+      const bool last = round >= max_secondary;
+      eng.check(nm_frame_deep(ctx, &t, T.eps_re.data(), v.nc, T.eps_im.data(), v.nr, cmode,
+                              cmode == NM_CARDIOID_MASK ? mask.data() : nullptr, round ? rq_pix.data() : nullptr,
+                              round ? (int64_t)rq_pix.size() : 0, last ? NM_MODE_REBASE : NM_MODE_REQUEUE),
+                "nm_frame_deep");
+      eng.check(nm_launch(ctx), "nm_launch");
+      nm_stats st; eng.check(nm_frame_stats(ctx, &st), "nm_frame_stats"); absorb(st);
+      info_.references++;
+      int64_t n_rq = nm_frame_requeue(ctx, nullptr, nullptr, 0);
+      if (n_rq < 0) eng.check((int)n_rq, "nm_frame_requeue");
+      if (n_rq == 0) break;
+      info_.glitched += (unsigned long long)n_rq;
+      rq_pix.resize((size_t)n_rq); rq_iter.resize((size_t)n_rq);
+      nm_frame_requeue(ctx, rq_pix.data(), rq_iter.data(), n_rq);
+      // next reference: the glitched sample flagged earliest, lowest pixel id on ties
+      size_t best = 0;
+      for (size_t i = 1; i < rq_pix.size(); i++)
+        if (rq_iter[i] < rq_iter[best] || (rq_iter[i] == rq_iter[best] && rq_pix[i] < rq_pix[best])) best = i;
+      const double t_hp = now_s();
+      newman_b200::build_tables(v, rq_pix[best] / v.nc, rq_pix[best] % v.nc, T);
+      info_.host_precompute_s += now_s() - t_hp;
+      cmode = NM_CARDIOID_NONE;  // listed samples already passed the cardioid test
+      round++;
+    }
+    eng.check(nm_read_rows(ctx, 0, v.nr, out), "nm_read_rows");
+  }
+
+  std::shared_ptr<Signature> s = std::make_shared<Signature>();
+  s->N = N; s->nr = grid.nr; s->nc = grid.nc; s->max_secondary = max_secondary;
+  s->tol = error_tolerance; s->gtol = glitch_tolerance;
+  s->cre = mpf_class(center.re, center.re.get_prec()); s->cim = mpf_class(center.im, center.im.get_prec());
+  s->sre = mpf_class(sz.re, sz.re.get_prec()); s->sim = mpf_class(sz.im, sz.im.get_prec());
+  rendered_ = s;
+  info_.frame_s = now_s() - t_begin;
+}
+
+void Mandelbrot::resolveRGB(const unsigned char* pal_rgb, int n_pal, int sc, bool smooth, unsigned char* rgb_out) {
+  if (!engine_ || engine_->device != device) engine_ = std::make_shared<newman_b200::Engine>(device);
+  // the host raster is authoritative (scaleUp/scaleDown and copies edit it), so resolve from it
+  engine_->check(nm_resolve_grid(engine_->ctx, reinterpret_cast<const nm_escape*>(grid.values.data()), grid.nr, grid.nc,
+                                 pal_rgb, n_pal, N, sc, smooth ? 1 : 0, rgb_out),
+                 "nm_resolve_grid");
+}
+
+// ---- view geometry (mandelbrot.cpp:285-316): same mpf expressions, so views stay bit-identical ----
+HPComplex Mandelbrot::pointAt(int r, int c, int sc) const {
+  HPComplex pt;
+  pt.re = center.re + (sc * c - cols() / 2) * sz.re;
+  pt.im = center.im + (rows() / 2 - sc * r - 1) * sz.im;
+  return pt;
+}
+
+void Mandelbrot::translate(int dr, int dc, int sc) {
+  center.re = center.re - dc * sc * sz.re;
+  center.im = center.im + dr * sc * sz.im;
+}
+
+void Mandelbrot::zoom(float scale) {
+  const double inv = 1.0 / scale;
+  sz.re *= inv;
+  sz.im *= inv;
+  setPrecision();
+}
+
+void Mandelbrot::zoomAt(float scale, int r, int c, int sc) {
+  HPComplex anchor = pointAt(r, c, sc);  // the sample under the cursor keeps its coordinate
+  const double inv = 1.0 / scale;
+  sz.re *= inv;
+  sz.im *= inv;
+  center.re = anchor.re - (sc * c - cols() / 2) * sz.re;
+  center.im = anchor.im - (rows() / 2 - sc * r - 1) * sz.im;
+  setPrecision();
+}
+
+// ---- raster access and multisample rescale (mandelbrot.cpp:318-360) ---------------------------------
+const RenderGrid::EscapeValue& Mandelbrot::at(int r, int c) { return grid.at(r, c); }
+
+RenderGrid::EscapeValue Mandelbrot::at(int r, int c, int sc) {
+  float sum = 0.0f;  // float32 accumulator, like the reference
+  for (int r1 = 0; r1 < sc; r1++)
+    for (int c1 = 0; c1 < sc; c1++) {
+      const RenderGrid::EscapeValue& e = grid.at(sc * r + r1, sc * c + c1);
+      sum += e.iterations + e.smoothing;
+    }
+  sum /= sc * sc;
+  RenderGrid::EscapeValue avg;
+  avg.iterations = (int)sum;
+  avg.smoothing = sum - avg.iterations;
+  return avg;
+}
+
+void Mandelbrot::scaleUp(int sc) {
+  RenderGrid big(rows() * sc, cols() * sc);
+  for (int r = 0; r < big.nr; r++)
+    for (int c = 0; c < big.nc; c++) big.at(r, c) = grid.at(r / sc, c / sc);
+  grid = std::move(big);
+  sz.re = sz.re / sc;
+  sz.im = sz.im / sc;
+  setPrecision();
+}
+
+void Mandelbrot::scaleDown(int sc) {
+  RenderGrid small_(rows() / sc, cols() / sc);
+  for (int r = 0; r < small_.nr; r++)
+    for (int c = 0; c < small_.nc; c++) small_.at(r, c) = at(r, c, sc);
+  grid = std::move(small_);
+  sz.re = sz.re * sc;
+  sz.im = sz.im * sc;
+  setPrecision();
+}

@@ -472,7 +472,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     return fail(ctx, NM_EINVAL, "nm_frame_deep: bad arguments");
   if (t->M < 1 || t->N < t->M || !t->x_hi || !t->x_lo || !t->a || !t->b || !t->c)
     return fail(ctx, NM_EINVAL, "nm_frame_deep: bad tables (M=%d N=%d)", t->M, t->N);
-  if (!t->has_escape && t->M != t->N)
+  if (!t->has_escape && t->M != t->N && cardioid_mode != NM_CARDIOID_ALL)
     return fail(ctx, NM_EINVAL, "nm_frame_deep: orbit shorter than N needs its escaped iterate (has_escape)");
   if (cardioid_mode == NM_CARDIOID_MASK && !cardioid_mask) return fail(ctx, NM_EINVAL, "cardioid mask missing");
   if (mode != NM_MODE_REQUEUE && mode != NM_MODE_REBASE) return fail(ctx, NM_EINVAL, "bad mode");

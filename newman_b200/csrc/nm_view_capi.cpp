@@ -1,0 +1,237 @@
+// View-level C-ABI (nmv_*): one `class Mandelbrot` behind an opaque handle, so ctypes / cgo / JNI
+// bindings drive the same drop-in object the reference's viewer would. No exception crosses.
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "../../include/newman_b200.h"
+#include "../../include/newman_b200/mandelbrot.h"
+#include "hp_host.h"
+
+namespace {
+struct Access : public Mandelbrot {  // reach the protected raster for bulk copies
+  Access(int nr, int nc) : Mandelbrot(nr, nc) {}
+  RenderGrid& g() { return grid; }
+  const RenderGrid& g() const { return grid; }
+};
+}  // namespace
+
+struct nmv_view {
+  Access m;
+  std::string err;
+  newman_b200::DeepTablesHost tabs;
+  nmv_view(int nr, int nc) : m(nr, nc) {}
+};
+
+namespace {
+std::string g_err;
+
+newman_b200::ViewHP hp_of(nmv_view* v) {
+  newman_b200::ViewHP h;
+  h.center_re = v->m.center.re.get_mpf_t(); h.center_im = v->m.center.im.get_mpf_t();
+  h.sz_re = v->m.sz.re.get_mpf_t(); h.sz_im = v->m.sz.im.get_mpf_t();
+  h.nr = v->m.rows(); h.nc = v->m.cols(); h.N = v->m.N;
+  mp_bitcnt_t p = v->m.center.re.get_prec();
+  if (v->m.center.im.get_prec() > p) p = v->m.center.im.get_prec();
+  if (v->m.sz.re.get_prec() > p) p = v->m.sz.re.get_prec();
+  if (v->m.sz.im.get_prec() > p) p = v->m.sz.im.get_prec();
+  h.prec = p;
+  return h;
+}
+
+template <typename F>
+int guarded(nmv_view* v, F f) {
+  if (!v) return NM_EINVAL;
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    v->err = e.what();
+    if (v->err.find("no CUDA device") != std::string::npos) return NM_ENODEV;
+    if (v->err.find("exceed double range") != std::string::npos) return NM_ERANGE;
+    return NM_ECUDA;
+  } catch (...) {
+    v->err = "unknown C++ exception";
+    return NM_ECUDA;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+nmv_view* nmv_create(int nr, int nc) {
+  if (nr < 1 || nc < 1) { g_err = "nmv_create: bad size"; return nullptr; }
+  try {
+    return new nmv_view(nr, nc);
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+void nmv_destroy(nmv_view* v) { delete v; }
+
+const char* nmv_last_error(const nmv_view* v) { return v ? v->err.c_str() : g_err.c_str(); }
+
+int nmv_set_view(nmv_view* v, int N, const char* sz_re, const char* sz_im, const char* c_re, const char* c_im,
+                 double tol) {
+  return guarded(v, [&]() {
+    v->m.N = N;
+    if (sz_re && sz_im) {
+      v->m.sz.re = sz_re;
+      v->m.sz.im = sz_im;
+      v->m.zoom(1.0f);
+    }
+    if (c_re && c_im) {
+      v->m.center.re = c_re;
+      v->m.center.im = c_im;
+    }
+    v->m.error_tolerance = tol;
+    return NM_OK;
+  });
+}
+
+int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, int device, int host_threads) {
+  if (!v) return NM_EINVAL;
+  if (glitch_tol >= 0) v->m.glitch_tolerance = glitch_tol;
+  if (max_secondary >= 0) v->m.max_secondary = max_secondary;
+  if (device >= 0) v->m.device = device;
+  if (host_threads >= 0) v->m.host_threads = host_threads;
+  return NM_OK;
+}
+
+int nmv_rows(const nmv_view* v) { return v ? v->m.rows() : NM_EINVAL; }
+int nmv_cols(const nmv_view* v) { return v ? v->m.cols() : NM_EINVAL; }
+int nmv_use_hardware(nmv_view* v) { return v ? (v->m.useHardware() ? 1 : 0) : NM_EINVAL; }
+int nmv_precision_bits(const nmv_view* v) { return v ? (int)v->m.center.re.get_prec() : NM_EINVAL; }
+
+int nmv_precompute(nmv_view* v) { return guarded(v, [&]() { v->m.precompute(); return NM_OK; }); }
+int nmv_compute_row(nmv_view* v, int r) {
+  return guarded(v, [&]() {
+    if (r < 0 || r >= v->m.rows()) { v->err = "row out of range"; return NM_EINVAL; }
+    v->m.computeRow(r);
+    return NM_OK;
+  });
+}
+int nmv_render(nmv_view* v, nm_escape* out) {
+  return guarded(v, [&]() {
+    v->m.precompute();
+    for (int r = 0; r < v->m.rows(); r++) v->m.computeRow(r);
+    if (out) std::memcpy(out, v->m.g().values.data(), v->m.g().values.size() * sizeof(nm_escape));
+    return NM_OK;
+  });
+}
+int nmv_read_grid(const nmv_view* v, nm_escape* out) {
+  if (!v || !out) return NM_EINVAL;
+  std::memcpy(out, v->m.g().values.data(), v->m.g().values.size() * sizeof(nm_escape));
+  return NM_OK;
+}
+int nmv_write_grid(nmv_view* v, const nm_escape* in) {
+  if (!v || !in) return NM_EINVAL;
+  std::memcpy(static_cast<void*>(v->m.g().values.data()), in, v->m.g().values.size() * sizeof(nm_escape));
+  return NM_OK;
+}
+int nmv_at_sc(nmv_view* v, int r, int c, int sc, nm_escape* out) {
+  if (!v || !out || sc < 1 || r < 0 || c < 0 || (r + 1) * sc > v->m.rows() || (c + 1) * sc > v->m.cols()) return NM_EINVAL;
+  RenderGrid::EscapeValue e = v->m.at(r, c, sc);
+  out->iterations = e.iterations;
+  out->smoothing = e.smoothing;
+  return NM_OK;
+}
+int nmv_scale(nmv_view* v, int sc, int up) {
+  return guarded(v, [&]() {
+    if (sc < 1) return NM_EINVAL;
+    if (up) v->m.scaleUp(sc); else v->m.scaleDown(sc);
+    return NM_OK;
+  });
+}
+int nmv_zoom(nmv_view* v, float scale) { return guarded(v, [&]() { v->m.zoom(scale); return NM_OK; }); }
+int nmv_translate(nmv_view* v, int dr, int dc, int sc) { return guarded(v, [&]() { v->m.translate(dr, dc, sc); return NM_OK; }); }
+int nmv_zoom_at(nmv_view* v, float scale, int r, int c, int sc) {
+  return guarded(v, [&]() { v->m.zoomAt(scale, r, c, sc); return NM_OK; });
+}
+int nmv_load_legacy(nmv_view* v, const char* fn) { return guarded(v, [&]() { v->m.loadLegacy(fn); return NM_OK; }); }
+int nmv_save(nmv_view* v, const char* fn) { return guarded(v, [&]() { v->m.save(fn); return NM_OK; }); }
+
+int nmv_view_string(const nmv_view* v, int which, char* buf, int cap) {
+  if (!v || !buf || cap < 2 || which < 0 || which > 3) return NM_EINVAL;
+  const mpf_class& f = which == 0 ? v->m.center.re : which == 1 ? v->m.center.im : which == 2 ? v->m.sz.re : v->m.sz.im;
+  mp_exp_t e;
+  char* s = mpf_get_str(nullptr, &e, 10, 0, f.get_mpf_t());
+  int n = snprintf(buf, cap, "%s@%ld", s, (long)e);
+  free(s);
+  return n;
+}
+
+int nmv_frame_info_get(const nmv_view* v, nmv_frame_info* out) {
+  if (!v || !out) return NM_EINVAL;
+  const newman_b200::FrameInfo& f = v->m.frameInfo();
+  out->hardware = f.hardware; out->precision_bits = f.precision_bits; out->orbit_len = f.orbit_len;
+  out->probe_row = f.probe_row; out->probe_col = f.probe_col; out->references = f.references;
+  out->executed_iters = f.executed_iters; out->series_evals = f.series_evals; out->skipped_pixels = f.skipped_pixels;
+  out->glitched = f.glitched; out->rebased = f.rebased; out->fixups = f.fixups; out->kernel_launches = f.kernel_launches;
+  out->ambiguous = f.ambiguous;
+  out->host_precompute_s = f.host_precompute_s; out->device_ms = f.device_ms; out->frame_s = f.frame_s;
+  return NM_OK;
+}
+
+int nmv_resolve(nmv_view* v, const uint8_t* pal_rgb, int n_pal, int sc, int smooth, uint8_t* rgb_out) {
+  return guarded(v, [&]() { v->m.resolveRGB(pal_rgb, n_pal, sc, smooth != 0, rgb_out); return NM_OK; });
+}
+
+int nmv_host_tables(nmv_view* v, int row, int col, int* has_escape, int* probe_row, int* probe_col) {
+  return guarded(v, [&]() {
+    newman_b200::ViewHP h = hp_of(v);
+    if (row < 0 || col < 0) {
+      int len;
+      newman_b200::find_probe(h, v->m.host_threads, row, col, len);
+    }
+    newman_b200::build_tables(h, row, col, v->tabs);
+    if (has_escape) *has_escape = v->tabs.has_escape ? 1 : 0;
+    if (probe_row) *probe_row = row;
+    if (probe_col) *probe_col = col;
+    return v->tabs.M;
+  });
+}
+
+int nmv_host_table(const nmv_view* v, int which, double* out) {
+  if (!v || !out) return NM_EINVAL;
+  const std::vector<double>* src = nullptr;
+  switch (which) {
+    case 0: src = &v->tabs.x_hi; break;
+    case 1: src = &v->tabs.x_lo; break;
+    case 2: src = &v->tabs.a; break;
+    case 3: src = &v->tabs.b; break;
+    case 4: src = &v->tabs.c; break;
+    case 5: src = &v->tabs.eps_re; break;
+    case 6: src = &v->tabs.eps_im; break;
+    default: return NM_EINVAL;
+  }
+  std::memcpy(out, src->data(), src->size() * sizeof(double));
+  return (int)src->size();
+}
+
+int nmv_host_coords(nmv_view* v, double* c_re, double* c_im) {
+  return guarded(v, [&]() {
+    std::vector<double> a, b;
+    newman_b200::pixel_coords(hp_of(v), a, b);
+    std::memcpy(c_re, a.data(), a.size() * sizeof(double));
+    std::memcpy(c_im, b.data(), b.size() * sizeof(double));
+    return NM_OK;
+  });
+}
+
+int nmv_host_cardioid(nmv_view* v, uint8_t* mask_or_null) {
+  return guarded(v, [&]() {
+    std::vector<uint8_t> mask;
+    int mode = newman_b200::classify_cardioid(hp_of(v), v->m.host_threads, mask);
+    if (mode == NM_CARDIOID_MASK && mask_or_null) std::memcpy(mask_or_null, mask.data(), mask.size());
+    return mode;
+  });
+}
+
+int nmv_host_in_cardioid(nmv_view* v, int r, int c) {
+  return guarded(v, [&]() { return newman_b200::in_cardioid_pixel(hp_of(v), r, c) ? 1 : 0; });
+}
+
+}  // extern "C"

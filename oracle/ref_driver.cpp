@@ -167,6 +167,10 @@ ORACLE_API void ref_read_grid(void* h, void* out) {
   RefView* v = (RefView*)h;
   std::memcpy(out, v->raster().values.data(), v->raster().values.size() * sizeof(RenderGrid::EscapeValue));
 }
+ORACLE_API void ref_write_grid(void* h, const void* in) {
+  RefView* v = (RefView*)h;
+  std::memcpy((void*)&v->raster().values[0], in, v->raster().values.size() * sizeof(RenderGrid::EscapeValue));
+}
 ORACLE_API void ref_zoom(void* h, float s) { ((RefView*)h)->zoom(s); }
 ORACLE_API void ref_translate(void* h, int dr, int dc, int sc) { ((RefView*)h)->translate(dr, dc, sc); }
 ORACLE_API void ref_zoom_at(void* h, float s, int r, int c, int sc) { ((RefView*)h)->zoomAt(s, r, c, sc); }

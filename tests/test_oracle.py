@@ -1,0 +1,163 @@
+"""Pin Oracle-P (oracle/oracle_p.c): against the committed golden fixtures (always) and against the
+compiled reference live (where oracle/_ref exists)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracles
+from oracles import ESC, KATS, RefView, Tables, p_render_deep, p_render_hw, p_resolve
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "kats.json")))
+needs_ref = pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built")
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def load_fixture(name):
+    z = np.load(os.path.join(HERE, "golden", name))
+    t = Tables(z["x_hi"], z["x_lo"], z["a"], z["b"], z["c"], int(z["N"]), float(z["tol"]), float(z["glitch_tol"]))
+    return z, t
+
+
+def test_hw_restatement_vs_golden_fixture():
+    """Plain-double loop restated in C == the reference's raster (iterations and smoothing bits)."""
+    z = np.load(os.path.join(HERE, "golden", "kat_1c.npz"))
+    out, st = p_render_hw(z["c_re"], z["c_im"], 256, np.ascontiguousarray(z["cardioid"]))
+    ref = z["ref"]
+    assert np.array_equal(out["iterations"], ref["iterations"])
+    assert np.array_equal(bits(out["smoothing"]), bits(ref["smoothing"]))
+    assert digest(ref["iterations"]) == GOLD["KAT-1c"]["ref_iterations_sha256"]
+    # long-double cardioid test (no mask) decides the same on this view
+    out2, _ = p_render_hw(z["c_re"], z["c_im"], 256)
+    assert np.array_equal(out2["iterations"], ref["iterations"])
+
+
+@pytest.mark.parametrize("fx,kat", [("kat_d30.npz", "KAT-D30"), ("kat_s.npz", "KAT-S")])
+def test_deep_restatement_vs_golden_fixture(fx, kat):
+    z, t = load_fixture(fx)
+    out, rq_pix, rq_it, st = p_render_deep(t, z["eps_re"], z["eps_im"])
+    assert digest(out["iterations"]) == GOLD[kat]["oraclep_iterations_sha256"]
+    assert digest(out["smoothing"]) == GOLD[kat]["oraclep_smoothing_sha256"]
+    assert st == GOLD[kat]["oraclep_stats"]
+    ref = z["ref"]
+    ok = out["iterations"] >= 0
+    mism = int((out["iterations"][ok] != ref["iterations"][ok]).sum())
+    assert mism == GOLD[kat]["count_mismatch_vs_ref"]
+    if kat == "KAT-D30":
+        assert mism == 0  # short continuation: every non-glitched count equals the reference's
+
+
+@needs_ref
+@pytest.mark.parametrize("kat", ["KAT-1c", "KAT-1b"])
+def test_hw_restatement_vs_reference_live(kat):
+    k = KATS[kat]
+    v = RefView(**k)
+    ref, _ = v.render_all()
+    cre, cim = v.coords()
+    out, st = p_render_hw(cre, cim, k["N"])
+    assert np.array_equal(out["iterations"], ref["iterations"])
+    assert np.array_equal(bits(out["smoothing"]), bits(ref["smoothing"]))
+    assert digest(ref["iterations"]) == GOLD[kat]["ref_iterations_sha256"]
+    assert digest(ref["smoothing"]) == GOLD[kat]["ref_smoothing_sha256"]
+    assert st["executed_iters"] >= GOLD[kat]["executed"]
+
+
+@needs_ref
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D60", "KAT-D90", "KAT-B", "KAT-T3"])
+def test_series_and_phase2_vs_reference_live(kat):
+    """Phases 1-2 are the reference's own double arithmetic: every non-glitched sample must carry the
+    reference's escape count; KAT-B (tol=1e9) resolves 12287/12288 samples in the phase-2 search."""
+    k = KATS[kat]
+    v = RefView(**k)
+    v.precompute()
+    ref, _ = v.render_all()
+    assert digest(ref["iterations"]) == GOLD[kat]["ref_iterations_sha256"]
+    t = v.tables()
+    er, ei = v.eps()
+    out, rq_pix, _, st = p_render_deep(t, er, ei)
+    ok = out["iterations"] >= 0
+    assert ok.sum() >= ok.size - 8
+    assert np.array_equal(out["iterations"][ok], ref["iterations"][ok])
+    sm_bad = int((bits(out["smoothing"])[ok] != bits(ref["smoothing"])[ok]).sum())
+    assert sm_bad <= 2  # the reference truncates an mpf, K3 rounds a double add: <= 1 ulp in |z|^2
+    if kat == "KAT-B":
+        assert st["executed_iters"] <= 1 and sm_bad == 0
+
+
+@needs_ref
+def test_continuation_vs_reference():
+    """Long chaotic continuation (KAT-S, ~2000 iterations past the series): agreement with the
+    reference's 64-bit mpf continuation is statistical (SURVEY.md finding 4); pin the measured level."""
+    k = KATS["KAT-S"]
+    v = RefView(**k)
+    v.precompute()
+    ref, _ = v.render_all()
+    t = v.tables()
+    er, ei = v.eps()
+    out, rq_pix, _, _ = p_render_deep(t, er, ei, mode=1)  # rebasing pass: every sample resolved
+    assert (out["iterations"] >= 0).all()
+    frac = (out["iterations"] == ref["iterations"]).mean()
+    assert frac > 0.95, frac
+
+
+def test_secondary_reference_pick_rule():
+    pix = np.array([50, 7, 9, 70], dtype=np.int32)
+    it = np.array([300, 120, 120, 119], dtype=np.int32)
+    assert oracles.oraclep().oraclep_pick_reference(oracles.vp(pix), oracles.vp(it), 4) == 3
+    it[3] = 500
+    assert oracles.oraclep().oraclep_pick_reference(oracles.vp(pix), oracles.vp(it), 4) == 1
+
+
+def test_trunc_add3_properties():
+    """trunc53(hi+lo+d) against exact rational arithmetic."""
+    from fractions import Fraction
+    import math
+    rng = np.random.default_rng(3)
+    P = oracles.oraclep()
+    for _ in range(2000):
+        hi = float(rng.normal()) * 10.0 ** int(rng.integers(-3, 3))
+        lo = hi * 2.0 ** -53 * float(rng.random())
+        d = float(rng.normal()) * 10.0 ** int(rng.integers(-20, 2))
+        got = P.oraclep_trunc_add3(hi, lo, d)
+        exact = Fraction(hi) + Fraction(lo) + Fraction(d)
+        # truncation toward zero to 53 bits
+        if exact == 0:
+            want = 0.0
+        else:
+            s = -1 if exact < 0 else 1
+            a = abs(exact)
+            e = math.floor(math.log2(a)) if a > 0 else 0
+            while Fraction(2) ** e > a:
+                e -= 1
+            while Fraction(2) ** (e + 1) <= a:
+                e += 1
+            q = Fraction(2) ** (e - 52)
+            want = s * float((a // q) * q)
+        assert got == want, (hi, lo, d, got, want)
+
+
+def test_resolve_restatement_basics():
+    g = np.zeros((4, 4), dtype=ESC)
+    g["iterations"] = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 8, 8, 8], [0, 0, 9, 9]]
+    g["smoothing"] = 0.5
+    pal = (np.arange(30, dtype=np.uint8).reshape(10, 3) * 8).astype(np.uint8)
+    flat = p_resolve(g, pal, N=8, sc=1, smooth=False)
+    assert (flat[2] == 0).all()                       # iterations >= N -> black (viewer.cpp:90)
+    assert (flat[0, 1] == pal[1]).all()
+    sm = p_resolve(g, pal, N=8, sc=1, smooth=True)
+    assert (sm[0, 0] == pal[0]).all()                 # pal[-1] clamps to pal[0]
+    assert (sm[0, 2] == (pal[1].astype(int) + pal[2].astype(int)) // 2).all()
+    ms = p_resolve(g, pal, N=8, sc=2, smooth=False)
+    assert ms.shape == (2, 2, 3)
+    want = (pal[0].astype(np.float32) + pal[1] + pal[4] + pal[5]) / 4.0
+    assert (ms[0, 0] == np.trunc(want).astype(np.uint8)).all()
