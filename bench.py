@@ -1,0 +1,484 @@
+#!/usr/bin/env python
+"""bench.py — newman hot path on B200: pixel-iterations/s (Giter/s) on BASELINE.json configs[1]
+("cfg2": 1920x1080 zoom at 1e-50, N = 65536, series + perturbation at tolerance 1e-10, 2x
+multisampling => 2160 x 3840 grid samples).
+
+  python bench.py [--gpus N --steps K --warmup W]            our CUDA path (one process per GPU)
+  python bench.py --impl reference [...]                      the reference's own CPU code (oracle/_ref)
+
+A "step" = one full frame: series skip (K2) + perturbation (K3) for every sample, including the
+glitch re-queue rounds against secondary reference orbits and the float32 smoothing fix-ups.
+  value : executed pixel-iterations (K3 delta updates) / device time, tables resident in HBM
+  e2e   : same frames through the C-ABI with HOST (pinned) buffers: tables H2D, raster D2H, wall clock
+The host-side arbitrary-precision work (probe search, orbit, series; the reference's own algorithm)
+is done once outside the timed region on both arms and reported as host_precompute_s.
+
+N > 1 (weak scaling): the same view rendered with N x as many grid rows (vertical super-sampling
+x N); rank r renders the interleaved rows r, r+N, ...; tables are computed on rank 0 and broadcast
+(NCCL), the raster bands are gathered to rank 0. No collective sits on the per-pixel data path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K3_INST_PER_ITER = 10   # 7 DFMA + 2 DADD + 1 DMUL (k3_perturb.cuh)
+K3_FLOPS_PER_ITER = 17
+K2_INST_PER_EVAL = 19   # 12 DMUL + 6 DADD + ... (k2_series.cuh phase-1 body incl. the compare)
+METRIC = "executed pixel-iterations/sec"
+UNIT = "Giter/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--scale", type=int, default=1, help="divide the grid by this (debug only; invalid as a bench number)")
+    ap.add_argument("--cpu-sample", type=int, default=1536, help="pixels in the timed CPU-reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def view_for(cfg):
+    import newman_b200
+    return newman_b200.Mandelbrot(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_sample(cfg, probe, n_pix, procs):
+    """Time the reference's own per-pixel code (Oracle-R: /root/reference/mandelbrot.cpp compiled
+    unmodified) on a strided sample of the workload, one process per core (the reference is
+    single-threaded and its GMP precision is process-global). Returns dict for the JSON line."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles
+    if not oracles.have_ref():
+        return None
+    total = cfg["nr"] * cfg["nc"]
+    pix = (np.arange(n_pix, dtype=np.int64) * (total // n_pix) + (total // n_pix) // 3).astype(np.int32)
+    chunks = [pix[i::procs] for i in range(procs)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_ref_worker, [(cfg, probe, c) for c in chunks])
+    wall = time.perf_counter() - t0
+    it = np.zeros(n_pix, dtype=np.int32)
+    Ls = np.zeros(n_pix, dtype=np.int32)
+    sm = np.zeros(n_pix, dtype=np.float32)
+    busy = 0.0
+    setup = 0.0
+    for i, (o, L, secs, pre, _hw) in enumerate(res):
+        it[i::procs] = o["iterations"]; sm[i::procs] = o["smoothing"]; Ls[i::procs] = L
+        busy = max(busy, secs); setup = max(setup, pre)
+    N = cfg["N"]
+    if res[0][4]:   # plain-double path: it+1 loop trips when escaped, N otherwise (cardioid skips not separable here)
+        executed = int(np.where(it < N, it + 1, N).sum(dtype=np.int64))
+    else:           # loop 'for (i = d.size(); i < N; i++)' (mandelbrot.cpp:212): it-L+1 trips if escaped, N-L if not
+        executed = int(np.where(it >= Ls, np.where(it < N, it - Ls + 1, N - Ls), 0).sum(dtype=np.int64))
+    return dict(pix=pix, it=it, sm=sm, L=Ls, executed=executed, effective=int(np.minimum(it, N).sum()), wall=wall,
+                busy=busy, setup=setup, procs=procs)
+
+
+def _ref_worker(a):
+    cfg, probe, pix = a
+    import oracles
+    t0 = time.perf_counter()
+    v = oracles.RefView(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
+    hw = v.use_hardware()
+    L = np.zeros(len(pix), dtype=np.int32)
+    if not hw:
+        v.precompute_at(probe[0], probe[1])  # same reference point findProbe selects (tests pin that)
+        t = v.tables()
+        er, ei = v.eps()
+        ot = t.op()
+        import ctypes as C
+        P = oracles.oraclep()
+        for k, p in enumerate(pix):
+            r, c = divmod(int(p), cfg["nc"])
+            L[k] = P.oraclep_series_L(C.byref(ot), er[c], ei[r], None, None)
+    pre = time.perf_counter() - t0
+    out, secs = v.compute_pixels(pix)
+    return out, L, secs, pre, hw
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation, all host cores, bounded sample/step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from newman_b200 import workloads
+    cfg = workloads.config(args.workload, scale=args.scale, y_mult=1)
+    procs = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles
+    if not oracles.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnewman_ref.so not built (needs /root/reference once)"}))
+        return 0
+    t0 = time.perf_counter()
+    probe = (0, 0)
+    if cfg["sz"] is not None:
+        h = view_for(cfg).host_tables()
+        probe = h["probe"]
+    pre_s = time.perf_counter() - t0
+    n_pix = max(procs, args.cpu_sample // 2)
+    vals, walls = [], []
+    for s in range(args.warmup + args.steps):
+        r = cpu_reference_sample(cfg, probe, n_pix, procs)
+        if s >= args.warmup:
+            vals.append(r["executed"] / r["busy"] / 1e9)
+            walls.append(r["busy"])
+    value = statistics.mean(vals)
+    frac = n_pix / (cfg["nr"] * cfg["nc"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(walls), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "mpf+f64", "data": "synthetic",
+        "config": {"workload": cfg["label"], "grid": [cfg["nr"], cfg["nc"]], "N": cfg["N"], "tol": cfg["tol"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
+                         "sample": f"{n_pix} strided samples of the {cfg['nr']}x{cfg['nc']} raster per step "
+                                   f"({frac:.2e} of a frame), per-pixel getIterations; probe search excluded"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frame_s_extrapolated": statistics.mean(walls) / frac, "host_precompute_s": pre_s, "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import newman_b200
+    from newman_b200 import pipeline, workloads
+    from newman_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    devt = torch.device("cuda", local)
+    dev = newman_b200.Device(local)
+    stream = torch.cuda.Stream(device=devt)
+    dev.set_stream(stream.cuda_stream)
+
+    cfg = workloads.config(args.workload, scale=args.scale, y_mult=world)
+    nr, nc, N = cfg["nr"], cfg["nc"], cfg["N"]
+    hw = cfg["sz"] is None
+    rows = pipeline.local_rows(nr, rank, world)
+    rows_t = torch.as_tensor(rows, device=devt)
+    view = view_for(cfg) if rank == 0 else None
+    host_pre = [0.0]
+
+    def bcast_tables(row, col):
+        """rank 0: host arbitrary-precision work (C++/GMP, threaded) -> device tensors -> NCCL broadcast."""
+        keys = ("x_hi", "x_lo", "a", "b", "c", "eps_re", "eps_im")
+        if rank == 0:
+            t0 = time.perf_counter()
+            h = view.host_tables(row, col)
+            host_pre[0] += time.perf_counter() - t0
+            meta = torch.tensor([h["M"], h["has_escape"], h["probe"][0], h["probe"][1]], dtype=torch.int64, device=devt)
+        else:
+            h = None
+            meta = torch.zeros(4, dtype=torch.int64, device=devt)
+        if world > 1:
+            dist.broadcast(meta, 0)
+        M, he, pr, pc = [int(x) for x in meta.tolist()]
+        sizes = [2 * (M + he), 2 * M, 2 * M, 2 * M, 2 * M, nc, nr]
+        d = {"M": M, "has_escape": he, "probe": (pr, pc)}
+        for k, n in zip(keys, sizes):
+            t = torch.from_numpy(h[k]).to(devt) if rank == 0 else torch.empty(n, dtype=torch.float64, device=devt)
+            if world > 1:
+                dist.broadcast(t, 0)
+            d[k] = t
+        return pipeline.TableSet(d, N, cfg["tol"], 1e-6)
+
+    def reduce_pick(best_iter, best_pix, n_local):
+        big = np.iinfo(np.int64).max
+        key = big if best_iter == big else (best_iter << 40) | best_pix
+        if world > 1:
+            t = torch.tensor([key], dtype=torch.int64, device=devt)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            key = int(t.item())
+        return None if key == big else key & ((1 << 40) - 1)
+
+    eps_cache = {}
+
+    def eps_rows(ts):
+        k = id(ts)
+        if k not in eps_cache:
+            e = ts.arr["eps_im"]
+            eps_cache[k] = (e[rows_t].contiguous() if isinstance(e, torch.Tensor) and e.is_cuda else
+                            e[torch.as_tensor(rows)].contiguous().pin_memory() if isinstance(e, torch.Tensor) else
+                            np.ascontiguousarray(e[rows]))
+        return eps_cache[k]
+
+    stats_total = {}
+
+    def add_stats(res):
+        for st in res["stats"]:
+            for k, v in st.items():
+                stats_total[k] = stats_total.get(k, 0) + v
+
+    # ---- plain-double workload (cfg1) ------------------------------------------------------------
+    if hw:
+        if rank == 0:
+            cre, cim = view.host_coords()
+            coords = [torch.from_numpy(cre).to(devt), torch.from_numpy(cim).to(devt)]
+        else:
+            coords = [torch.empty(nc, dtype=torch.float64, device=devt), torch.empty(nr, dtype=torch.float64, device=devt)]
+        if world > 1:
+            for t in coords:
+                dist.broadcast(t, 0)
+        cim_loc = coords[1][rows_t].contiguous()
+        coords_h = [coords[0].cpu().pin_memory(), cim_loc.cpu().pin_memory()]
+
+        def frame(device_resident=True):
+            c = coords[0] if device_resident else coords_h[0]
+            ci = cim_loc if device_resident else coords_h[1]
+            dev.frame_hw(c, ci, N)
+            dev.launch()
+            amb = dev.ambiguous()
+            for p in amb:  # rare; the mpf verdict needs the host view (rank 0 holds it for world == 1)
+                if view is not None and world == 1 and view.host_in_cardioid(int(p) // nc, int(p) % nc):
+                    dev.poke(int(p), N, 0.0)
+            st = dev.stats()
+            for k, v in st.items():
+                stats_total[k] = stats_total.get(k, 0) + v
+        chain_dev = chain_host = None
+        primary = None
+    else:
+        # ---- deep workload: tables (rank 0 -> broadcast), discover the secondary-reference chain ----
+        primary = bcast_tables(-1, -1)
+        chain_dev = []
+
+        def discover(gp):
+            ts = bcast_tables(gp // nc, gp % nc)
+            chain_dev.append(ts)
+            return ts
+
+        res0 = pipeline.render_rounds(dev, primary, discover, nc, rows, reduce_pick=reduce_pick, eps_rows=eps_rows)
+        refs = res0["refs"]
+        to_host = lambda ts: ts.map(lambda t: t.cpu().pin_memory())
+        primary_h = to_host(primary)
+        chain_host = [to_host(ts) for ts in chain_dev]
+
+        def frame(device_resident=True):
+            chain = chain_dev if device_resident else chain_host
+            it = iter(chain)
+            res = pipeline.render_rounds(dev, primary if device_resident else primary_h, lambda gp: next(it), nc, rows,
+                                         reduce_pick=reduce_pick, eps_rows=eps_rows)
+            assert res["refs"] == refs, "secondary reference chain changed between frames"
+            add_stats(res)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        frame(True)
+
+    # FP64 issue peak measured live on this box (MEASURED_PEAKS.json has no FP64 entry)
+    peak_dfma, _ = dev.fp64_peak(0, 1 << 15)
+    peak_dadd, _ = dev.fp64_peak(1, 1 << 15)
+    dev.sync()
+
+    # ---- timed: device-resident ---------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    stats_total.clear()
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        frame(True)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    st_dev = dict(stats_total)
+
+    # ---- timed: end to end with host buffers --------------------------------------------------------
+    out_dev = torch.empty((len(rows), nc, 2), dtype=torch.int32, device=devt)
+    out_host = torch.empty((nr, nc, 2), dtype=torch.int32).pin_memory() if rank == 0 else None
+    gathered = [torch.empty_like(out_dev) for _ in range(world)] if (rank == 0 and world > 1) else None
+    if world > 1:
+        lens = [len(pipeline.local_rows(nr, r, world)) for r in range(world)]
+        assert len(set(lens)) == 1, "grid rows must divide evenly across ranks"
+
+    def frame_e2e():
+        frame(False)
+        if world == 1:
+            dev.read_rows(0, len(rows), out_host)
+        else:
+            dev.read_rows(0, len(rows), out_dev)
+            dist.gather(out_dev, gathered, dst=0)
+            if rank == 0:
+                for r in range(world):
+                    out_host[r::world].copy_(gathered[r], non_blocking=True)
+        torch.cuda.synchronize()
+
+    frame_e2e()
+    stats_total.clear()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    st_e2e = dict(stats_total)
+
+    # ---- reductions over ranks ------------------------------------------------------------------------
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=devt)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=devt)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = allmax(ms)
+    e2e_s = allmax(e2e_s)
+    executed = allsum(st_dev["executed_iters"])          # over all steps, all ranks
+    executed_e2e = allsum(st_e2e["executed_iters"])
+    evals = allsum(st_dev.get("series_evals", 0))
+    launches = allsum(st_dev["kernel_launches"])
+    k3_ms = allmax(st_dev.get("ms_k3", 0.0) + st_dev.get("ms_k1", 0.0))
+    k2_ms = allmax(st_dev.get("ms_k2", 0.0))
+
+    if rank == 0:
+        grid = np.frombuffer(out_host.numpy().tobytes(), dtype=newman_b200.ESCAPE_DTYPE).reshape(nr, nc)
+        effective = int(np.minimum(np.maximum(grid["iterations"], 0), N).sum(dtype=np.int64))
+        value = executed / (ms * 1e-3) / 1e9
+        e2e_value = executed_e2e / e2e_s / 1e9
+        per_step_tables = 0 if hw else (primary.nbytes() + sum(t.nbytes() for t in chain_dev))
+        h2d = (8 * (nc + len(rows))) * world if hw else per_step_tables * world
+        d2h = nr * nc * 8
+        # roofline of the dominant kernel, FP64 pipe (no tensor cores, not HBM bound)
+        k_inst = executed / world * (K3_INST_PER_ITER if not hw else 8)
+        k_name = "k3_level (FP64 perturbation)" if not hw else "k1_escape (plain double)"
+        k_ms = k3_ms
+        if k2_ms > k3_ms:
+            k_name, k_inst, k_ms = "k2_series (series scan)", evals / world * K2_INST_PER_EVAL, k2_ms
+        achieved = k_inst / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["label"] + (f", rows x{world} (weak scaling)" if world > 1 else ""),
+                       "grid": [nr, nc], "N": N, "tol": cfg["tol"], "glitch_tol": 1e-6,
+                       "parallelism": f"row-interleaved bands x{world}",
+                       "l2": "working set per step (state queues + raster) exceeds L2; tables are meant to be L2/SMEM resident"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock, barrier+synchronize both sides"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64_pipe", "kernel": k_name, "achieved": achieved, "peak": peak_dadd / 1e9,
+                         "unit": "Ginst/s", "frac": achieved / (peak_dadd / 1e9) if peak_dadd else None, "traffic": None,
+                         "peak_source": "measured live: nm_fp64_peak DADD issue rate (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_dfma_ginst": peak_dfma / 1e9,
+                         "fp64_tflops": executed / world * K3_FLOPS_PER_ITER / (k3_ms * 1e-3) / 1e12 if (k3_ms > 0 and not hw) else None,
+                         "fp64_tflops_peak_dfma": 2 * peak_dfma / 1e12,
+                         "kernel_ms_per_step": k_ms / args.steps, "k2_ms_per_step": k2_ms / args.steps,
+                         "k3_ms_per_step": k3_ms / args.steps},
+            "executed_iters_per_step": executed / args.steps, "series_evals_per_step": evals / args.steps,
+            "effective_giter_s": effective / (ms / args.steps * 1e-3) / 1e9,
+            "secondary_references": 0 if hw else len(refs), "glitched_per_step": st_dev.get("glitched", 0) / args.steps,
+            "rebased_per_step": st_dev.get("rebased", 0) / args.steps, "fixups_per_step": st_dev.get("fixups", 0) / args.steps,
+            "host_precompute_s": host_pre[0],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            procs = os.cpu_count() or 1
+            probe = (0, 0) if hw else primary.probe
+            r = cpu_reference_sample(cfg, probe, max(procs, args.cpu_sample), procs)
+            if r is not None:
+                pix = r["pix"]
+                mine = grid.reshape(-1)[pix]
+                eq = float((mine["iterations"] == r["it"]).mean())
+                line["cpu_baseline"] = {
+                    "value": r["executed"] / r["busy"] / 1e9, "unit": UNIT, "cores": r["procs"], "kind": "reference",
+                    "sample": f"{len(pix)} strided samples of the {nr}x{nc} raster ({len(pix) / (nr * nc):.2e} of a frame), "
+                              f"reference getIterations per pixel, {r['busy']:.1f}s busy on the slowest core; probe search excluded",
+                    "frame_s_extrapolated": r["busy"] * (nr * nc) / len(pix),
+                    "parity_on_sample": {"equal_count_frac": eq, "n": int(len(pix))}}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref not built on this box"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -1,0 +1,47 @@
+"""Named views (BASELINE.json `configs`, SURVEY.md §8d parametrisation). A view is fully
+deterministic: there is no RNG anywhere on this path; the "seed" is the centre digit string.
+
+depth D := scale on the default view: sz.re = 4*D/nc_grid, sz.im = 3*D/nr_grid (mandelbrot.cpp:14).
+"""
+from fractions import Fraction
+
+# Seahorse-valley filament between the period-998 (size 6e-16) and period-8007 (size 9e-33)
+# minibrots, followed down to 1e-50 by tools/find_view.py (greedy high-count auto-zoom). At 1e-50:
+# reference orbit M ~ 6.2e4 < N, series skip L ~ 4.7e4, escape counts 5.2e4..6.2e4, no interior
+# samples, series coefficients finite (max |C| ~ 4e180) -> inside the reference's working range.
+CFG2_CENTER = ("-0.74364388703715870430384830821904672021612495145852386428093",
+               "0.13182590420531197076319081924762009190133695173845852602774")
+
+
+def _dec(fr, digits=40):
+    """Fraction -> scientific decimal string (exact to `digits` significant digits)."""
+    if fr == 0:
+        return "0"
+    e = 0
+    f = Fraction(fr)
+    while f >= 10:
+        f /= 10; e += 1
+    while f < 1:
+        f *= 10; e -= 1
+    m = (f.numerator * 10 ** digits) // f.denominator
+    s = str(m)
+    return f"{s[0]}.{s[1:]}e{e}"
+
+
+def config(name, scale=1, y_mult=1):
+    """Return dict(nr, nc, N, sz, center, tol, sc, label).
+    scale: divide both grid dimensions by `scale` keeping the view extent (test-size variants).
+    y_mult: multiply the number of grid rows keeping the extent (weak-scaling workload: N GPUs render
+            a y_mult = N times vertically super-sampled raster, rows interleaved across ranks)."""
+    if name == "cfg1":
+        nr, nc, N, sc = 768 // scale, 1024 // scale, 1024, 1
+        return dict(nr=nr * y_mult, nc=nc, N=N, sz=None if y_mult == 1 else (_dec(Fraction(4, nc)), _dec(Fraction(3, nr * y_mult))),
+                    center=None, tol=1e-10, sc=sc,
+                    label="cfg1: 1024x768 default full view, N=1024, plain double")
+    if name == "cfg2":
+        nr, nc, N, sc = 2160 // scale, 3840 // scale, 65536, 2
+        d = Fraction(1, 10 ** 50)
+        sz = (_dec(4 * d / nc), _dec(3 * d / (nr * y_mult)))
+        return dict(nr=nr * y_mult, nc=nc, N=N, sz=sz, center=CFG2_CENTER, tol=1e-10, sc=sc,
+                    label="cfg2: 1920x1080 zoom at 1e-50, N=65536, series+perturbation tol 1e-10, 2x multisampling")
+    raise KeyError(name)

@@ -26,6 +26,7 @@ struct RefView : public Mandelbrot {
   }
   const RenderGrid& raster() const { return grid; }
   bool cardioid(const HPComplex& p) { return inCardioid(p); }
+  RenderGrid::EscapeValue one(const HPComplex& p) { return useHardware() ? getIterationsHW(p) : getIterations(p); }
   HPComplex pixel(int r, int c) const {
     HPComplex pt;
     pt.im = center.im + (rows() / 2 - r - 1) * sz.im;
@@ -149,6 +150,19 @@ ORACLE_API double ref_compute_rows(void* h, const int* rows, int n, void* out) {
                   &v->raster().values[(size_t)rows[k] * nc], (size_t)nc * sizeof(RenderGrid::EscapeValue));
   }
   return secs;
+}
+// The per-pixel body of computeRow (mandelbrot.cpp:269-283) for an arbitrary list of pixel ids
+// (r*cols+c): same pixel map, same getIterations/getIterationsHW. Lets the timed CPU baseline be a
+// bounded, strided sample of a frame whose full render would take hours.
+ORACLE_API double ref_compute_pixels(void* h, const int* pix, int n, void* out) {
+  RefView* v = (RefView*)h;
+  RenderGrid::EscapeValue* o = (RenderGrid::EscapeValue*)out;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int k = 0; k < n; k++) {
+    int r = pix[k] / v->cols(), c = pix[k] % v->cols();
+    o[k] = v->one(v->pixel(r, c));
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 ORACLE_API double ref_render_all(void* h, void* out) {
   RefView* v = (RefView*)h;

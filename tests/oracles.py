@@ -129,7 +129,7 @@ class RefView:
             L = C.CDLL(REF_SO)
             L.ref_create.restype = C.c_void_p
             L.ref_create.argtypes = [C.c_int, C.c_int]
-            for f in ("ref_precompute", "ref_render_all", "ref_compute_rows"):
+            for f in ("ref_precompute", "ref_render_all", "ref_compute_rows", "ref_compute_pixels"):
                 getattr(L, f).restype = C.c_double
             L.ref_destroy.argtypes = [C.c_void_p]
             L.ref_set_view.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double]
@@ -137,6 +137,7 @@ class RefView:
             L.ref_precompute_at.argtypes = [C.c_void_p, C.c_int, C.c_int]
             L.ref_render_all.argtypes = [C.c_void_p, C.c_void_p]
             L.ref_compute_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.ref_compute_pixels.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
             for f in ("ref_orbit_len", "ref_precision_bits", "ref_use_hardware", "ref_rows", "ref_cols"):
                 getattr(L, f).argtypes = [C.c_void_p]
             L.ref_dump_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -192,6 +193,12 @@ class RefView:
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         out = np.zeros((len(rows), self.nc), dtype=ESC)
         secs = self.lib().ref_compute_rows(self.h, vp(rows), len(rows), vp(out))
+        return out, secs
+
+    def compute_pixels(self, pix):
+        pix = np.ascontiguousarray(pix, dtype=np.int32)
+        out = np.zeros(len(pix), dtype=ESC)
+        secs = self.lib().ref_compute_pixels(self.h, vp(pix), len(pix), vp(out))
         return out, secs
 
     def coords(self):
@@ -256,3 +263,39 @@ KATS = {
     "KAT-S": dict(nr=30, nc=40, N=20000, sz=("1e-18", "1e-18"),
                   center=("-0.743643887037158704752191506114774", "0.131825904205311970493132056385139")),
 }
+
+
+class OracleDevice:
+    """Oracle-P behind the newman_b200.Device frame interface (frame_deep / launch / requeue / stats /
+    read_rows): lets the round orchestration (newman_b200.pipeline.render_rounds) and the multi-rank
+    logic be exercised on CPU, and gives the GPU tests a whole-frame expectation. TEST ONLY."""
+
+    def __init__(self):
+        self.out = None
+
+    def frame_deep(self, tables, eps_re, eps_im, cardioid_mode=0, mask=None, pix_list=None, mode=0):
+        keep = tables._keep
+        arr = keep if isinstance(keep, dict) else dict(zip(("x_hi", "x_lo", "a", "b", "c"), keep))
+        self._t = Tables(np.asarray(arr["x_hi"]), np.asarray(arr["x_lo"]), np.asarray(arr["a"]), np.asarray(arr["b"]),
+                         np.asarray(arr["c"]), tables.N, tables.tol, tables.glitch_tol)
+        self._args = (np.ascontiguousarray(eps_re), np.ascontiguousarray(eps_im), cardioid_mode, mask,
+                      None if pix_list is None else np.ascontiguousarray(pix_list, dtype=np.int32), mode)
+        self.nr, self.nc = len(eps_im), len(eps_re)
+        if pix_list is None or self.out is None:
+            self.out = np.zeros((self.nr, self.nc), dtype=ESC)
+
+    def launch(self):
+        er, ei, cm, mask, pl, mode = self._args
+        _, self._rq_pix, self._rq_it, self._st = p_render_deep(self._t, er, ei, cm, mask, pl, mode, out=self.out)
+
+    def stats(self):
+        d = dict(self._st)
+        d.update(pixels=self.nr * self.nc, fixups=0, kernel_launches=0, sweeps=0, ms_k1=0.0, ms_k2=0.0, ms_k3=0.0, ms_k4=0.0)
+        return d
+
+    def requeue(self):
+        return self._rq_pix, self._rq_it
+
+    def read_rows(self, r0=0, r1=None, out=None):
+        r1 = self.nr if r1 is None else r1
+        return self.out[r0:r1].copy()

@@ -1,0 +1,154 @@
+"""-m gpu: whole frames through the drop-in class (C++ Mandelbrot via the view-level C-ABI):
+primary reference + glitch re-queue rounds + colour resolve, against Oracle-P driving the same
+round logic, the compiled reference where it is defined, and the committed fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+import newman_b200
+import oracles
+from newman_b200 import pipeline, workloads
+from oracles import KATS, OracleDevice, RefView, Tables
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+needs_ref = pytest.mark.skipif(not oracles.have_ref(), reason="oracle/_ref not built")
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def mk(k, **kw):
+    return newman_b200.Mandelbrot(k["nr"], k["nc"], N=k["N"], sz=k.get("sz"), center=k.get("center"),
+                                  tol=k.get("tol", 1e-10), **kw)
+
+
+def oracle_frame(m, N, tol, max_secondary=16):
+    """Oracle-P through the same round orchestration, tables from the host C++ (pinned elsewhere)."""
+    nc = m.cols()
+    mkts = lambda d: pipeline.TableSet(d, N, tol, 1e-6)
+    primary = mkts(m.host_tables())
+    od = OracleDevice()
+    res = pipeline.render_rounds(od, primary, lambda gp: mkts(m.host_tables(gp // nc, gp % nc)), nc,
+                                 np.arange(m.rows()), max_secondary=max_secondary)
+    return od.out, res
+
+
+def test_fixture_kat_1c_through_class():
+    z = np.load(os.path.join(HERE, "golden", "kat_1c.npz"))
+    got = newman_b200.Mandelbrot(48, 64, N=256).render()
+    assert np.array_equal(got["iterations"], z["ref"]["iterations"])
+    assert np.array_equal(bits(got["smoothing"]), bits(z["ref"]["smoothing"]))
+
+
+@pytest.mark.parametrize("fx", ["kat_d30.npz", "kat_s.npz"])
+def test_fixture_deep_device_level(dev, fx):
+    z = np.load(os.path.join(HERE, "golden", fx))
+    tabs = dev.make_tables(z["x_hi"], z["x_lo"], z["a"], z["b"], z["c"], int(z["N"]), float(z["tol"]), float(z["glitch_tol"]))
+    out = dev.render_deep(tabs, z["eps_re"], z["eps_im"])
+    gpix, git = dev.requeue()
+    assert np.array_equal(out["iterations"], z["oraclep"]["iterations"])
+    assert np.array_equal(bits(out["smoothing"]), bits(z["oraclep"]["smoothing"]))
+    assert sorted(gpix.tolist()) == sorted(z["rq_pix"].tolist())
+
+
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D60", "KAT-D90", "KAT-S", "KAT-T3", "KAT-B"])
+def test_class_frame_equals_oracle_rounds(kat):
+    """precompute()+computeRow() of the drop-in == Oracle-P run through the same secondary-reference
+    rounds (bit for bit, every sample resolved)."""
+    k = KATS[kat]
+    m = mk(k)
+    got = m.render()
+    info = m.frame_info()
+    exp, res = oracle_frame(mk(k), k["N"], k.get("tol", 1e-10))
+    assert (got["iterations"] >= 0).all()
+    assert np.array_equal(got["iterations"], exp["iterations"])
+    assert np.array_equal(bits(got["smoothing"]), bits(exp["smoothing"]))
+    assert info["references"] == 1 + len(res["refs"])
+    assert info["executed_iters"] == sum(s["executed_iters"] for s in res["stats"])
+
+
+@needs_ref
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D60", "KAT-D90", "KAT-B", "KAT-T3"])
+def test_class_frame_vs_reference(kat):
+    """Where the reference is defined and its continuation short, the whole frame — including the
+    samples resolved against secondary references — carries the reference's escape counts."""
+    k = KATS[kat]
+    v = RefView(**k)
+    v.precompute()
+    ref, _ = v.render_all()
+    got = mk(k).render()
+    assert np.array_equal(got["iterations"], ref["iterations"])
+    assert (bits(got["smoothing"]) != bits(ref["smoothing"])).sum() <= 8
+
+
+def test_cfg2_small_frame_and_resolve():
+    """The bench view (1e-50, N=65536) on a 54x96 grid: class frame == oracle rounds; K4 == restatement."""
+    cfg = workloads.config("cfg2", scale=40)
+    m = mk(cfg)
+    got = m.render()
+    exp, res = oracle_frame(mk(cfg), cfg["N"], cfg["tol"])
+    assert np.array_equal(got["iterations"], exp["iterations"])
+    assert np.array_equal(bits(got["smoothing"]), bits(exp["smoothing"]))
+    pal = (np.arange(3 * cfg["N"]) * 13 % 256).astype(np.uint8).reshape(-1, 3)
+    for sc in (1, 2, 3):
+        for smooth in (False, True):
+            rgb = m.resolve(pal, sc=sc, smooth=smooth)
+            assert np.array_equal(rgb, oracles.p_resolve(got, pal, cfg["N"], sc, smooth)), (sc, smooth)
+
+
+def test_max_secondary_zero_uses_rebasing_pass():
+    k = KATS["KAT-S"]
+    got = mk(k, max_secondary=0).render()
+    exp, res = oracle_frame(mk(k), k["N"], 1e-10, max_secondary=0)
+    assert (got["iterations"] >= 0).all()
+    assert np.array_equal(got["iterations"], exp["iterations"])
+
+
+def test_cardioid_modes_deep(dev):
+    # interior view: every sample (N, 0) without any iteration
+    m = newman_b200.Mandelbrot(16, 16, N=100, sz=("1e-30", "1e-30"), center=("-0.1", "0.1"))
+    g = m.render()
+    assert (g["iterations"] == 100).all() and (g["smoothing"] == 0).all()
+    assert m.frame_info()["executed_iters"] == 0
+    # view straddling the cusp: masked samples are interior, the rest iterate
+    m = newman_b200.Mandelbrot(8, 8, N=300, sz=("1e-30", "1e-30"), center=("0.25", "0"))
+    g = m.render()
+    mode, mask = m.host_cardioid()
+    assert (g["iterations"][mask == 1] == 300).all()
+
+
+def test_frame_reuse_and_invalidation():
+    m = newman_b200.Mandelbrot(48, 64, N=256)
+    m.precompute()
+    a = m.grid()
+    m.computeRow(3)          # current frame: no re-render
+    n0 = m.frame_info()["kernel_launches"]
+    m.zoom(2.0)              # view changed -> computeRow must render again
+    m.computeRow(0)
+    b = m.grid()
+    assert not np.array_equal(a["iterations"], b["iterations"])
+    assert m.frame_info()["kernel_launches"] >= 1 and n0 >= 1
+
+
+def test_edge_sizes(dev):
+    # 1x1 and ragged sizes (not multiples of the warp) on both paths
+    for nr, nc in ((1, 1), (3, 37), (33, 5)):
+        m = newman_b200.Mandelbrot(nr, nc, N=64)
+        g = m.render()
+        cre, cim = m.host_coords()
+        exp, _ = oracles.p_render_hw(cre, cim, 64)
+        assert np.array_equal(g["iterations"], exp["iterations"])
+    m = newman_b200.Mandelbrot(3, 5, N=500, sz=("1e-25", "1e-25"), center=("0", "1"))
+    g = m.render()
+    exp, _ = oracle_frame(newman_b200.Mandelbrot(3, 5, N=500, sz=("1e-25", "1e-25"), center=("0", "1")), 500, 1e-10)
+    assert np.array_equal(g["iterations"], exp["iterations"])
+    # N = 0 and N = 1
+    for N in (0, 1):
+        m = newman_b200.Mandelbrot(4, 4, N=N)
+        g = m.render()
+        cre, cim = m.host_coords()
+        exp, _ = oracles.p_render_hw(cre, cim, N)
+        assert np.array_equal(g["iterations"], exp["iterations"])
