@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--scale", type=int, default=1, help="divide the grid by this (debug only; invalid as a bench number)")
-    ap.add_argument("--cpu-sample", type=int, default=1536, help="pixels in the timed CPU-reference sample")
+    ap.add_argument("--cpu-sample", type=int, default=6144, help="pixels in the timed CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 

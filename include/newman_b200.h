@@ -56,6 +56,12 @@ NM_API const char* nm_version(void);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream. */
 NM_API int nm_set_stream(nm_ctx* ctx, void* cuda_stream);
 NM_API int nm_sync(nm_ctx* ctx);
+/* Tuning / verification switches (defaults in parentheses):
+ *   NM_OPT_K2_LITERAL (0)  1: K2 scans every series index like the reference (mandelbrot.cpp:165-181)
+ *                          instead of testing only the indices the per-index filter cannot rule out.
+ *                          Both give the same L by construction; the tests run both. */
+#define NM_OPT_K2_LITERAL 1
+NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
 /* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
 NM_API int nm_cancel(nm_ctx* ctx);
 

@@ -17,6 +17,7 @@ ESCAPE_DTYPE = np.dtype([("iterations", "<i4"), ("smoothing", "<f4")])  # grid.h
 NM_OK, NM_EINVAL, NM_ENODEV, NM_ECUDA, NM_ENOMEM, NM_ESTATE, NM_ERANGE, NM_ECANCELLED = 0, -1, -2, -3, -4, -5, -6, -7
 CARDIOID_NONE, CARDIOID_ALL, CARDIOID_MASK = 0, 1, 2
 MODE_REQUEUE, MODE_REBASE = 0, 1
+OPT_K2_LITERAL = 1
 
 
 class NmError(RuntimeError):
@@ -54,6 +55,7 @@ DEVICE_API = {
     "nm_version": (C.c_char_p, []),
     "nm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nm_sync": (C.c_int, [C.c_void_p]),
+    "nm_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "nm_cancel": (C.c_int, [C.c_void_p]),
     "nm_frame_hw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "nm_frame_deep": (C.c_int, [C.c_void_p, C.POINTER(DeepTables), C.c_void_p, C.c_int, C.c_void_p, C.c_int,

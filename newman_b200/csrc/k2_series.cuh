@@ -6,10 +6,33 @@
 //     unstable  <=>  |b|^2 * tol < |c|^2        (isUnstable, mandelbrot.cpp:138-142)
 // with A/B/C descended to double by truncation (166-168), eps from the mpf subtraction (155-159),
 // eps^2 = sq(eps), eps^3 = eps*eps^2 (160-161), all without FMA. Neither the test nor
-// d[i] = (a+b)+c (180) depends on the previous index, so we run the test for i = 1.. until it first
-// fires and then evaluate d[] in closed form only where the reference reads it: at found = L-1 and
-// at the O(log L) probes of the phase-2 binary search (186-200). The ops and their order are the
-// reference's; the build uses -fmad=false.
+// d[i] = (a+b)+c (180) depends on the previous index, so only the FIRST index at which the test
+// fires matters, and d[] is needed only where the reference reads it: at found = L-1 and at the
+// O(log L) probes of the phase-2 binary search (186-200). Every test that is evaluated uses the
+// reference's ops in the reference's order; the build uses -fmad=false.
+//
+// Two ways to find the first firing index (template LITERAL):
+//   LITERAL   the reference's scan: test i = 1, 2, ... (19 FP64 instructions per index per sample —
+//             twice a perturbation iteration; this would make the "skip" the dominant cost)
+//   filtered  a pixel-independent per-index filter says which indices CAN fire for a sample with
+//             log2|eps| = le; only those are tested, in ascending order, with the exact test.
+//             The filter has no false negatives (derivation below), so L is the same integer.
+//
+// Filter. With p = log2|B_i| + 2 le (= log2|b|), q = log2|C_i| + 3 le (= log2|c|), lt = log2 tol:
+//   (1) q <= -545: both components of c are below 2^-539, their squares round to +0, |c|^2 == 0 and
+//       `x < 0` is false for every x >= 0: the test cannot fire.
+//   (2) else if |b|^2*tol is a normal double with room to spare (2p + min(lt,0) >= -990) and nothing
+//       overflows (2p + max(lt,0) <= 1000, 2q <= 1000): every intermediate that matters is normal, so
+//       computed |b|^2*tol and |c|^2 carry relative errors of a few dozen ulp (or |c|^2 < 2^-999 is
+//       far below |b|^2*tol and the test is false). Then "fires" implies
+//       tol*|B_i|^2/|C_i|^2 < |eps|^2 (1 + 1e-14), i.e.   rlog_i := lt/2 + log2|B_i| - log2|C_i| <= le + ETA
+//       with ETA = 1e-6 >> 1e-14: index i is a *candidate*.
+//   (3) otherwise (denormal |b|^2*tol, or overflow) anything can happen in floating point: *unsafe*,
+//       always tested.
+// Samples with |eps| < 2^-333 (eps^3 denormal: beyond the reference's own depth limit) or non-finite
+// le use the literal scan. Prefix minima/maxima of the per-index thresholds make "first index that
+// must be tested" three binary searches; from there the scan walks forward testing only must-test
+// indices. On every known-answer view the first candidate fires (1.00 exact tests per sample).
 //
 // Phase 2 forms X[found] + d[found] in mpf and truncates to double (184-186, 61). We carry X as
 // hi + lo (hi = trunc53(X), lo = trunc53(X - hi)) and form trunc53(hi + lo + d) with error-free
@@ -19,6 +42,17 @@
 #include "nm_common.cuh"
 
 namespace nm {
+
+struct K2Filter {  // per-index thresholds in units of log2|eps| (length M each)
+  double* rlog;    // candidate iff rlog[i] <= le + ETA
+  double* a;       // |c|^2 can be nonzero iff le > a[i]
+  double* b;       // |b|^2*tol may be denormal iff le < b[i]
+  double* ov;      // something may overflow iff le > ov[i]
+  double* pmin_rlog;
+  double* pmin_ov;
+  double* pmin_a;
+  double* pmax_b;
+};
 
 struct K2Params {
   const double2* A;
@@ -44,9 +78,12 @@ struct K2Params {
   FixupRec* fix;
   unsigned long long fix_cap;
   double log_bailout;
+  K2Filter f;
 };
 
 constexpr int K2_THREADS = 256;
+constexpr double K2_ETA = 1e-6;
+constexpr double K2_LE_MIN = -333.0;
 
 struct Cplx { double re, im; };
 
@@ -55,6 +92,15 @@ __device__ __forceinline__ Cplx cmul(double ar, double ai, double br, double bi)
   r.re = ar * br - ai * bi;
   r.im = ar * bi + ai * br;
   return r;
+}
+
+// log2 of the modulus without overflow/underflow of the squares; -inf for 0.
+__device__ __forceinline__ double log2_abs(double x, double y) {
+  double ax = fabs(x), ay = fabs(y);
+  double m = fmax(ax, ay), n = fmin(ax, ay);
+  if (m == 0.0) return -INFINITY;
+  double r = n / m;
+  return log2(m) + 0.5 * log2(1.0 + r * r);
 }
 
 // trunc53(hi + lo + d): see header comment.
@@ -83,128 +129,240 @@ struct SeriesEval {
     r.im = (ta.im + tb.im) + tc.im;
     return r;
   }
+  // the reference's isUnstable at index i (mandelbrot.cpp:166-173, 138-142)
+  __device__ __forceinline__ bool unstable(int i, double tol) const {
+    double2 b = B[i], c = C[i];
+    Cplx tb = cmul(b.x, b.y, e2r, e2i);
+    Cplx tc = cmul(c.x, c.y, e3r, e3i);
+    double bmag = tb.re * tb.re + tb.im * tb.im;
+    double cmag = tc.re * tc.re + tc.im * tc.im;
+    return bmag * tol < cmag;
+  }
 };
 
+// first i in [1, M) with arr[i] <= key (arr non-increasing), else M
+__device__ __forceinline__ int first_le(const double* arr, int M, double key) {
+  int lo = 1, hi = M;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (arr[mid] <= key) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+__device__ __forceinline__ int first_lt(const double* arr, int M, double key) {
+  int lo = 1, hi = M;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (arr[mid] < key) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+// first i in [1, M) with arr[i] > key (arr non-decreasing), else M
+__device__ __forceinline__ int first_gt(const double* arr, int M, double key) {
+  int lo = 1, hi = M;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (arr[mid] > key) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+template <bool LITERAL>
 __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
-  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned long long evals = 0, skipped = 0;
 
-  for (; w < p.W; w += stride) {
-    int pix = p.pix_list ? p.pix_list[w] : (int)w;
-    if (p.cardioid_mode == NM_CARDIOID_ALL || (p.cardioid_mode == NM_CARDIOID_MASK && p.mask[pix])) {
-      p.out[pix].iterations = p.N;
-      p.out[pix].smoothing = 0.0f;
-      p.init_j[w] = -1;
-      skipped++;
-      continue;
-    }
-    int r = pix / p.nc, c = pix - r * p.nc;
-    SeriesEval se;
-    se.A = p.A; se.B = p.B; se.C = p.C;
-    se.er = p.eps_re[c];
-    se.ei = p.eps_im[r];
-    // eps2 = sq(eps): (re*re - im*im, 2.0*re*im); eps3 = eps*eps2
-    se.e2r = se.er * se.er - se.ei * se.ei;
-    se.e2i = (2.0 * se.er) * se.ei;
-    Cplx e3 = cmul(se.er, se.ei, se.e2r, se.e2i);
-    se.e3r = e3.re; se.e3i = e3.im;
+  // warp-uniform trip count: the tail of the loop body is warp-aggregated
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < p.W; base += stride) {
+    const long long w = base + lane;
+    const bool valid = w < p.W;
+    int handoff_L = -1;  // >= 0: this sample continues in K3 from table index L
 
-    // ---- phase 1: first unstable index ---------------------------------------------------------
-    int L = p.M;
-    for (int i = 1; i < p.M; ++i) {
-      double2 b = p.B[i], cc = p.C[i];
-      Cplx tb = cmul(b.x, b.y, se.e2r, se.e2i);
-      Cplx tc = cmul(cc.x, cc.y, se.e3r, se.e3i);
-      double bmag = tb.re * tb.re + tb.im * tb.im;
-      double cmag = tc.re * tc.re + tc.im * tc.im;
-      evals++;
-      if (bmag * p.tol < cmag) {
-        int good = i - 3;
-        if (good < 1) good = 1;
-        L = good;
-        break;
+    if (valid) {
+      int pix = p.pix_list ? p.pix_list[w] : (int)w;
+      if (p.cardioid_mode == NM_CARDIOID_ALL || (p.cardioid_mode == NM_CARDIOID_MASK && p.mask[pix])) {
+        p.out[pix].iterations = p.N;
+        p.out[pix].smoothing = 0.0f;
+        p.init_j[w] = -1;
+        skipped++;
+      } else {
+        int r = pix / p.nc, c = pix - r * p.nc;
+        SeriesEval se;
+        se.A = p.A; se.B = p.B; se.C = p.C;
+        se.er = p.eps_re[c];
+        se.ei = p.eps_im[r];
+        // eps2 = sq(eps): (re*re - im*im, 2.0*re*im); eps3 = eps*eps2
+        se.e2r = se.er * se.er - se.ei * se.ei;
+        se.e2i = (2.0 * se.er) * se.ei;
+        Cplx e3 = cmul(se.er, se.ei, se.e2r, se.e2i);
+        se.e3r = e3.re; se.e3i = e3.im;
+
+        // ---- phase 1: first unstable index --------------------------------------------------------
+        int first = p.M;  // index at which the test first fires (M: never)
+        bool literal = LITERAL;
+        double le = 0.0;
+        if (!LITERAL) {
+          if (se.er == 0.0 && se.ei == 0.0) {
+            literal = false;  // b = c = 0 at every index: `0*tol < 0` never fires
+          } else {
+            le = log2_abs(se.er, se.ei);
+            literal = !(le >= K2_LE_MIN) || !isfinite(le);
+            if (!literal) {
+              int i0 = first_le(p.f.pmin_rlog, p.M, le + K2_ETA);
+              int i1 = first_lt(p.f.pmin_ov, p.M, le);
+              int ia = first_lt(p.f.pmin_a, p.M, le), ib = first_gt(p.f.pmax_b, p.M, le);
+              int i2 = ia > ib ? ia : ib;
+              int i = i0 < i1 ? i0 : i1;
+              if (i2 < i) i = i2;
+              for (; i < p.M; ++i) {
+                bool must = (p.f.rlog[i] <= le + K2_ETA) || (le > p.f.a[i] && le < p.f.b[i]) || (le > p.f.ov[i]);
+                if (must) {
+                  evals++;
+                  if (se.unstable(i, p.tol)) { first = i; break; }
+                }
+              }
+            }
+          }
+        }
+        if (literal) {
+          for (int i = 1; i < p.M; ++i) {
+            evals++;
+            if (se.unstable(i, p.tol)) { first = i; break; }
+          }
+        }
+        int L = p.M;
+        if (first < p.M) {  // d.resize(max(i - 3, 1)), mandelbrot.cpp:173-177
+          L = first - 3;
+          if (L < 1) L = 1;
+        }
+
+        // ---- phase 2: did the series-approximated point already escape? -------------------------
+        int found = L - 1;
+        Cplx d = se.d_at(found);
+        double2 xh = p.Z[found + 1], xl = p.Xlo[found];
+        double yr = trunc_add3(xh.x, xl.x, d.re);
+        double yi = trunc_add3(xh.y, xl.y, d.im);
+        double mag = yr * yr + yi * yi;
+        if (mag > BAILOUT2) {
+          int low = 0, high = L - 1, mid = L / 2;
+          while (low <= high) {
+            Cplx dm = se.d_at(mid);
+            double2 mh = p.Z[mid + 1], ml = p.Xlo[mid];
+            double mr = trunc_add3(mh.x, ml.x, dm.re);
+            double mi = trunc_add3(mh.y, ml.y, dm.im);
+            double mm = mr * mr + mi * mi;
+            if (!(mm > BAILOUT2)) low = mid + 1;
+            else { high = mid - 1; found = mid; }
+            mid = (low + high) / 2;
+          }
+          d = se.d_at(found);
+          xh = p.Z[found + 1]; xl = p.Xlo[found];
+          yr = trunc_add3(xh.x, xl.x, d.re);
+          yi = trunc_add3(xh.y, xl.y, d.im);
+          mag = yr * yr + yi * yi;
+          bool unc;
+          float s = smoothing_f32(mag, p.log_bailout, &unc);
+          p.out[pix].iterations = found;
+          p.out[pix].smoothing = s;
+          if (unc) push_fixup(p.ctr, p.fix, p.fix_cap, pix, mag);
+          p.init_j[w] = -1;
+        } else if (L >= p.N) {  // loop 'for (i = d.size(); i < N; i++)' (212) is empty
+          p.out[pix].iterations = p.N;
+          p.out[pix].smoothing = 0.0f;
+          p.init_j[w] = -1;
+        } else {
+          // ---- hand over to K3: delta paired with Z[L] = X[L-1] ---------------------------------
+          p.init_d[w] = make_double2(d.re, d.im);
+          p.init_j[w] = L;
+          handoff_L = L;
+        }
       }
     }
-
-    // ---- phase 2: did the series-approximated point already escape? ---------------------------
-    int found = L - 1;
-    Cplx d = se.d_at(found);
-    double2 xh = p.Z[found + 1], xl = p.Xlo[found];
-    double yr = trunc_add3(xh.x, xl.x, d.re);
-    double yi = trunc_add3(xh.y, xl.y, d.im);
-    double mag = yr * yr + yi * yi;
-    if (mag > BAILOUT2) {
-      int low = 0, high = L - 1, mid = L / 2;
-      while (low <= high) {
-        Cplx dm = se.d_at(mid);
-        double2 mh = p.Z[mid + 1], ml = p.Xlo[mid];
-        double mr = trunc_add3(mh.x, ml.x, dm.re);
-        double mi = trunc_add3(mh.y, ml.y, dm.im);
-        double mm = mr * mr + mi * mi;
-        if (!(mm > BAILOUT2)) low = mid + 1;
-        else { high = mid - 1; found = mid; }
-        mid = (low + high) / 2;
-      }
-      d = se.d_at(found);
-      xh = p.Z[found + 1]; xl = p.Xlo[found];
-      yr = trunc_add3(xh.x, xl.x, d.re);
-      yi = trunc_add3(xh.y, xl.y, d.im);
-      mag = yr * yr + yi * yi;
-      bool unc;
-      float s = smoothing_f32(mag, p.log_bailout, &unc);
-      p.out[pix].iterations = found;
-      p.out[pix].smoothing = s;
-      if (unc) push_fixup(p.ctr, p.fix, p.fix_cap, pix, mag);
-      p.init_j[w] = -1;
-      continue;
+    // warp-aggregated histogram of the start chunk (neighbouring samples share it almost always)
+    {
+      int bin = handoff_L >= 0 ? handoff_L / p.CH : -1;
+      unsigned peers = __match_any_sync(FULL_MASK, bin);
+      if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&p.hist[bin], (unsigned)__popc(peers));
     }
-
-    // ---- hand over to K3 ------------------------------------------------------------------------
-    if (L >= p.N) {  // loop 'for (i = d.size(); i < N; i++)' (212) is empty
-      p.out[pix].iterations = p.N;
-      p.out[pix].smoothing = 0.0f;
-      p.init_j[w] = -1;
-      continue;
-    }
-    p.init_d[w] = make_double2(d.re, d.im);
-    p.init_j[w] = L;  // state: delta paired with Z[L] = X[L-1]
-    atomicAdd(&p.hist[L / p.CH], 1u);
   }
 
   for (int o = 16; o; o >>= 1) {
     evals += __shfl_xor_sync(FULL_MASK, evals, o);
     skipped += __shfl_xor_sync(FULL_MASK, skipped, o);
   }
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
     if (evals) atomicAdd(&p.ctr[CTR_SERIES], evals);
     if (skipped) atomicAdd(&p.ctr[CTR_SKIPPED], skipped);
   }
 }
 
-// Exclusive scan of the per-chunk histogram (K+1 <= a few thousand entries): one CTA.
+// Per-index filter thresholds + their prefix minima/maxima. One CTA; each thread owns a contiguous
+// segment (pixel-independent, O(M) once per frame).
+__global__ void __launch_bounds__(1024) k2_prepare(const double2* B, const double2* C, int M, double tol, K2Filter f) {
+  __shared__ double s_rlog[1024], s_ov[1024], s_a[1024], s_b[1024];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int seg = (M + nt - 1) / nt;
+  const int i0 = t * seg, i1 = min(M, i0 + seg);
+  const double lt = log2(tol);
+  const double lt_neg = fmin(lt, 0.0), lt_pos = fmax(lt, 0.0);
+  double m_rlog = INFINITY, m_ov = INFINITY, m_a = INFINITY, m_b = -INFINITY;
+  for (int i = i0; i < i1; ++i) {
+    double rlog = INFINITY, a = INFINITY, b = -INFINITY, ov = INFINITY;
+    if (i >= 1) {
+      double2 Bi = B[i], Ci = C[i];
+      double lb = log2_abs(Bi.x, Bi.y), lc = log2_abs(Ci.x, Ci.y);
+      if (lc != -INFINITY) {            // C_i == 0: |c|^2 == 0, the test cannot fire
+        rlog = (lb == -INFINITY) ? -INFINITY : 0.5 * lt + lb - lc;
+        a = (-545.0 - lc) / 3.0;
+        b = (lb == -INFINITY) ? INFINITY : (-990.0 - lt_neg - 2.0 * lb) / 4.0;
+        double c1 = (lb == -INFINITY) ? INFINITY : (1000.0 - lt_pos - 2.0 * lb) / 4.0;
+        double c2 = (1000.0 - 2.0 * lc) / 6.0;
+        ov = fmin(c1, c2);
+      }
+    }
+    f.rlog[i] = rlog; f.a[i] = a; f.b[i] = b; f.ov[i] = ov;
+    m_rlog = fmin(m_rlog, rlog); m_ov = fmin(m_ov, ov); m_a = fmin(m_a, a); m_b = fmax(m_b, b);
+    f.pmin_rlog[i] = m_rlog; f.pmin_ov[i] = m_ov; f.pmin_a[i] = m_a; f.pmax_b[i] = m_b;
+  }
+  s_rlog[t] = m_rlog; s_ov[t] = m_ov; s_a[t] = m_a; s_b[t] = m_b;
+  __syncthreads();
+  double c_rlog = INFINITY, c_ov = INFINITY, c_a = INFINITY, c_b = -INFINITY;
+  for (int s = 0; s < t; ++s) {
+    c_rlog = fmin(c_rlog, s_rlog[s]); c_ov = fmin(c_ov, s_ov[s]); c_a = fmin(c_a, s_a[s]); c_b = fmax(c_b, s_b[s]);
+  }
+  for (int i = i0; i < i1; ++i) {
+    f.pmin_rlog[i] = fmin(f.pmin_rlog[i], c_rlog);
+    f.pmin_ov[i] = fmin(f.pmin_ov[i], c_ov);
+    f.pmin_a[i] = fmin(f.pmin_a[i], c_a);
+    f.pmax_b[i] = fmax(f.pmax_b[i], c_b);
+  }
+}
+
+// Exclusive scan of the per-chunk histogram (K+1 <= a few thousand entries).
 __global__ void k2_scan(const unsigned* hist, unsigned* offs, unsigned* cursor, int K1n) {
-  __shared__ unsigned carry;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
     unsigned acc = 0;
     for (int i = 0; i < K1n; ++i) { offs[i] = acc; cursor[i] = acc; acc += hist[i]; }
     offs[K1n] = acc;
-    carry = acc;
   }
-  __syncthreads();
 }
 
-// Scatter fresh work indices into chunk-sorted order.
+// Scatter fresh work indices into chunk-sorted order (warp-aggregated slot reservation).
 __global__ void __launch_bounds__(256) k2_scatter(const int32_t* init_j, long long W, int CH,
                                                   unsigned* cursor, int32_t* fresh_ids) {
-  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; w < W; w += stride) {
-    int j = init_j[w];
-    if (j >= 0) {
-      unsigned slot = atomicAdd(&cursor[j / CH], 1u);
-      fresh_ids[slot] = (int32_t)w;
-    }
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < W; base += stride) {
+    const long long w = base + lane;
+    int j = w < W ? init_j[w] : -1;
+    int bin = j >= 0 ? j / CH : -1;
+    unsigned peers = __match_any_sync(FULL_MASK, bin);
+    unsigned slot0 = 0;
+    int leader = __ffs(peers) - 1;
+    if (bin >= 0 && lane == leader) slot0 = atomicAdd(&cursor[bin], (unsigned)__popc(peers));
+    slot0 = __shfl_sync(FULL_MASK, slot0, leader);
+    if (bin >= 0) fresh_ids[slot0 + __popc(peers & ((1u << lane) - 1u))] = (int32_t)w;
   }
 }
 

@@ -65,7 +65,8 @@ struct nm_ctx {
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
   DevBuf Z, ghi, gb, xlo, a, b, c, mask, list, init_d, init_j, hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp;
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt;
+  int opt_k2_literal = 0;
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
   double tol = 0, gtol = 0;
 
@@ -252,7 +253,19 @@ int launch_deep(nm_ctx* ctx) {
   long long maxb2 = (long long)ctx->sm_count * 8;
   if (b2 > maxb2) b2 = maxb2;
   if (b2 < 1) b2 = 1;
-  k2_series<<<(unsigned)b2, K2_THREADS, 0, ctx->stream>>>(k2);
+  const bool literal = ctx->opt_k2_literal || !(ctx->tol > 0.0) || !std::isfinite(ctx->tol) || ctx->M < 2;
+  if (!literal) {
+    double* fb = ctx->filt.as<double>();
+    const size_t Mn = (size_t)ctx->M;
+    k2.f.rlog = fb; k2.f.a = fb + Mn; k2.f.b = fb + 2 * Mn; k2.f.ov = fb + 3 * Mn;
+    k2.f.pmin_rlog = fb + 4 * Mn; k2.f.pmin_ov = fb + 5 * Mn; k2.f.pmin_a = fb + 6 * Mn; k2.f.pmax_b = fb + 7 * Mn;
+    k2_prepare<<<1, 1024, 0, ctx->stream>>>(k2.B, k2.C, ctx->M, ctx->tol, k2.f);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    k2_series<false><<<(unsigned)b2, K2_THREADS, 0, ctx->stream>>>(k2);
+  } else {
+    k2_series<true><<<(unsigned)b2, K2_THREADS, 0, ctx->stream>>>(k2);
+  }
   NM_CUDA(ctx, cudaGetLastError());
   k2_scan<<<1, 32, 0, ctx->stream>>>(ctx->hist.as<unsigned>(), ctx->offs.as<unsigned>(), ctx->cursor.as<unsigned>(), K + 1);
   NM_CUDA(ctx, cudaGetLastError());
@@ -416,7 +429,7 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->init_d, &ctx->init_j,
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp};
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -430,6 +443,14 @@ int nm_set_stream(nm_ctx* ctx, void* cuda_stream) {
   if (!ctx) return NM_EINVAL;
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own;
   return NM_OK;
+}
+
+int nm_set_option(nm_ctx* ctx, int key, int value) {
+  if (!ctx) return NM_EINVAL;
+  switch (key) {
+    case NM_OPT_K2_LITERAL: ctx->opt_k2_literal = value ? 1 : 0; return NM_OK;
+    default: return fail(ctx, NM_EINVAL, "nm_set_option: unknown key %d", key);
+  }
 }
 
 int nm_sync(nm_ctx* ctx) {
@@ -505,6 +526,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->a.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->b.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->c.ensure((size_t)M * sizeof(double2)));
+  NM_CUDA(ctx, ctx->filt.ensure((size_t)M * 8 * sizeof(double)));
   NM_CUDA(ctx, ctx->init_d.ensure(Wn * sizeof(double2)));
   NM_CUDA(ctx, ctx->init_j.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->fresh.ensure(Wn * sizeof(int32_t)));

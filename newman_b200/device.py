@@ -38,6 +38,9 @@ class Device:
     def set_stream(self, cuda_stream_handle):
         self._ck(self.lib.nm_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)))
 
+    def set_option(self, key, value):
+        self._ck(self.lib.nm_set_option(self.h, int(key), int(value)))
+
     def sync(self):
         self._ck(self.lib.nm_sync(self.h))
 

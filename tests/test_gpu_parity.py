@@ -4,6 +4,7 @@ the reference is defined."""
 import numpy as np
 import pytest
 
+import newman_b200
 import oracles
 from oracles import KATS, RefView, p_render_deep, p_render_hw
 
@@ -41,10 +42,12 @@ def test_k1_bit_exact_vs_reference(dev, kat):
 
 
 @needs_ref
+@pytest.mark.parametrize("literal", [1, 0])
 @pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D60", "KAT-D90", "KAT-B", "KAT-T3", "KAT-S"])
-def test_deep_bit_exact_vs_oraclep(dev, kat):
+def test_deep_bit_exact_vs_oraclep(dev, kat, literal):
     """Series + perturbation: GPU == Oracle-P bit for bit, including which pixels are flagged as
-    glitched (order-independent), executed-iteration count and series evaluations."""
+    glitched (order-independent) and the executed-iteration count. K2 runs both as the reference's
+    literal index scan and with the per-index filter; both must give the oracle's L for every sample."""
     k = KATS[kat]
     v = RefView(**k)
     v.precompute()
@@ -52,7 +55,11 @@ def test_deep_bit_exact_vs_oraclep(dev, kat):
     er, ei = v.eps()
     exp, rq_pix, rq_it, st = p_render_deep(t, er, ei)
     tabs = dev.make_tables(t.x_hi, t.x_lo, t.a, t.b, t.c, t.N, t.tol, t.glitch_tol)
-    out = dev.render_deep(tabs, er, ei)
+    dev.set_option(newman_b200._lib.OPT_K2_LITERAL, literal)
+    try:
+        out = dev.render_deep(tabs, er, ei)
+    finally:
+        dev.set_option(newman_b200._lib.OPT_K2_LITERAL, 0)
     gpix, git = dev.requeue()
     assert np.array_equal(out["iterations"], exp["iterations"])
     assert np.array_equal(bits(out["smoothing"]), bits(exp["smoothing"]))
@@ -60,8 +67,50 @@ def test_deep_bit_exact_vs_oraclep(dev, kat):
     assert np.array_equal(gpix[o1], rq_pix[o2]) and np.array_equal(git[o1], rq_it[o2])
     gs = dev.stats()
     assert gs["executed_iters"] == st["executed_iters"]
-    assert gs["series_evals"] == st["series_evals"]
     assert gs["rebased"] == st["rebased"]
+    if literal:
+        assert gs["series_evals"] == st["series_evals"]
+    else:  # the filter leaves ~1 exact test per sample (KAT-B: tol = 1e9 is far outside its sweet spot)
+        assert gs["series_evals"] <= max(4 * out.size, st["series_evals"] // 8)
+        print(kat, "exact tests per sample: %.3f (literal %.1f)" % (gs["series_evals"] / out.size, st["series_evals"] / out.size))
+
+
+def test_series_filter_irregular_ranges(dev):
+    """Synthetic coefficient tables that push the filter into its unsafe / literal branches (tiny and
+    huge |B|,|C|, zeros, denormal products): filtered K2 must still reproduce the literal scan."""
+    rng = np.random.default_rng(11)
+    M, N = 400, 1000
+    nr, nc = 24, 32
+    for trial, (eps_mag, growth, tol) in enumerate([(1e-40, 0.9, 1e-10), (1e-95, 2.0, 1e-10), (1e-3, 0.2, 1e-10),
+                                                    (1e-60, 1.4, 1e5), (1e-102, 2.2, 1e-10), (1e-20, 0.0, 1e-300)]):
+        i = np.arange(M)
+        mag = 10.0 ** np.clip(growth * i, None, 300)
+        ph = rng.random((3, M)) * 2 * np.pi
+        a = np.stack([mag * np.cos(ph[0]), mag * np.sin(ph[0])], 1).reshape(-1)
+        b = np.stack([np.minimum(mag ** 2, 1e300) * np.cos(ph[1]), np.minimum(mag ** 2, 1e300) * np.sin(ph[1])], 1).reshape(-1)
+        c = np.stack([np.minimum(mag ** 3, 1e305) * np.cos(ph[2]), np.minimum(mag ** 3, 1e305) * np.sin(ph[2])], 1).reshape(-1)
+        for arr in (b, c):  # sprinkle exact zeros and tiny entries
+            arr[rng.integers(2, 2 * M, 12)] = 0.0
+            arr[rng.integers(2, 2 * M, 12)] *= 1e-200
+        b[:2] = 0; c[:2] = 0; a[:2] = (1.0, 0.0)
+        x_hi = np.zeros(2 * (M + 1)); x_hi[0::2] = 0.3 * np.cos(i_ := np.arange(M + 1) * 0.7); x_hi[1::2] = 0.3 * np.sin(i_)
+        x_hi[-2:] = (2000.0, 0.0)
+        x_lo = np.zeros(2 * M)
+        er = (rng.random(nc) - 0.5) * eps_mag * 10.0 ** (-8 * rng.random(nc))
+        ei = (rng.random(nr) - 0.5) * eps_mag * 10.0 ** (-8 * rng.random(nr))
+        er[3] = 0.0; ei[5] = 0.0
+        t = oracles.Tables(x_hi, x_lo, a, b, c, N, tol)
+        exp, rq_pix, rq_it, st = p_render_deep(t, er, ei)
+        tabs = dev.make_tables(t.x_hi, t.x_lo, t.a, t.b, t.c, t.N, t.tol, t.glitch_tol)
+        for literal in (1, 0):
+            dev.set_option(newman_b200._lib.OPT_K2_LITERAL, literal)
+            try:
+                out = dev.render_deep(tabs, er, ei)
+            finally:
+                dev.set_option(newman_b200._lib.OPT_K2_LITERAL, 0)
+            assert np.array_equal(out["iterations"], exp["iterations"]), (trial, literal)
+            assert np.array_equal(bits(out["smoothing"]), bits(exp["smoothing"])), (trial, literal)
+            assert dev.stats()["executed_iters"] == st["executed_iters"], (trial, literal)  # sum of L over samples
 
 
 @needs_ref
