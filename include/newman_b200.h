@@ -61,6 +61,9 @@ NM_API int nm_sync(nm_ctx* ctx);
  *                          instead of testing only the indices the per-index filter cannot rule out.
  *                          Both give the same L by construction; the tests run both. */
 #define NM_OPT_K2_LITERAL 1
+/*   NM_OPT_K3_GROUP (2)    pixels per lane in the fast perturbation kernel (k3_fast.cuh): 4 or 2;
+ *                          0/1 selects the simple one-pixel-per-lane kernel (k3_perturb.cuh). Same results. */
+#define NM_OPT_K3_GROUP 2
 NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
 /* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
 NM_API int nm_cancel(nm_ctx* ctx);
@@ -136,6 +139,7 @@ typedef struct nm_stats {
   uint64_t fixups;          /* smoothing values re-evaluated on the host */
   uint64_t kernel_launches; /* kernels of ours launched for this frame */
   uint64_t sweeps;          /* K3 passes over the orbit */
+  uint64_t checked_steps;   /* k3_fast: lane-steps taken one at a time with exact checks (rest run in blocks of 4) */
   float ms_k1, ms_k2, ms_k3, ms_k4; /* device time per stage (CUDA events on the ctx stream) */
 } nm_stats;
 NM_API int nm_frame_stats(nm_ctx* ctx, nm_stats* out);

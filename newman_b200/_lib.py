@@ -18,6 +18,7 @@ NM_OK, NM_EINVAL, NM_ENODEV, NM_ECUDA, NM_ENOMEM, NM_ESTATE, NM_ERANGE, NM_ECANC
 CARDIOID_NONE, CARDIOID_ALL, CARDIOID_MASK = 0, 1, 2
 MODE_REQUEUE, MODE_REBASE = 0, 1
 OPT_K2_LITERAL = 1
+OPT_K3_GROUP = 2
 
 
 class NmError(RuntimeError):
@@ -37,7 +38,7 @@ class DeepTables(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "pixels", "executed_iters", "series_evals", "skipped_pixels", "glitched", "rebased", "fixups",
-        "kernel_launches", "sweeps")] + [(n, C.c_float) for n in ("ms_k1", "ms_k2", "ms_k3", "ms_k4")]
+        "kernel_launches", "sweeps", "checked_steps")] + [(n, C.c_float) for n in ("ms_k1", "ms_k2", "ms_k3", "ms_k4")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

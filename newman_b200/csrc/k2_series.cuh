@@ -71,8 +71,7 @@ struct K2Params {
   const uint8_t* mask;
   double2* init_d;          // [W] delta at j0
   int32_t* init_j;          // [W] table index j0 = L of the first K3 state, or -1 if finished here
-  unsigned* hist;           // [K+1] fresh samples per orbit chunk
-  int CH;
+  unsigned* hist;           // [Jmax+2] fresh samples per exact start index L
   nm_escape* out;
   unsigned long long* ctr;
   FixupRec* fix;
@@ -279,9 +278,9 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
         }
       }
     }
-    // warp-aggregated histogram of the start chunk (neighbouring samples share it almost always)
+    // warp-aggregated histogram of the start index (neighbouring samples share L almost always)
     {
-      int bin = handoff_L >= 0 ? handoff_L / p.CH : -1;
+      int bin = handoff_L;
       unsigned peers = __match_any_sync(FULL_MASK, bin);
       if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&p.hist[bin], (unsigned)__popc(peers));
     }
@@ -339,24 +338,36 @@ __global__ void __launch_bounds__(1024) k2_prepare(const double2* B, const doubl
   }
 }
 
-// Exclusive scan of the per-chunk histogram (K+1 <= a few thousand entries).
-__global__ void k2_scan(const unsigned* hist, unsigned* offs, unsigned* cursor, int K1n) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    unsigned acc = 0;
-    for (int i = 0; i < K1n; ++i) { offs[i] = acc; cursor[i] = acc; acc += hist[i]; }
-    offs[K1n] = acc;
+// Exclusive scan of the start-index histogram with every run rounded up to a multiple of G (the
+// per-lane pixel group of k3_fast): offs[L] .. offs[L+1] holds the samples that start at L, padded
+// with -1. One CTA, each thread owns a contiguous segment of the n bins.
+__global__ void __launch_bounds__(1024) k2_scan(const unsigned* hist, unsigned* offs, unsigned* cursor, int n, unsigned G) {
+  __shared__ unsigned s_tot[1024];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int seg = (n + nt - 1) / nt;
+  const int i0 = t * seg, i1 = min(n, i0 + seg);
+  unsigned acc = 0;
+  for (int i = i0; i < i1; ++i) acc += (hist[i] + G - 1) / G * G;
+  s_tot[t] = acc;
+  __syncthreads();
+  unsigned base = 0;
+  for (int s = 0; s < t; ++s) base += s_tot[s];
+  for (int i = i0; i < i1; ++i) {
+    offs[i] = base; cursor[i] = base;
+    base += (hist[i] + G - 1) / G * G;
   }
+  if (i1 == n && i0 <= n) offs[n] = base;  // the owner of the last segment (or an empty tail thread: same value)
 }
 
-// Scatter fresh work indices into chunk-sorted order (warp-aggregated slot reservation).
-__global__ void __launch_bounds__(256) k2_scatter(const int32_t* init_j, long long W, int CH,
-                                                  unsigned* cursor, int32_t* fresh_ids) {
+// Scatter fresh work indices into start-index-sorted order (warp-aggregated slot reservation).
+// fresh_ids is pre-filled with -1 so the padding of each run reads as "no sample".
+__global__ void __launch_bounds__(256) k2_scatter(const int32_t* init_j, long long W, unsigned* cursor,
+                                                  int32_t* fresh_ids) {
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < W; base += stride) {
     const long long w = base + lane;
-    int j = w < W ? init_j[w] : -1;
-    int bin = j >= 0 ? j / CH : -1;
+    int bin = w < W ? init_j[w] : -1;
     unsigned peers = __match_any_sync(FULL_MASK, bin);
     unsigned slot0 = 0;
     int leader = __ffs(peers) - 1;

@@ -52,7 +52,7 @@ struct K3Params {
   const PixState* cur;
   const unsigned long long* cur_count;
   const int32_t* fresh_ids;
-  const unsigned* fresh_off;   // nullptr after sweep 0
+  const unsigned* fresh_off;   // [Jmax+2] offsets by exact start index; nullptr after sweep 0
   const double2* init_d;
   const int32_t* init_j;
   const int32_t* pix_list;
@@ -119,9 +119,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
   const unsigned long long n_cur = p.cur_count ? *p.cur_count : 0ULL;
   unsigned long long n_fresh = 0;
   unsigned fresh_begin = 0;
-  if (p.fresh_off) {
-    fresh_begin = p.fresh_off[p.k];
-    n_fresh = p.fresh_off[p.k + 1] - fresh_begin;
+  if (p.fresh_off) {  // fresh samples are sorted by exact start index; runs are padded with -1
+    int l1 = jbase + CH;
+    if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
+    fresh_begin = p.fresh_off[jbase];
+    n_fresh = p.fresh_off[l1] - fresh_begin;
   }
   const unsigned long long total = n_cur + n_fresh;
   if (total == 0) return;  // uniform across the grid: nothing lives in this chunk
@@ -165,21 +167,27 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
       if (!active) {
         unsigned long long idx = base + __popc(idle & lt_mask);
         if (idx < total) {
+          bool got = true;
           if (idx < n_cur) {
             PixState s = p.cur[idx];
             dr = s.dr; di = s.di; pix = s.pix; j = s.j; off = s.off;
           } else {
             int w = p.fresh_ids[fresh_begin + (unsigned)(idx - n_cur)];
-            double2 d0 = p.init_d[w];
-            dr = d0.x; di = d0.y;
-            j = p.init_j[w];
-            off = -1;
-            pix = p.pix_list ? p.pix_list[w] : w;
+            got = w >= 0;
+            if (got) {
+              double2 d0 = p.init_d[w];
+              dr = d0.x; di = d0.y;
+              j = p.init_j[w];
+              off = -1;
+              pix = p.pix_list ? p.pix_list[w] : w;
+            }
           }
-          int r = pix / p.nc, c = pix - r * p.nc;
-          er = p.eps_re[c];
-          ei = p.eps_im[r];
-          active = true;
+          if (got) {
+            int r = pix / p.nc, c = pix - r * p.nc;
+            er = p.eps_re[c];
+            ei = p.eps_im[r];
+            active = true;
+          }
         }
       }
       break;  // one reservation per round; leftovers are picked up after the next burst

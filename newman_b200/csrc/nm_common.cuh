@@ -33,7 +33,9 @@ enum Counter {
   CTR_Q_RESTART,      // K3: rebased pixels appended for the next sweep
   CTR_Q_CUR,          // K3: size of the current input queue
   CTR_DONE,           // K3: pixels finished
-  CTR_COUNT = 16
+  CTR_CHECKED,        // K3 fast kernel: lane-steps taken in the checked (non-block) path
+  CTR_ESCAPED,        // K3 fast kernel: escape records waiting for k3_smooth
+  CTR_COUNT = 24
 };
 
 struct FixupRec {  // smoothing value to be re-evaluated with the host libm

@@ -9,7 +9,7 @@
 //            Xlo[M]      16 B      low parts of X (phase-2 truncated add)
 //            A,B,C[M]    16 B each descended series coefficients
 //            eps_re[nc], eps_im[nr]
-//            init_d[W] 16 B, init_j[W] 4 B, fresh_ids[W] 4 B     K2 -> K3 hand-over, chunk-sorted
+//            init_d[W] 16 B, init_j[W] 4 B, fresh_ids[~W] 4 B    K2 -> K3 hand-over, sorted by start index
 //            q[2][W], rq[2][W]   32 B PixState      level ping-pong queues, rebase queues
 //            rq_pix[W], rq_iter[W]                   glitch re-queue list
 // No CPU fallback exists: without a device every entry returns NM_ENODEV.
@@ -23,6 +23,7 @@
 #include "k1_escape.cuh"
 #include "k2_series.cuh"
 #include "k3_perturb.cuh"
+#include "k3_fast.cuh"
 #include "k4_resolve.cuh"
 
 using namespace nm;
@@ -65,8 +66,10 @@ struct nm_ctx {
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
   DevBuf Z, ghi, gb, xlo, a, b, c, mask, list, init_d, init_j, hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp, filt;
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt, esc;
   int opt_k2_literal = 0;
+  int opt_k3_group = 2;  // pixels per lane in k3_fast (0: simple kernel only)
+  int occ_k3f[2] = {0, 0};
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
   double tol = 0, gtol = 0;
 
@@ -175,6 +178,7 @@ int finish_frame(nm_ctx* ctx) {
   ctx->stats.skipped_pixels = ctx->h_ctr[CTR_SKIPPED];
   ctx->stats.glitched = ctx->h_ctr[CTR_REQUEUE];
   ctx->stats.rebased = ctx->h_ctr[CTR_REBASED];
+  ctx->stats.checked_steps = ctx->h_ctr[CTR_CHECKED];
   ctx->stats.fixups = nfix;
   float ms = 0;
   if (ctx->kind == 1) {
@@ -232,7 +236,10 @@ int launch_deep(nm_ctx* ctx) {
   unsigned long long* rcount = qctr + 2 * (K + 2);
 
   NM_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-  NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (K + 2) * sizeof(unsigned), ctx->stream));
+  const int G = (ctx->mode == NM_MODE_REQUEUE && ctx->opt_k3_group > 1) ? ctx->opt_k3_group : 1;
+  const int nbins = ctx->Jmax + 1;  // start indices L in [0, Jmax]
+  NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(nbins + 2) * sizeof(unsigned), ctx->stream));
+  NM_CUDA(ctx, cudaMemsetAsync(ctx->fresh.p, 0xFF, ((size_t)ctx->W + (size_t)4 * (nbins + 2)) * sizeof(int32_t), ctx->stream));
 
   K2Params k2;
   k2.A = ctx->a.as<double2>(); k2.B = ctx->b.as<double2>(); k2.C = ctx->c.as<double2>();
@@ -244,7 +251,7 @@ int launch_deep(nm_ctx* ctx) {
   k2.cardioid_mode = ctx->cardioid_mode;
   k2.mask = ctx->mask.as<uint8_t>();
   k2.init_d = ctx->init_d.as<double2>(); k2.init_j = ctx->init_j.as<int32_t>();
-  k2.hist = ctx->hist.as<unsigned>(); k2.CH = CH;
+  k2.hist = ctx->hist.as<unsigned>();
   k2.out = ctx->out.as<nm_escape>();
   k2.ctr = ctx->ctr.as<unsigned long long>();
   k2.fix = ctx->fix.as<FixupRec>(); k2.fix_cap = ctx->fix_cap;
@@ -267,9 +274,9 @@ int launch_deep(nm_ctx* ctx) {
     k2_series<true><<<(unsigned)b2, K2_THREADS, 0, ctx->stream>>>(k2);
   }
   NM_CUDA(ctx, cudaGetLastError());
-  k2_scan<<<1, 32, 0, ctx->stream>>>(ctx->hist.as<unsigned>(), ctx->offs.as<unsigned>(), ctx->cursor.as<unsigned>(), K + 1);
+  k2_scan<<<1, 1024, 0, ctx->stream>>>(ctx->hist.as<unsigned>(), ctx->offs.as<unsigned>(), ctx->cursor.as<unsigned>(), nbins, (unsigned)G);
   NM_CUDA(ctx, cudaGetLastError());
-  k2_scatter<<<(unsigned)b2, 256, 0, ctx->stream>>>(ctx->init_j.as<int32_t>(), ctx->W, CH, ctx->cursor.as<unsigned>(),
+  k2_scatter<<<(unsigned)b2, 256, 0, ctx->stream>>>(ctx->init_j.as<int32_t>(), ctx->W, ctx->cursor.as<unsigned>(),
                                                     ctx->fresh.as<int32_t>());
   NM_CUDA(ctx, cudaGetLastError());
   ctx->stats.kernel_launches += 3;
@@ -288,8 +295,10 @@ int launch_deep(nm_ctx* ctx) {
   p.rq_pix = ctx->rq_pix.as<int32_t>(); p.rq_iter = ctx->rq_iter.as<int32_t>();
   p.log_bailout = ctx->log_bailout;
 
-  const size_t smem = (size_t)(CH + 4) * (sizeof(double2) + sizeof(int32_t));
-  const int occ = ctx->occ_k3[ctx->mode == NM_MODE_REBASE ? 1 : 0];
+  const size_t smem = (size_t)(CH + 4) * (sizeof(double2) + sizeof(double));
+  int occ = ctx->occ_k3[ctx->mode == NM_MODE_REBASE ? 1 : 0];
+  if (G == 2) occ = ctx->occ_k3f[0];
+  if (G == 4) occ = ctx->occ_k3f[1];
   const unsigned blocks = (unsigned)(ctx->sm_count * occ);
 
   for (int sweep = 0;; ++sweep) {
@@ -311,8 +320,11 @@ int launch_deep(nm_ctx* ctx) {
       p.restart_count = &rcount[par ^ 1];
       p.head = &head[k];
       p.fresh_off = sweep == 0 ? ctx->offs.as<unsigned>() : nullptr;
-      cudaError_t e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE>(ctx, p, blocks, smem)
-                                                  : launch_level<NM_MODE_REQUEUE>(ctx, p, blocks, smem);
+      cudaError_t e;
+      if (G == 4) { k3_fast<4><<<blocks, K3F_THREADS, smem, ctx->stream>>>(p, ctx->esc.as<EscRec>()); e = cudaGetLastError(); }
+      else if (G == 2) { k3_fast<2><<<blocks, K3F_THREADS, smem, ctx->stream>>>(p, ctx->esc.as<EscRec>()); e = cudaGetLastError(); }
+      else e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE>(ctx, p, blocks, smem)
+                                           : launch_level<NM_MODE_REQUEUE>(ctx, p, blocks, smem);
       if (e != cudaSuccess) return fail(ctx, NM_ECUDA, "k3_level launch: %s", cudaGetErrorString(e));
       ctx->stats.kernel_launches++;
     }
@@ -322,6 +334,13 @@ int launch_deep(nm_ctx* ctx) {
                                  cudaMemcpyDeviceToHost, ctx->stream));
     NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_ctr[0] == 0 || ctx->h_ctr[1] != 0) break;
+  }
+  if (G > 1) {  // smoothing of the escapes k3_fast recorded (dense list, one converged kernel)
+    k3_smooth<<<(unsigned)(ctx->sm_count * 8), 256, 0, ctx->stream>>>(ctx->esc.as<EscRec>(),
+        &ctx->ctr.as<unsigned long long>()[CTR_ESCAPED], ctx->out.as<nm_escape>(), ctx->ctr.as<unsigned long long>(),
+        ctx->fix.as<FixupRec>(), ctx->fix_cap, ctx->log_bailout);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
   }
   NM_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   return NM_OK;
@@ -407,9 +426,13 @@ int nm_create(int device, nm_ctx** out) {
   NM_CREATE_CUDA(cudaMallocHost((void**)&ctx->h_flag, sizeof(unsigned long long)));
   *ctx->h_flag = 1ULL;
   ctx->log_bailout = log(1024.0);
-  const size_t smem = (size_t)(ctx->CH + 4) * (sizeof(double2) + sizeof(int32_t));
+  const size_t smem = (size_t)(ctx->CH + 4) * (sizeof(double2) + sizeof(double));
   NM_CREATE_CUDA(cudaFuncSetAttribute(k3_level<NM_MODE_REQUEUE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NM_CREATE_CUDA(cudaFuncSetAttribute(k3_level<NM_MODE_REBASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_fast<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3f[0], k3_fast<2>, K3F_THREADS, smem));
+  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3f[1], k3_fast<4>, K3F_THREADS, smem));
   NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k1, k1_escape, K1_THREADS, 0));
   NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3[0], k3_level<NM_MODE_REQUEUE>, K3_THREADS, smem));
   NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3[1], k3_level<NM_MODE_REBASE>, K3_THREADS, smem));
@@ -417,6 +440,8 @@ int nm_create(int device, nm_ctx** out) {
   if (ctx->occ_k1 < 1) ctx->occ_k1 = 1;
   if (ctx->occ_k3[0] < 1) ctx->occ_k3[0] = 1;
   if (ctx->occ_k3[1] < 1) ctx->occ_k3[1] = 1;
+  if (ctx->occ_k3f[0] < 1) ctx->occ_k3f[0] = 1;
+  if (ctx->occ_k3f[1] < 1) ctx->occ_k3f[1] = 1;
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
   return NM_OK;
@@ -429,7 +454,7 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->init_d, &ctx->init_j,
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt};
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->esc};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -449,6 +474,10 @@ int nm_set_option(nm_ctx* ctx, int key, int value) {
   if (!ctx) return NM_EINVAL;
   switch (key) {
     case NM_OPT_K2_LITERAL: ctx->opt_k2_literal = value ? 1 : 0; return NM_OK;
+    case NM_OPT_K3_GROUP:
+      if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, NM_EINVAL, "NM_OPT_K3_GROUP must be 0, 1, 2 or 4");
+      ctx->opt_k3_group = value;
+      return NM_OK;
     default: return fail(ctx, NM_EINVAL, "nm_set_option: unknown key %d", key);
   }
 }
@@ -529,10 +558,10 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->filt.ensure((size_t)M * 8 * sizeof(double)));
   NM_CUDA(ctx, ctx->init_d.ensure(Wn * sizeof(double2)));
   NM_CUDA(ctx, ctx->init_j.ensure(Wn * sizeof(int32_t)));
-  NM_CUDA(ctx, ctx->fresh.ensure(Wn * sizeof(int32_t)));
-  NM_CUDA(ctx, ctx->hist.ensure((size_t)(K + 2) * sizeof(unsigned)));
-  NM_CUDA(ctx, ctx->offs.ensure((size_t)(K + 2) * sizeof(unsigned)));
-  NM_CUDA(ctx, ctx->cursor.ensure((size_t)(K + 2) * sizeof(unsigned)));
+  NM_CUDA(ctx, ctx->fresh.ensure((Wn + (size_t)4 * (J1 + 2)) * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->hist.ensure((size_t)(J1 + 4) * sizeof(unsigned)));
+  NM_CUDA(ctx, ctx->offs.ensure((size_t)(J1 + 4) * sizeof(unsigned)));
+  NM_CUDA(ctx, ctx->cursor.ensure((size_t)(J1 + 4) * sizeof(unsigned)));
   for (int i = 0; i < 2; i++) {
     NM_CUDA(ctx, ctx->q[i].ensure(Wn * sizeof(PixState)));
     NM_CUDA(ctx, ctx->rq[i].ensure(Wn * sizeof(PixState)));
@@ -540,6 +569,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->qctr.ensure((size_t)(2 * (K + 2) + 2) * sizeof(unsigned long long)));
   NM_CUDA(ctx, ctx->rq_pix.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->rq_iter.ensure(Wn * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->esc.ensure(Wn * sizeof(EscRec)));
 
   cudaStream_t s = ctx->stream;
   NM_CUDA(ctx, cudaMemsetAsync(ctx->Z.p, 0, (size_t)(J1 + 8) * sizeof(double2), s));

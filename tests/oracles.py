@@ -290,7 +290,7 @@ class OracleDevice:
 
     def stats(self):
         d = dict(self._st)
-        d.update(pixels=self.nr * self.nc, fixups=0, kernel_launches=0, sweeps=0, ms_k1=0.0, ms_k2=0.0, ms_k3=0.0, ms_k4=0.0)
+        d.update(pixels=self.nr * self.nc, fixups=0, kernel_launches=0, sweeps=0, checked_steps=0, ms_k1=0.0, ms_k2=0.0, ms_k3=0.0, ms_k4=0.0)
         return d
 
     def requeue(self):

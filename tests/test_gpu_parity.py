@@ -75,6 +75,33 @@ def test_deep_bit_exact_vs_oraclep(dev, kat, literal):
         print(kat, "exact tests per sample: %.3f (literal %.1f)" % (gs["series_evals"] / out.size, st["series_evals"] / out.size))
 
 
+@needs_ref
+@pytest.mark.parametrize("group", [0, 2, 4])
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D90", "KAT-S"])
+def test_k3_kernel_variants_agree(dev, kat, group):
+    """The simple (1 pixel/lane) and fast (2 or 4 same-index pixels/lane, branch-free blocks) kernels
+    take identical decisions: rasters, glitch lists, executed-iteration and rebase counts."""
+    k = KATS[kat]
+    v = RefView(**k)
+    v.precompute()
+    t = v.tables()
+    er, ei = v.eps()
+    exp, rq_pix, rq_it, st = p_render_deep(t, er, ei)
+    tabs = dev.make_tables(t.x_hi, t.x_lo, t.a, t.b, t.c, t.N, t.tol, t.glitch_tol)
+    dev.set_option(newman_b200._lib.OPT_K3_GROUP, group)
+    try:
+        out = dev.render_deep(tabs, er, ei)
+        gpix, git = dev.requeue()
+        gs = dev.stats()
+    finally:
+        dev.set_option(newman_b200._lib.OPT_K3_GROUP, 2)
+    assert np.array_equal(out["iterations"], exp["iterations"])
+    assert np.array_equal(bits(out["smoothing"]), bits(exp["smoothing"]))
+    o1 = np.argsort(gpix); o2 = np.argsort(rq_pix)
+    assert np.array_equal(gpix[o1], rq_pix[o2]) and np.array_equal(git[o1], rq_it[o2])
+    assert gs["executed_iters"] == st["executed_iters"] and gs["rebased"] == st["rebased"]
+
+
 def test_series_filter_irregular_ranges(dev):
     """Synthetic coefficient tables that push the filter into its unsafe / literal branches (tiny and
     huge |B|,|C|, zeros, denormal products): filtered K2 must still reproduce the literal scan."""
