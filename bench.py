@@ -205,8 +205,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import newman_b200
-    from newman_b200 import pipeline, workloads
-    from newman_b200 import _lib as L
+    from newman_b200 import multigpu, pipeline, workloads
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,14 +252,7 @@ def run_ours(args):
             d[k] = t
         return pipeline.TableSet(d, N, cfg["tol"], 1e-6)
 
-    def reduce_pick(best_iter, best_pix, n_local):
-        big = np.iinfo(np.int64).max
-        key = big if best_iter == big else (best_iter << 40) | best_pix
-        if world > 1:
-            t = torch.tensor([key], dtype=torch.int64, device=devt)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            key = int(t.item())
-        return None if key == big else key & ((1 << 40) - 1)
+    reduce_pick = multigpu.make_reduce_pick(world, devt)
 
     eps_cache = {}
 
@@ -363,7 +355,6 @@ def run_ours(args):
     # ---- timed: end to end with host buffers --------------------------------------------------------
     out_dev = torch.empty((len(rows), nc, 2), dtype=torch.int32, device=devt)
     out_host = torch.empty((nr, nc, 2), dtype=torch.int32).pin_memory() if rank == 0 else None
-    gathered = [torch.empty_like(out_dev) for _ in range(world)] if (rank == 0 and world > 1) else None
     if world > 1:
         lens = [len(pipeline.local_rows(nr, r, world)) for r in range(world)]
         assert len(set(lens)) == 1, "grid rows must divide evenly across ranks"
@@ -371,13 +362,12 @@ def run_ours(args):
     def frame_e2e():
         frame(False)
         if world == 1:
-            dev.read_rows(0, len(rows), out_host)
+            dev.read_rows(0, len(rows), out_host)          # D2H straight into pinned host memory
         else:
-            dev.read_rows(0, len(rows), out_dev)
-            dist.gather(out_dev, gathered, dst=0)
+            dev.read_rows(0, len(rows), out_dev)           # band stays on the device ...
+            full = multigpu.gather_bands(out_dev, nr, rank, world)   # ... NCCL gather to the host-facing rank
             if rank == 0:
-                for r in range(world):
-                    out_host[r::world].copy_(gathered[r], non_blocking=True)
+                out_host.copy_(full, non_blocking=True)    # ... one D2H of the assembled raster
         torch.cuda.synchronize()
 
     frame_e2e()

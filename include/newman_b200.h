@@ -223,6 +223,21 @@ NM_API int nmv_host_coords(nmv_view* v, double* c_re, double* c_im);       /* ma
 NM_API int nmv_host_cardioid(nmv_view* v, uint8_t* mask_or_null);          /* returns NM_CARDIOID_* */
 NM_API int nmv_host_in_cardioid(nmv_view* v, int r, int c);                /* mandelbrot.cpp:63-71 */
 
+/* ==== palette: MultiWaveGenerator through C (include/newman_b200/multiwave.h == reference
+ * multiwave.h:8-37). The N-entry RGB table is built on the host, like the reference
+ * (multiwave.cpp:75-116, viewer.cpp:66-68); nm_resolve / nmv_resolve consume it. */
+typedef struct nmp_palette nmp_palette;
+NM_API nmp_palette* nmp_create(void);
+NM_API void nmp_destroy(nmp_palette* p);
+NM_API int nmp_load_file(nmp_palette* p, const char* fn);            /* .pal text, multiwave.cpp:19-48 */
+NM_API int nmp_save_file(const nmp_palette* p, const char* fn);      /* multiwave.cpp:50-73 */
+NM_API int nmp_clear(nmp_palette* p);
+NM_API int nmp_add_hue_cycle(nmp_palette* p, const float* hues_deg, int n, int period);
+NM_API int nmp_set_hue_period(nmp_palette* p, int period);
+NM_API int nmp_set_sat_cycle(nmp_palette* p, const float* sats, int n, int period);
+NM_API int nmp_add_lum_wave(nmp_palette* p, float amplitude, int period);
+NM_API int nmp_cache(const nmp_palette* p, int N, uint8_t* rgb_out); /* cache(N): 3*N bytes r,g,b */
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ from ._lib import (CARDIOID_ALL, CARDIOID_MASK, CARDIOID_NONE, ESCAPE_DTYPE, MOD
                    load)
 from .device import Device
 from .view import Mandelbrot
+from .palette import MultiWaveGenerator
 
-__all__ = ["Device", "Mandelbrot", "NmError", "load", "ESCAPE_DTYPE", "CARDIOID_NONE", "CARDIOID_ALL", "CARDIOID_MASK",
+__all__ = ["Device", "Mandelbrot", "MultiWaveGenerator", "NmError", "load", "ESCAPE_DTYPE", "CARDIOID_NONE", "CARDIOID_ALL", "CARDIOID_MASK",
            "MODE_REQUEUE", "MODE_REBASE"]

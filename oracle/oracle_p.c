@@ -281,3 +281,68 @@ op_escape oraclep_at_sc(const op_escape* grid, int nc, int r, int c, int sc) { /
   e.smoothing = sum - e.iterations;
   return e;
 }
+
+/* ---- multiwave palette (multiwave.cpp:5-17, 75-116) --------------------------------------------- */
+static uint8_t to_byte(float v) {
+  float x = v * 255.0f + 0.5f;
+  if (!(x > 0.0f)) return 0;
+  if (x >= 255.0f) return 255;
+  return (uint8_t)x;
+}
+static float hue_channel(float p, float q, float t) {
+  if (t < 0.0f) t += 1.0f;
+  if (t > 1.0f) t -= 1.0f;
+  if (t < 1.0f / 6.0f) return p + (q - p) * 6.0f * t;
+  if (t < 0.5f) return q;
+  if (t < 2.0f / 3.0f) return p + (q - p) * (2.0f / 3.0f - t) * 6.0f;
+  return p;
+}
+static void hsl2rgb(float h_deg, float s, float l, uint8_t* rgb) {
+  float h = fmodf(h_deg, 360.0f);
+  if (h < 0.0f) h += 360.0f;
+  h /= 360.0f;
+  if (s <= 0.0f) { rgb[0] = rgb[1] = rgb[2] = to_byte(l); return; }
+  float q = l < 0.5f ? l * (1.0f + s) : l + s - l * s;
+  float p = 2.0f * l - q;
+  rgb[0] = to_byte(hue_channel(p, q, h + 1.0f / 3.0f));
+  rgb[1] = to_byte(hue_channel(p, q, h));
+  rgb[2] = to_byte(hue_channel(p, q, h - 1.0f / 3.0f));
+}
+static void interp3(const uint8_t* a, const uint8_t* b, float t, uint8_t* o) {
+  for (int k = 0; k < 3; k++) o[k] = (uint8_t)clampf((1.0f - t) * a[k] + t * b[k]);
+}
+static float cycle_value(const float* v, int n, int period, int step) { /* FloatCycle::value */
+  float t = (size_t)n * (step % period) / (float)period;
+  int i0 = (int)t, i1 = (i0 + 1) % n;
+  t -= i0;
+  return (float)((1.0 - t) * v[i0] + t * v[i1]);
+}
+void oraclep_palette_cache(int n_cycles, const int* hue_counts, const float* hue_values, const int* hue_periods,
+                           int hue_period, int n_sat, const float* sat_values, int sat_period, int n_lum,
+                           const float* lum_amp, const int* lum_period, int N, uint8_t* rgb) {
+  const float tau = (float)(2.0 * 3.14159265358979);
+  for (int i = 0; i < N; i++) {
+    float sat = cycle_value(sat_values, n_sat, sat_period, i);
+    float lum = 0.0f;
+    for (int k = 0; k < n_lum; k++) lum += lum_amp[k] * sinf(i * tau / lum_period[k]);
+    lum = (float)(1.0 / (1.0 + exp(-lum)));
+    float ty = (size_t)n_cycles * (i % hue_period) / (float)hue_period;
+    int y0 = (int)ty, y1 = (y0 + 1) % n_cycles;
+    ty -= y0;
+    uint8_t col[2][3];
+    int ys[2] = {y0, y1};
+    for (int w = 0; w < 2; w++) {
+      const float* hv = hue_values;
+      for (int k = 0; k < ys[w]; k++) hv += hue_counts[k];
+      int n = hue_counts[ys[w]], per = hue_periods[ys[w]];
+      float tx = (size_t)n * (i % per) / (float)per;
+      int x0 = (int)tx, x1 = (x0 + 1) % n;
+      tx -= x0;
+      uint8_t a[3], b[3];
+      hsl2rgb(hv[x0], sat, lum, a);
+      hsl2rgb(hv[x1], sat, lum, b);
+      interp3(a, b, tx, col[w]);
+    }
+    interp3(col[0], col[1], ty, rgb + 3 * i);
+  }
+}

@@ -55,6 +55,12 @@ void oraclep_resolve(const op_escape* grid, int nr, int nc, const uint8_t* pal, 
 /* mandelbrot.cpp:320-332: iteration-space box average with a float32 accumulator. */
 op_escape oraclep_at_sc(const op_escape* grid, int nc, int r, int c, int sc);
 
+/* multiwave.cpp:75-116 with this repo's colour conventions (CSS hsl2rgb, round(255v); interp truncates).
+ * hue cycles are passed flattened: cycle k has hue_counts[k] values followed in hue_values. */
+void oraclep_palette_cache(int n_cycles, const int* hue_counts, const float* hue_values, const int* hue_periods,
+                           int hue_period, int n_sat, const float* sat_values, int sat_period, int n_lum,
+                           const float* lum_amp, const int* lum_period, int N, uint8_t* rgb);
+
 float oraclep_smoothing(double r2);
 double oraclep_trunc_add3(double hi, double lo, double d);
 #endif

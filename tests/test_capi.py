@@ -9,13 +9,14 @@ import pytest
 import newman_b200
 from newman_b200 import _lib as L
 from newman_b200 import view as V
+from newman_b200 import palette as PAL
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "newman_b200.h")).read()
-    return sorted(set(re.findall(r"NM_API[^;(]*?\b(nmv?_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"NM_API[^;(]*?\b(nm[vp]?_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported():
@@ -28,7 +29,7 @@ def test_header_symbols_exported():
 
 def test_bindings_cover_header():
     names = set(declared_symbols())
-    bound = set(L.DEVICE_API) | set(V.VIEW_API)
+    bound = set(L.DEVICE_API) | set(V.VIEW_API) | set(PAL.PALETTE_API)
     assert names == bound, (names - bound, bound - names)
 
 
