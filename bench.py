@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--scale", type=int, default=1, help="divide the grid by this (debug only; invalid as a bench number)")
     ap.add_argument("--cpu-sample", type=int, default=6144, help="pixels in the timed CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ymult", type=int, default=0, help="debug: force the weak-scaling row multiplier")
     return ap.parse_args()
 
 
@@ -219,9 +220,10 @@ def run_ours(args):
     devt = torch.device("cuda", local)
     dev = newman_b200.Device(local)
     stream = torch.cuda.Stream(device=devt)
+    torch.cuda.set_stream(stream)      # torch ops and NCCL order against the stream our kernels run on
     dev.set_stream(stream.cuda_stream)
 
-    cfg = workloads.config(args.workload, scale=args.scale, y_mult=world)
+    cfg = workloads.config(args.workload, scale=args.scale, y_mult=args.ymult or world)
     nr, nc, N = cfg["nr"], cfg["nc"], cfg["N"]
     hw = cfg["sz"] is None
     rows = pipeline.local_rows(nr, rank, world)
@@ -250,6 +252,7 @@ def run_ours(args):
             if world > 1:
                 dist.broadcast(t, 0)
             d[k] = t
+        torch.cuda.synchronize()       # broadcasts have landed before the C-ABI copies from these buffers
         return pipeline.TableSet(d, N, cfg["tol"], 1e-6)
 
     reduce_pick = multigpu.make_reduce_pick(world, devt)
@@ -263,6 +266,7 @@ def run_ours(args):
             eps_cache[k] = (e[rows_t].contiguous() if isinstance(e, torch.Tensor) and e.is_cuda else
                             e[torch.as_tensor(rows)].contiguous().pin_memory() if isinstance(e, torch.Tensor) else
                             np.ascontiguousarray(e[rows]))
+            torch.cuda.synchronize()
         return eps_cache[k]
 
     stats_total = {}
@@ -320,7 +324,8 @@ def run_ours(args):
             it = iter(chain)
             res = pipeline.render_rounds(dev, primary if device_resident else primary_h, lambda gp: next(it), nc, rows,
                                          reduce_pick=reduce_pick, eps_rows=eps_rows)
-            assert res["refs"] == refs, "secondary reference chain changed between frames"
+            assert res["refs"] == refs, f"secondary reference chain changed between frames: {res['refs']} vs {refs}; " \
+                f"glitched {[st['glitched'] for st in res['stats']]}"
             add_stats(res)
 
     def barrier():
