@@ -61,7 +61,7 @@ NM_API int nm_sync(nm_ctx* ctx);
  *                          instead of testing only the indices the per-index filter cannot rule out.
  *                          Both give the same L by construction; the tests run both. */
 #define NM_OPT_K2_LITERAL 1
-/*   NM_OPT_K3_GROUP (2)    pixels per lane in the fast perturbation kernel (k3_fast.cuh): 4 or 2;
+/*   NM_OPT_K3_GROUP (4)    pixels per lane in the fast perturbation kernel (k3_fast.cuh): 4 or 2;
  *                          0/1 selects the simple one-pixel-per-lane kernel (k3_perturb.cuh). Same results. */
 #define NM_OPT_K3_GROUP 2
 NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
@@ -165,6 +165,7 @@ NM_API int nm_resolve_grid(nm_ctx* ctx, const nm_escape* grid, int nr, int nc, c
 
 /* ---- measurement helpers --------------------------------------------------------------------
  * FP64-pipe peak probe: runs `iters` dependent-chain DFMA (kind 0), DADD (1), DMUL (2) per thread
+ * (kind 3: the K3 iteration body from registers, counted as 10 instructions per pixel-iteration)
  * over a full-chip grid and returns instructions/s. Used by bench.py for the roofline denominator
  * (MEASURED_PEAKS.json carries no FP64 entry). */
 NM_API int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms);

@@ -179,4 +179,28 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters,
   if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// The K3 iteration body itself (4 pixels per thread, all operands in distinct registers, no memory):
+// what the FP64 pipe sustains for this exact instruction mix (7 DFMA + 2 DADD + 1 DMUL per pixel-
+// iteration with three different 64-bit register operands per DFMA).
+__global__ void __launch_bounds__(256) fp64_k3mix_kernel(double* sink, int iters, double xr, double xi, double yr, double yi) {
+  double dr[4], di[4], er[4], ei[4];
+  int acc = 0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { dr[s] = 1e-9 * (threadIdx.x + s); di[s] = -1e-9 * (s + 1); er[s] = 1e-12 * s; ei[s] = 2e-12; }
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      double wr = __fma_rn(2.0, xr, dr[s]);
+      double wi = __fma_rn(2.0, xi, di[s]);
+      double ndr = __fma_rn(-di[s], wi, __fma_rn(dr[s], wr, er[s]));
+      double ndi = __fma_rn(di[s], wr, __fma_rn(dr[s], wi, ei[s]));
+      dr[s] = ndr; di[s] = ndi;
+      double zr = yr + ndr, zi = yi + ndi;
+      acc |= __double2hiint(__fma_rn(zi, zi, zr * zr));  // integer pipe, like the kernel's candidate compare
+    }
+  }
+  if (acc == 123456) sink[0] = acc + dr[0] + di[1];
+}
+
 }  // namespace nm

@@ -39,7 +39,7 @@
 // transforms and one round-toward-zero add; it can differ from the mpf value only if the exact sum
 // lies within 2^-106 (relative) of a double, where the mpf digits below lo would decide.
 #pragma once
-#include "nm_common.cuh"
+#include "k3_checked.cuh"
 
 namespace nm {
 
@@ -69,8 +69,9 @@ struct K2Params {
   long long W;              // number of work items
   int cardioid_mode;
   const uint8_t* mask;
-  double2* init_d;          // [W] delta at j0
-  int32_t* init_j;          // [W] table index j0 = L of the first K3 state, or -1 if finished here
+  FreshArrays fresh;        // [W] K3 start state of work item w (j = -1 if the sample finished here)
+  int align4;               // 1: take the <= 3 checked steps that make j a multiple of 4 (k3_fast)
+  CheckedParams ck;         // tables/lists for those steps
   unsigned* hist;           // [Jmax+2] fresh samples per exact start index L
   nm_escape* out;
   unsigned long long* ctr;
@@ -170,7 +171,7 @@ template <bool LITERAL>
 __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  unsigned long long evals = 0, skipped = 0;
+  unsigned long long evals = 0, skipped = 0, aligned_steps = 0;
 
   // warp-uniform trip count: the tail of the loop body is warp-aggregated
   for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < p.W; base += stride) {
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
       if (p.cardioid_mode == NM_CARDIOID_ALL || (p.cardioid_mode == NM_CARDIOID_MASK && p.mask[pix])) {
         p.out[pix].iterations = p.N;
         p.out[pix].smoothing = 0.0f;
-        p.init_j[w] = -1;
+        p.fresh.j[w] = -1;
         skipped++;
       } else {
         int r = pix / p.nc, c = pix - r * p.nc;
@@ -265,16 +266,30 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
           p.out[pix].iterations = found;
           p.out[pix].smoothing = s;
           if (unc) push_fixup(p.ctr, p.fix, p.fix_cap, pix, mag);
-          p.init_j[w] = -1;
+          p.fresh.j[w] = -1;
         } else if (L >= p.N) {  // loop 'for (i = d.size(); i < N; i++)' (212) is empty
           p.out[pix].iterations = p.N;
           p.out[pix].smoothing = 0.0f;
-          p.init_j[w] = -1;
+          p.fresh.j[w] = -1;
         } else {
           // ---- hand over to K3: delta paired with Z[L] = X[L-1] ---------------------------------
-          p.init_d[w] = make_double2(d.re, d.im);
-          p.init_j[w] = L;
-          handoff_L = L;
+          double dr = d.re, di = d.im;
+          int j = L, off = -1;
+          bool cont = true;
+          if (p.align4) {  // k3_fast works on indices that are multiples of 4: take up to 3 exact steps here
+            int steps = 0;
+            cont = advance_checked(p.ck, pix, se.er, se.ei, off, dr, di, j, (4 - (L & 3)) & 3, &steps);
+            aligned_steps += (unsigned long long)steps;
+          }
+          if (cont) {
+            p.fresh.d[w] = make_double2(dr, di);
+            p.fresh.j[w] = j;
+            p.fresh.off[w] = off;
+            p.fresh.pix[w] = pix;
+            handoff_L = j;
+          } else {
+            p.fresh.j[w] = -1;
+          }
         }
       }
     }
@@ -289,8 +304,10 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
   for (int o = 16; o; o >>= 1) {
     evals += __shfl_xor_sync(FULL_MASK, evals, o);
     skipped += __shfl_xor_sync(FULL_MASK, skipped, o);
+    aligned_steps += __shfl_xor_sync(FULL_MASK, aligned_steps, o);
   }
   if (lane == 0) {
+    if (aligned_steps) atomicAdd(&p.ctr[CTR_EXECUTED], aligned_steps);
     if (evals) atomicAdd(&p.ctr[CTR_SERIES], evals);
     if (skipped) atomicAdd(&p.ctr[CTR_SKIPPED], skipped);
   }
@@ -361,8 +378,10 @@ __global__ void __launch_bounds__(1024) k2_scan(const unsigned* hist, unsigned* 
 
 // Scatter fresh work indices into start-index-sorted order (warp-aggregated slot reservation).
 // fresh_ids is pre-filled with -1 so the padding of each run reads as "no sample".
-__global__ void __launch_bounds__(256) k2_scatter(const int32_t* init_j, long long W, unsigned* cursor,
+__global__ void __launch_bounds__(256) k2_scatter(const int32_t* init_j, long long W_fixed,
+                                                  const unsigned long long* W_ptr, unsigned* cursor,
                                                   int32_t* fresh_ids) {
+  const long long W = W_ptr ? (long long)*W_ptr : W_fixed;
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < W; base += stride) {

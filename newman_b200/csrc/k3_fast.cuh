@@ -1,61 +1,84 @@
 // K3 (fast path, NM_MODE_REQUEUE) — same arithmetic as k3_perturb.cuh (see there for the operation
-// order, the table layout and the level/chunk scheduling), re-organised around what ncu showed for
-// the first version (profiles/r01a_k3_level_v1_metrics.txt): the FP64 pipe was only 44 % busy
-// because the shared-memory pipe was 93 % busy — a warp-wide 16-byte load returns 512 B through a
-// 128 B/clk path (4 wavefronts even when every lane reads the same address), i.e. as many SM
-// cycles per iteration as the FP64 work itself, doubled again by bank conflicts once lanes had
-// drifted to different orbit indices.
+// order, the table layout and the level/chunk scheduling), re-organised around what ncu showed
+// (profiles/): the simple kernel kept the FP64 pipe only 44 % busy because the shared-memory pipe
+// was 93 % busy — a warp-wide 16-byte load returns 512 B through a 128 B/clk path (4 wavefronts
+// even when every lane reads the same address), as many SM cycles per iteration as the FP64 work.
 //
-// Here every lane carries P pixels that sit at the SAME orbit index j, so one Z[j+1] / glitch-bound
-// load feeds P delta updates (shared-memory wavefronts per pixel-iteration drop ~8x), and the P
-// independent dependency chains give the FP64 pipe ILP. Within a lane the P pixels advance in lock
-// step from where they were picked up to the end of the chunk. Survivors of the previous chunk all
-// start at the chunk boundary; fresh pixels from K2 are grouped by their exact start index L (runs
-// padded to a multiple of P by the scatter), so a group always shares j.
-//
-// Inner loop: blocks of 4 iterations without any branch. Per iteration and pixel: 10 FP64
+// k3_fast<P>: every lane carries P pixels that sit at the SAME orbit index j, so one Z[j+1] /
+// glitch-bound load feeds P delta updates (shared-memory wavefronts per pixel-iteration drop ~4P x)
+// and the P independent dependency chains give the FP64 pipe ILP. All states handled here have
+// j == 0 (mod 4) and advance in branch-free blocks of 4 iterations: per iteration and pixel 10 FP64
 // instructions + one integer compare that ORs "high word of |z|^2 <= high word of the glitch bound"
-// into a flag; the escape test is made once per block on the last |z|^2 (once |z| > 1024 it grows
-// monotonically and cannot overflow within 3 more steps). A flagged block is replayed from its
-// saved start state one step at a time with the exact double comparisons, so every decision is
-// identical to the simple kernel and to the oracle.
+// into a per-pixel flag; the escape test is made once per block on the last |z|^2 (once |z| > 1024
+// it grows monotonically and cannot overflow within 3 more steps).
 //
-// The pass is warp-synchronous: the block loop's trip condition is a warp vote, lanes whose block
-// was flagged (or that have < 4 steps left) take the checked steps together in one converged
-// section, and escapes are only *recorded* there (pixel, iteration, |z|^2) with one warp-aggregated
-// reservation per slot; the smoothing logarithms run afterwards in k3_smooth over the dense list.
-// (An earlier version let each lane loop on its own: after the first escape the lanes of a warp
-// drifted apart and the level where most pixels escape ran 3x slower than a full level.)
+// Nothing is decided inside this kernel. A pixel whose block was flagged is rolled back to the
+// block's start state and EXPORTED (state, index) while its lane-mates simply keep their end-of-
+// block state; so is a pixel that cannot take another whole block (iteration limit or end of the
+// orbit table less than 4 steps away). Exported pixels are parked on the reference orbit itself
+// (delta = eps = 0, which stays 0 and never flags) until the lane's pass through the chunk ends, and
+// are appended to the event queue with the same warp-aggregated reservation as the survivors that
+// move on to the next chunk. k3_events then replays at most 4 checked steps per exported pixel with
+// the exact double comparisons — escape (+ smoothing), glitch (-> re-queue list), iteration limit,
+// rebase at the end of the orbit, or "false alarm" (-> carried into the next sweep, index again a
+// multiple of 4). Every decision is therefore the one k3_perturb.cuh and the oracle take.
+//
+// (Two earlier versions replayed flagged blocks inside the warp; on the level where half of the
+// pixels escape that cost 3x, later 1.6x, the time of a full level, and latency-bound tail levels
+// ran 5x slower than the simple kernel — profiles/r01b_*.)
 #pragma once
+#include "k3_checked.cuh"
 #include "k3_perturb.cuh"
 
 namespace nm {
 
 constexpr int K3F_THREADS = 256;
 
-struct __align__(16) EscRec {  // an escaped pixel waiting for its smoothing value
-  int32_t pix;
-  int32_t it;
-  double r2;
-};
+__global__ void __launch_bounds__(256) k3_events(CheckedParams p, const double* eps_re, const double* eps_im, int nc,
+                                                 const PixState* events, const unsigned long long* count,
+                                                 FreshArrays carry, unsigned long long* carry_count, unsigned* hist) {
+  const unsigned long long n = *count;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long executed = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    PixState e = events[i];
+    const int r = e.pix / nc, c = e.pix - r * nc;
+    int steps = 0;
+    if (advance_checked(p, e.pix, eps_re[c], eps_im[r], e.off, e.dr, e.di, e.j, 4, &steps)) {
+      // carried into the next sweep (index is a multiple of 4 again: 0 after a rebase, block start + 4 else)
+      unsigned long long slot = atomicAdd(carry_count, 1ULL);
+      carry.d[slot] = make_double2(e.dr, e.di);
+      carry.j[slot] = e.j;
+      carry.off[slot] = e.off;
+      carry.pix[slot] = e.pix;
+      atomicAdd(&hist[e.j], 1u);
+    }
+    executed += (unsigned long long)steps;
+  }
+  for (int o = 16; o; o >>= 1) executed += __shfl_xor_sync(FULL_MASK, executed, o);
+  if ((threadIdx.x & 31) == 0 && executed) {
+    atomicAdd(&p.ctr[CTR_EXECUTED], executed);
+    atomicAdd(&p.ctr[CTR_CHECKED], executed);
+  }
+}
 
 template <int P>
-__global__ void __launch_bounds__(K3F_THREADS) k3_fast(K3Params p, EscRec* esc_list) {
+__global__ void __launch_bounds__(K3F_THREADS, (P == 4 ? 2 : 3))
+k3_fast(K3Params p, PixState* events) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
   const int jbase = p.k * CH;
   int nload = p.Jmax + 1 - jbase;
   if (nload > CH + 1) nload = CH + 1;
-  const int nload4 = (nload + 1) & ~1;  // bulk copies move multiples of 16 bytes
+  const int nload2 = (nload + 1) & ~1;  // bulk copies move multiples of 16 bytes
   double2* sZ = (double2*)smem_raw;
-  double* sGB = (double*)(smem_raw + (size_t)(CH + 4) * sizeof(double2));  // full glitch bounds gb[j]
-  const int32_t* sG = (const int32_t*)sGB;                                 // their high words: sG[2*i + 1]
+  const int32_t* sG = (const int32_t*)(smem_raw + (size_t)(CH + 4) * sizeof(double2));  // gb[] doubles; high word at [2i+1]
   __shared__ __align__(8) uint64_t bar;
 
   const unsigned long long n_cur = p.cur_count ? *p.cur_count : 0ULL;
   unsigned long long n_fresh = 0;
   unsigned fresh_begin = 0;
-  if (p.fresh_off) {
+  {
     int l1 = jbase + CH;
     if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
     fresh_begin = p.fresh_off[jbase];
@@ -72,23 +95,27 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_fast(K3Params p, EscRec* esc_l
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t bz = (uint32_t)nload * (uint32_t)sizeof(double2);
-    uint32_t bg = (uint32_t)nload4 * (uint32_t)sizeof(double);
+    uint32_t bg = (uint32_t)nload2 * (uint32_t)sizeof(double);
     mbar_expect_tx(&bar, bz + bg);
     bulk_g2s(sZ, p.Z + jbase, bz, &bar);
-    bulk_g2s(sGB, p.gb + jbase, bg, &bar);
+    bulk_g2s((void*)sG, p.gb + jbase, bg, &bar);
   }
 
   const int lane = threadIdx.x & 31;
   const int jend = jbase + CH;
   const int jcap = jend < p.Jmax ? jend : p.Jmax;  // a pass can never step beyond this index
 
-  double dr[P], di[P], er[P], ei[P];
-  int pix[P], off[P];
+  // slot state: 0 empty/parked, 1 live, 2 exported (ev_* hold the state to hand to k3_events)
+  double dr[P], di[P], er[P], ei[P], ev_dr[P], ev_di[P];
+  int pix[P], off[P], st[P], ev_j[P];
   bool drained = false;
   int j = 0;
-  unsigned long long executed = 0, rebased = 0, checked = 0;
+  unsigned long long executed = 0;
 #pragma unroll
-  for (int s = 0; s < P; ++s) { dr[s] = di[s] = er[s] = ei[s] = 0.0; pix[s] = -1; off[s] = -1; }
+  for (int s = 0; s < P; ++s) {
+    dr[s] = di[s] = er[s] = ei[s] = ev_dr[s] = ev_di[s] = 0.0;
+    pix[s] = -1; off[s] = -1; st[s] = 0; ev_j[s] = 0;
+  }
 
   mbar_wait(&bar, 0);
 
@@ -108,25 +135,25 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_fast(K3Params p, EscRec* esc_l
         if (g < g_total) {
 #pragma unroll
           for (int s = 0; s < P; ++s) {
-            dr[s] = di[s] = er[s] = ei[s] = 0.0; pix[s] = -1; off[s] = -1;
+            dr[s] = di[s] = er[s] = ei[s] = 0.0; pix[s] = -1; off[s] = -1; st[s] = 0;
             if (g < g_cur) {
               unsigned long long idx = g * P + s;
               if (idx < n_cur) {
-                PixState st = p.cur[idx];
-                dr[s] = st.dr; di[s] = st.di; pix[s] = st.pix; off[s] = st.off; j = st.j;
+                PixState q = p.cur[idx];
+                dr[s] = q.dr; di[s] = q.di; pix[s] = q.pix; off[s] = q.off; j = q.j;
               }
             } else {
               int w = p.fresh_ids[fresh_begin + (unsigned)((g - g_cur) * P + s)];
               if (w >= 0) {
-                double2 d0 = p.init_d[w];
-                dr[s] = d0.x; di[s] = d0.y; off[s] = -1; j = p.init_j[w];
-                pix[s] = p.pix_list ? p.pix_list[w] : w;
+                double2 d0 = p.fresh.d[w];
+                dr[s] = d0.x; di[s] = d0.y; off[s] = p.fresh.off[w]; j = p.fresh.j[w]; pix[s] = p.fresh.pix[w];
               }
             }
             if (pix[s] >= 0) {
               int r = pix[s] / p.nc, c = pix[s] - r * p.nc;
               er[s] = p.eps_re[c];
               ei[s] = p.eps_im[r];
+              st[s] = 1;
               lane_active = true;
             }
           }
@@ -138,30 +165,31 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_fast(K3Params p, EscRec* esc_l
     // ---- one warp-synchronous pass through the chunk -----------------------------------------------
     const int j_in = j;  // every slot of this lane's group entered at this index
     for (;;) {
-      // this lane's stop index: chunk end / end of the orbit table / nearest iteration limit
-      int jstop = jcap;
+      // Export the live slots that cannot take another whole block before the chunk end / table end /
+      // their iteration limit — unless they simply reached the chunk end with room beyond it: those
+      // move on to the next level after the loop. nb = whole blocks every remaining live slot can take.
+      int nb = 0x7fffffff;
       bool any_live = false;
 #pragma unroll
       for (int s = 0; s < P; ++s)
-        if (pix[s] >= 0) {
-          any_live = true;
-          int jN = p.N - 1 - off[s];
-          if (jN < jstop) jstop = jN;
+        if (st[s] == 1) {
+          const int jN = p.N - 1 - off[s];
+          const int lim = jcap < jN ? jcap : jN;
+          const int room = (lim - j) >> 2;
+          if (room > 0) { any_live = true; if (room < nb) nb = room; }
+          else if (!(j == jend && j < p.Jmax && jN > j)) {
+            st[s] = 2; ev_dr[s] = dr[s]; ev_di[s] = di[s]; ev_j[s] = j;
+            executed += (unsigned long long)(j - j_in);
+            dr[s] = di[s] = er[s] = ei[s] = 0.0;
+          }
         }
-      const bool running = lane_active && any_live && j < jstop;
-      if (!__any_sync(FULL_MASK, running)) break;
+      if (!(lane_active && any_live)) nb = 0;
+      if (!__any_sync(FULL_MASK, nb > 0)) break;
 
-      // fast blocks: the whole warp advances block by block; as soon as any lane's block is flagged
-      // the warp leaves the loop so that lane can take its checked steps while the others wait 4
-      // steps ahead of nobody (they are at the same index again afterwards)
-      bool flagged = false;
-      bool cand[P];  // slots whose checks must be repeated exactly (all of them for a short tail)
-#pragma unroll
-      for (int s = 0; s < P; ++s) cand[s] = true;
-      for (;;) {
-        const bool can = running && (jstop - j >= 4);
-        if (!__any_sync(FULL_MASK, can)) break;
-        if (can) {
+      // nb branch-free blocks; a flagged slot is rolled back, exported and parked on the spot, its
+      // lane-mates keep going (their limits can only be farther away, so nb stays valid)
+      for (int b = 0; __any_sync(FULL_MASK, b < nb); ++b) {
+        if (b < nb) {
           double dr0[P], di0[P];
 #pragma unroll
           for (int s = 0; s < P; ++s) { dr0[s] = dr[s]; di0[s] = di[s]; }
@@ -193,148 +221,42 @@ __global__ void __launch_bounds__(K3F_THREADS) k3_fast(K3Params p, EscRec* esc_l
           bool any_bad = false;
 #pragma unroll
           for (int s = 0; s < P; ++s) { bad[s] = bad[s] || (hi_last[s] >= ESC_HI); any_bad = any_bad || bad[s]; }
-          if (any_bad) {  // replay this block with exact checks (below, together with the other lanes)
+          if (any_bad) {
 #pragma unroll
-            for (int s = 0; s < P; ++s) { dr[s] = dr0[s]; di[s] = di0[s]; cand[s] = bad[s]; }
-            flagged = true;
-          } else {
-            j += 4;
-          }
-        }
-        if (__any_sync(FULL_MASK, flagged)) break;
-      }
-
-      // checked steps (converged): a flagged block, or the < 4 iterations left before jstop
-      int nslow = (running && (flagged || jstop - j < 4)) ? jstop - j : 0;
-      if (nslow > 4) nslow = 4;
-      checked += (unsigned long long)nslow;
-      bool esc[P], glt[P];
-      int ev_it[P];
-      double ev_r2[P];
-#pragma unroll
-      for (int s = 0; s < P; ++s) { esc[s] = glt[s] = false; ev_it[s] = 0; ev_r2[s] = 0.0; }
-      if (nslow > 0) {
-        double2 x = sZ[j - jbase];
-        for (int t = 0; t < nslow; ++t) {
-          const double2 y = sZ[j + 1 - jbase];
-          ++j;
-#pragma unroll
-          for (int s = 0; s < P; ++s) {
-            double wr = __fma_rn(2.0, x.x, dr[s]);
-            double wi = __fma_rn(2.0, x.y, di[s]);
-            double ndr = __fma_rn(-di[s], wi, __fma_rn(dr[s], wr, er[s]));
-            double ndi = __fma_rn(di[s], wr, __fma_rn(dr[s], wi, ei[s]));
-            dr[s] = ndr; di[s] = ndi;
-            if (cand[s] && pix[s] >= 0 && !esc[s] && !glt[s]) {
-              double zr = y.x + ndr, zi = y.y + ndi;
-              double zmag = __fma_rn(zi, zi, zr * zr);
-              if (zmag > BAILOUT2) {
-                esc[s] = true;
-                ev_it[s] = j + off[s];
-                ev_r2[s] = zr * zr + zi * zi;  // sqMag as the reference forms it (complex.h:23)
-              } else if (j != p.Jmax && zmag < sGB[j - jbase]) {
-                glt[s] = true;
-                ev_it[s] = j + off[s];
-              }
-              if (esc[s] || glt[s]) {  // finished: park the slot on the reference orbit (delta = eps = 0)
-                dr[s] = di[s] = er[s] = ei[s] = 0.0;
+            for (int s = 0; s < P; ++s)
+              if (st[s] == 1 && bad[s]) {
+                st[s] = 2; ev_dr[s] = dr0[s]; ev_di[s] = di0[s]; ev_j[s] = j;
                 executed += (unsigned long long)(j - j_in);
+                dr[s] = di[s] = er[s] = ei[s] = 0.0;
               }
-            }
           }
-          x = y;
+          j += 4;
         }
-      }
-      // record the events of this section: one reservation per slot for the whole warp
-      bool any_ev = false;
-#pragma unroll
-      for (int s = 0; s < P; ++s) any_ev = any_ev || esc[s] || glt[s];
-      if (__any_sync(FULL_MASK, any_ev))
-#pragma unroll
-      for (int s = 0; s < P; ++s) {
-        unsigned long long slot = warp_reserve(&p.ctr[CTR_ESCAPED], esc[s]);
-        if (esc[s]) {
-          EscRec e; e.pix = pix[s]; e.it = ev_it[s]; e.r2 = ev_r2[s];
-          esc_list[slot] = e;
-          pix[s] = -1;
-        }
-        slot = warp_reserve(&p.ctr[CTR_REQUEUE], glt[s]);
-        if (glt[s]) {
-          p.rq_pix[slot] = pix[s];
-          p.rq_iter[slot] = ev_it[s];
-          p.out[pix[s]].iterations = -1;
-          p.out[pix[s]].smoothing = 0.0f;
-          pix[s] = -1;
-        }
-      }
-      // iteration limit reached by some pixels of this lane: (N, 0)   (mandelbrot.cpp:226-228)
-      if (running && j == jstop) {
-#pragma unroll
-        for (int s = 0; s < P; ++s)
-          if (pix[s] >= 0 && j + off[s] + 1 >= p.N) {
-            p.out[pix[s]].iterations = p.N;
-            p.out[pix[s]].smoothing = 0.0f;
-            pix[s] = -1;
-            dr[s] = di[s] = er[s] = ei[s] = 0.0;
-            executed += (unsigned long long)(j - j_in);
-          }
       }
     }
 
-    // ---- hand the survivors on (converged; warp-aggregated appends) -----------------------------
+    // ---- hand over (converged; warp-aggregated appends) --------------------------------------------
 #pragma unroll
     for (int s = 0; s < P; ++s) {
-      bool live = lane_active && pix[s] >= 0;
-      if (live) executed += (unsigned long long)(j - j_in);
-      bool rebase = live && j == p.Jmax;
-      bool toNext = live && !rebase && j == jend;
-      if (rebase) {
-        // continue from the virtual iterate Z[0] = 0 with delta = z (exact algebra: z' = z^2 + c)
-        double2 xj = sZ[j - jbase];
-        dr[s] = xj.x + dr[s];
-        di[s] = xj.y + di[s];
-        rebased++;
-      }
-      unsigned long long slot = warp_reserve(p.restart_count, rebase);
-      if (rebase) {
-        PixState st; st.dr = dr[s]; st.di = di[s]; st.pix = pix[s]; st.j = 0; st.off = j + off[s]; st.pad = 0;
-        p.restart[slot] = st;
-      }
-      slot = warp_reserve(p.next_count, toNext);
+      const bool toNext = lane_active && st[s] == 1;   // reached the chunk end alive
+      const bool toEvents = lane_active && st[s] == 2;
+      if (toNext) executed += (unsigned long long)(j - j_in);
+      unsigned long long slot = warp_reserve(p.next_count, toNext);
       if (toNext) {
-        PixState st; st.dr = dr[s]; st.di = di[s]; st.pix = pix[s]; st.j = j; st.off = off[s]; st.pad = 0;
-        p.next[slot] = st;
+        PixState q; q.dr = dr[s]; q.di = di[s]; q.pix = pix[s]; q.j = j; q.off = off[s]; q.pad = 0;
+        p.next[slot] = q;
       }
-      pix[s] = -1;
+      slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
+      if (toEvents) {
+        PixState q; q.dr = ev_dr[s]; q.di = ev_di[s]; q.pix = pix[s]; q.j = ev_j[s]; q.off = off[s]; q.pad = 0;
+        events[slot] = q;
+      }
+      st[s] = 0; pix[s] = -1;
     }
   }
 
-  for (int o = 16; o; o >>= 1) {
-    executed += __shfl_xor_sync(FULL_MASK, executed, o);
-    rebased += __shfl_xor_sync(FULL_MASK, rebased, o);
-    checked += __shfl_xor_sync(FULL_MASK, checked, o);
-  }
-  if (lane == 0) {
-    if (executed) atomicAdd(&p.ctr[CTR_EXECUTED], executed);
-    if (rebased) atomicAdd(&p.ctr[CTR_REBASED], rebased);
-    if (checked) atomicAdd(&p.ctr[CTR_CHECKED], checked);
-  }
-}
-
-// Smoothing for the escapes recorded by k3_fast (mandelbrot.cpp:133-136, 218): dense, converged.
-__global__ void __launch_bounds__(256) k3_smooth(const EscRec* list, const unsigned long long* count, nm_escape* out,
-                                                 unsigned long long* ctr, FixupRec* fix, unsigned long long fix_cap,
-                                                 double log_bailout) {
-  const unsigned long long n = *count;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    EscRec e = list[i];
-    bool unc;
-    float s = smoothing_f32(e.r2, log_bailout, &unc);
-    nm_escape v; v.iterations = e.it; v.smoothing = s;
-    out[e.pix] = v;
-    if (unc) push_fixup(ctr, fix, fix_cap, e.pix, e.r2);
-  }
+  for (int o = 16; o; o >>= 1) executed += __shfl_xor_sync(FULL_MASK, executed, o);
+  if (lane == 0 && executed) atomicAdd(&p.ctr[CTR_EXECUTED], executed);
 }
 
 }  // namespace nm

@@ -53,9 +53,7 @@ struct K3Params {
   const unsigned long long* cur_count;
   const int32_t* fresh_ids;
   const unsigned* fresh_off;   // [Jmax+2] offsets by exact start index; nullptr after sweep 0
-  const double2* init_d;
-  const int32_t* init_j;
-  const int32_t* pix_list;
+  FreshArrays fresh;           // hand-over records the fresh_ids index
   PixState* next;
   unsigned long long* next_count;
   PixState* restart;
@@ -175,11 +173,11 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
             int w = p.fresh_ids[fresh_begin + (unsigned)(idx - n_cur)];
             got = w >= 0;
             if (got) {
-              double2 d0 = p.init_d[w];
+              double2 d0 = p.fresh.d[w];
               dr = d0.x; di = d0.y;
-              j = p.init_j[w];
-              off = -1;
-              pix = p.pix_list ? p.pix_list[w] : w;
+              j = p.fresh.j[w];
+              off = p.fresh.off[w];
+              pix = p.fresh.pix[w];
             }
           }
           if (got) {

@@ -34,8 +34,17 @@ enum Counter {
   CTR_Q_CUR,          // K3: size of the current input queue
   CTR_DONE,           // K3: pixels finished
   CTR_CHECKED,        // K3 fast kernel: lane-steps taken in the checked (non-block) path
-  CTR_ESCAPED,        // K3 fast kernel: escape records waiting for k3_smooth
+  CTR_EVENTS,         // K3 fast kernel: exported pixels waiting for k3_events
+  CTR_CARRY,          // K3 fast path: states carried into the next sweep
   CTR_COUNT = 24
+};
+
+// Hand-over records between K2 / carry-over and K3 ("fresh" entries), SoA in HBM.
+struct FreshArrays {
+  double2* d;     // delta
+  int32_t* j;     // table index, or -1: not a K3 state
+  int32_t* off;   // it = j + off
+  int32_t* pix;   // pixel id
 };
 
 struct FixupRec {  // smoothing value to be re-evaluated with the host libm

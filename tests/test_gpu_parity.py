@@ -94,7 +94,7 @@ def test_k3_kernel_variants_agree(dev, kat, group):
         gpix, git = dev.requeue()
         gs = dev.stats()
     finally:
-        dev.set_option(newman_b200._lib.OPT_K3_GROUP, 2)
+        dev.set_option(newman_b200._lib.OPT_K3_GROUP, 4)
     assert np.array_equal(out["iterations"], exp["iterations"])
     assert np.array_equal(bits(out["smoothing"]), bits(exp["smoothing"]))
     o1 = np.argsort(gpix); o2 = np.argsort(rq_pix)

@@ -7,7 +7,7 @@ import newman_b200
 d = newman_b200.Device(0)
 info = d.info()
 res = {"device": info}
-for kind, name in ((0, "dfma"), (1, "dadd"), (2, "dmul")):
+for kind, name in ((0, "dfma"), (1, "dadd"), (2, "dmul"), (3, "k3mix")):
     d.fp64_peak(kind, 1 << 12)
     best = 0
     for it in (1 << 15, 1 << 17):
