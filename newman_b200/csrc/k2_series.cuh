@@ -313,17 +313,11 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
   }
 }
 
-// Per-index filter thresholds + their prefix minima/maxima. One CTA; each thread owns a contiguous
-// segment (pixel-independent, O(M) once per frame).
-__global__ void __launch_bounds__(1024) k2_prepare(const double2* B, const double2* C, int M, double tol, K2Filter f) {
-  __shared__ double s_rlog[1024], s_ov[1024], s_a[1024], s_b[1024];
-  const int t = threadIdx.x, nt = blockDim.x;
-  const int seg = (M + nt - 1) / nt;
-  const int i0 = t * seg, i1 = min(M, i0 + seg);
+// Per-index filter thresholds (pixel-independent, O(M) once per frame): any grid.
+__global__ void __launch_bounds__(256) k2_prepare(const double2* B, const double2* C, int M, double tol, K2Filter f) {
   const double lt = log2(tol);
   const double lt_neg = fmin(lt, 0.0), lt_pos = fmax(lt, 0.0);
-  double m_rlog = INFINITY, m_ov = INFINITY, m_a = INFINITY, m_b = -INFINITY;
-  for (int i = i0; i < i1; ++i) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     double rlog = INFINITY, a = INFINITY, b = -INFINITY, ov = INFINITY;
     if (i >= 1) {
       double2 Bi = B[i], Ci = C[i];
@@ -338,15 +332,38 @@ __global__ void __launch_bounds__(1024) k2_prepare(const double2* B, const doubl
       }
     }
     f.rlog[i] = rlog; f.a[i] = a; f.b[i] = b; f.ov[i] = ov;
-    m_rlog = fmin(m_rlog, rlog); m_ov = fmin(m_ov, ov); m_a = fmin(m_a, a); m_b = fmax(m_b, b);
+  }
+}
+
+// Their prefix minima/maxima: one CTA, each thread owns a contiguous segment, segment totals are
+// combined with a warp-shuffle scan.
+__global__ void __launch_bounds__(1024) k2_prefix(int M, K2Filter f) {
+  __shared__ double s_rlog[32], s_ov[32], s_a[32], s_b[32];
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, wid = t >> 5;
+  const int seg = (M + nt - 1) / nt;
+  const int i0 = min(M, t * seg), i1 = min(M, i0 + seg);
+  double m_rlog = INFINITY, m_ov = INFINITY, m_a = INFINITY, m_b = -INFINITY;
+  for (int i = i0; i < i1; ++i) {
+    m_rlog = fmin(m_rlog, f.rlog[i]); m_ov = fmin(m_ov, f.ov[i]); m_a = fmin(m_a, f.a[i]); m_b = fmax(m_b, f.b[i]);
     f.pmin_rlog[i] = m_rlog; f.pmin_ov[i] = m_ov; f.pmin_a[i] = m_a; f.pmax_b[i] = m_b;
   }
-  s_rlog[t] = m_rlog; s_ov[t] = m_ov; s_a[t] = m_a; s_b[t] = m_b;
-  __syncthreads();
-  double c_rlog = INFINITY, c_ov = INFINITY, c_a = INFINITY, c_b = -INFINITY;
-  for (int s = 0; s < t; ++s) {
-    c_rlog = fmin(c_rlog, s_rlog[s]); c_ov = fmin(c_ov, s_ov[s]); c_a = fmin(c_a, s_a[s]); c_b = fmax(c_b, s_b[s]);
+  // inclusive scan of the segment totals inside each warp, then across warps
+  double w_rlog = m_rlog, w_ov = m_ov, w_a = m_a, w_b = m_b;
+  for (int o = 1; o < 32; o <<= 1) {
+    double r = __shfl_up_sync(FULL_MASK, w_rlog, o), v = __shfl_up_sync(FULL_MASK, w_ov, o);
+    double a = __shfl_up_sync(FULL_MASK, w_a, o), b = __shfl_up_sync(FULL_MASK, w_b, o);
+    if (lane >= o) { w_rlog = fmin(w_rlog, r); w_ov = fmin(w_ov, v); w_a = fmin(w_a, a); w_b = fmax(w_b, b); }
   }
+  if (lane == 31) { s_rlog[wid] = w_rlog; s_ov[wid] = w_ov; s_a[wid] = w_a; s_b[wid] = w_b; }
+  __syncthreads();
+  // carry-in of this thread = totals of all earlier threads
+  double c_rlog = INFINITY, c_ov = INFINITY, c_a = INFINITY, c_b = -INFINITY;
+  for (int w = 0; w < wid; ++w) {
+    c_rlog = fmin(c_rlog, s_rlog[w]); c_ov = fmin(c_ov, s_ov[w]); c_a = fmin(c_a, s_a[w]); c_b = fmax(c_b, s_b[w]);
+  }
+  double e_rlog = __shfl_up_sync(FULL_MASK, w_rlog, 1), e_ov = __shfl_up_sync(FULL_MASK, w_ov, 1);
+  double e_a = __shfl_up_sync(FULL_MASK, w_a, 1), e_b = __shfl_up_sync(FULL_MASK, w_b, 1);
+  if (lane > 0) { c_rlog = fmin(c_rlog, e_rlog); c_ov = fmin(c_ov, e_ov); c_a = fmin(c_a, e_a); c_b = fmax(c_b, e_b); }
   for (int i = i0; i < i1; ++i) {
     f.pmin_rlog[i] = fmin(f.pmin_rlog[i], c_rlog);
     f.pmin_ov[i] = fmin(f.pmin_ov[i], c_ov);
@@ -359,21 +376,26 @@ __global__ void __launch_bounds__(1024) k2_prepare(const double2* B, const doubl
 // per-lane pixel group of k3_fast): offs[L] .. offs[L+1] holds the samples that start at L, padded
 // with -1. One CTA, each thread owns a contiguous segment of the n bins.
 __global__ void __launch_bounds__(1024) k2_scan(const unsigned* hist, unsigned* offs, unsigned* cursor, int n, unsigned G) {
-  __shared__ unsigned s_tot[1024];
-  const int t = threadIdx.x, nt = blockDim.x;
+  __shared__ unsigned s_tot[32];
+  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, wid = t >> 5;
   const int seg = (n + nt - 1) / nt;
-  const int i0 = t * seg, i1 = min(n, i0 + seg);
+  const int i0 = min(n, t * seg), i1 = min(n, i0 + seg);
   unsigned acc = 0;
   for (int i = i0; i < i1; ++i) acc += (hist[i] + G - 1) / G * G;
-  s_tot[t] = acc;
+  unsigned incl = acc;  // inclusive scan over the warp
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned v = __shfl_up_sync(FULL_MASK, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_tot[wid] = incl;
   __syncthreads();
-  unsigned base = 0;
-  for (int s = 0; s < t; ++s) base += s_tot[s];
+  unsigned base = incl - acc;
+  for (int w = 0; w < wid; ++w) base += s_tot[w];
   for (int i = i0; i < i1; ++i) {
     offs[i] = base; cursor[i] = base;
     base += (hist[i] + G - 1) / G * G;
   }
-  if (i1 == n && i0 <= n) offs[n] = base;  // the owner of the last segment (or an empty tail thread: same value)
+  if (i1 == n) offs[n] = base;  // last owner and any empty tail thread agree on the grand total
 }
 
 // Scatter fresh work indices into start-index-sorted order (warp-aggregated slot reservation).

@@ -60,7 +60,7 @@ mp_bitcnt_t max_prec(const HPComplex& a, const HPComplex& b) {
 Mandelbrot::Mandelbrot() : Mandelbrot(1, 1) {}
 
 Mandelbrot::Mandelbrot(int nr, int nc)
-    : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(2), device(0), host_threads(0) {
+    : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(1), device(0), host_threads(0) {
   // default full view (mandelbrot.cpp:13-14)
   center.re = -0.5;
   center.im = 0.0;

@@ -291,9 +291,11 @@ int launch_deep(nm_ctx* ctx) {
     const size_t Mn = (size_t)ctx->M;
     k2.f.rlog = fb; k2.f.a = fb + Mn; k2.f.b = fb + 2 * Mn; k2.f.ov = fb + 3 * Mn;
     k2.f.pmin_rlog = fb + 4 * Mn; k2.f.pmin_ov = fb + 5 * Mn; k2.f.pmin_a = fb + 6 * Mn; k2.f.pmax_b = fb + 7 * Mn;
-    k2_prepare<<<1, 1024, 0, st>>>(k2.B, k2.C, ctx->M, ctx->tol, k2.f);
+    k2_prepare<<<(ctx->M + 255) / 256, 256, 0, st>>>(k2.B, k2.C, ctx->M, ctx->tol, k2.f);
     NM_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches++;
+    k2_prefix<<<1, 1024, 0, st>>>(ctx->M, k2.f);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 2;
     k2_series<false><<<(unsigned)b2, K2_THREADS, 0, st>>>(k2);
   } else {
     k2_series<true><<<(unsigned)b2, K2_THREADS, 0, st>>>(k2);

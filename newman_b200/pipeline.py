@@ -49,7 +49,7 @@ def local_rows(nr, rank, world):
     return np.arange(rank, nr, world, dtype=np.int64)
 
 
-def render_rounds(dev, primary, secondary_tables, nc, rows, max_secondary=2, cardioid_mode=L.CARDIOID_NONE,
+def render_rounds(dev, primary, secondary_tables, nc, rows, max_secondary=1, cardioid_mode=L.CARDIOID_NONE,
                   mask=None, reduce_pick=None, eps_rows=None):
     """Run primary + secondary rounds on `dev` for the grid rows `rows` (global row indices).
 

@@ -25,7 +25,7 @@ def mk(k, **kw):
                                   tol=k.get("tol", 1e-10), **kw)
 
 
-def oracle_frame(m, N, tol, max_secondary=2):
+def oracle_frame(m, N, tol, max_secondary=1):
     """Oracle-P through the same round orchestration, tables from the host C++ (pinned elsewhere)."""
     nc = m.cols()
     mkts = lambda d: pipeline.TableSet(d, N, tol, 1e-6)
