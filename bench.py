@@ -233,36 +233,42 @@ def run_ours(args):
 
     def bcast_tables(row, col):
         """rank 0: host arbitrary-precision work (C++/GMP, threaded) -> device tensors -> NCCL broadcast."""
-        keys = ("x_hi", "x_lo", "a", "b", "c", "eps_re", "eps_im")
         if rank == 0:
             t0 = time.perf_counter()
             h = view.host_tables(row, col)
             host_pre[0] += time.perf_counter() - t0
-            meta = torch.tensor([h["M"], h["has_escape"], h["probe"][0], h["probe"][1]], dtype=torch.int64, device=devt)
+            fe = pipeline.floatexp_level(h, cfg.get("floatexp", 0))
+            hs = pipeline.TableSet(h, N, cfg["tol"], 1e-6, fe)   # picks the double or mantissa/exponent arrays
+            meta = torch.tensor([h["M"], h["has_escape"], h["probe"][0], h["probe"][1], fe], dtype=torch.int64, device=devt)
         else:
-            h = None
-            meta = torch.zeros(4, dtype=torch.int64, device=devt)
+            hs = None
+            meta = torch.zeros(5, dtype=torch.int64, device=devt)
         if world > 1:
             dist.broadcast(meta, 0)
-        M, he, pr, pc = [int(x) for x in meta.tolist()]
-        sizes = [2 * (M + he), 2 * M, 2 * M, 2 * M, 2 * M, nc, nr]
+        M, he, pr, pc, fe = [int(x) for x in meta.tolist()]
+        sizes = {"x_hi": 2 * (M + he), "eps_re": nc, "eps_im": nr, "eps_re_e": nc, "eps_im_e": nr}
         d = {"M": M, "has_escape": he, "probe": (pr, pc)}
-        for k, n in zip(keys, sizes):
-            t = torch.from_numpy(h[k]).to(devt) if rank == 0 else torch.empty(n, dtype=torch.float64, device=devt)
+        for k in pipeline.TableSet.keys(fe):
+            dt = torch.int32 if k.endswith("_e") else torch.float64
+            t = (torch.from_numpy(np.ascontiguousarray(hs.arr[k])).to(devt) if rank == 0
+                 else torch.empty(sizes.get(k, 2 * M), dtype=dt, device=devt))
             if world > 1:
                 dist.broadcast(t, 0)
             d[k] = t
         torch.cuda.synchronize()       # broadcasts have landed before the C-ABI copies from these buffers
-        return pipeline.TableSet(d, N, cfg["tol"], 1e-6)
+        ts = pipeline.TableSet.__new__(pipeline.TableSet)
+        ts.M, ts.has_escape, ts.fe, ts.N, ts.tol, ts.glitch_tol, ts.probe = M, he, fe, N, cfg["tol"], 1e-6, (pr, pc)
+        ts.arr = {k: d[k] for k in pipeline.TableSet.keys(fe)}
+        return ts
 
     reduce_pick = multigpu.make_reduce_pick(world, devt)
 
     eps_cache = {}
 
-    def eps_rows(ts):
-        k = id(ts)
+    def eps_rows(ts, key):
+        k = (id(ts), key)
         if k not in eps_cache:
-            e = ts.arr["eps_im"]
+            e = ts.arr[key]
             eps_cache[k] = (e[rows_t].contiguous() if isinstance(e, torch.Tensor) and e.is_cuda else
                             e[torch.as_tensor(rows)].contiguous().pin_memory() if isinstance(e, torch.Tensor) else
                             np.ascontiguousarray(e[rows]))

@@ -95,6 +95,19 @@ typedef struct nm_deep_tables {
   const double* a;      /* [2*M] descended A[i] (mandelbrot.cpp:166) */
   const double* b;      /* [2*M] descended B[i] */
   const double* c;      /* [2*M] descended C[i] */
+  /* floatexp mode (all three non-NULL): a/b/c then hold MANTISSAS with 0.5 <= |m| < 1 and these the
+   * binary exponents, value = m * 2^e per component — exactly what mpf_get_d_2exp returns (truncating,
+   * like descend). Needed from pixel pitch ~1e-97 on, where |C| leaves double range and the reference
+   * itself stops working (SIGFPE); on shallower views both modes give bit-identical rasters. */
+  const int32_t* a_exp; /* [2*M] */
+  const int32_t* b_exp;
+  const int32_t* c_exp;
+  /* floatexp eps (both non-NULL; needs the floatexp series tables): eps_re/eps_im handed to
+   * nm_frame_deep are then MANTISSAS (0.5 <= |m| < 1) and these their binary exponents. Selects the
+   * scaled perturbation states (delta = (dr, di) * 2^e, csrc/floatexp.cuh) that views below a pixel
+   * pitch of ~1e-150 need (delta*delta, then delta and eps themselves, leave double range). */
+  const int32_t* eps_re_exp; /* [nc] */
+  const int32_t* eps_im_exp; /* [nr] */
 } nm_deep_tables;
 
 #define NM_CARDIOID_NONE 0 /* no pixel of the view is inside cardioid/bulb (mandelbrot.cpp:149) */
@@ -179,7 +192,7 @@ NM_API int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t*
 typedef struct nmv_view nmv_view;
 
 typedef struct nmv_frame_info {
-  int32_t hardware, precision_bits, orbit_len, probe_row, probe_col, references;
+  int32_t hardware /* 1 plain double, 0 series+perturbation, 2 same with floatexp series, 3 floatexp series + scaled deltas */, precision_bits, orbit_len, probe_row, probe_col, references;
   uint64_t executed_iters, series_evals, skipped_pixels, glitched, rebased, fixups, kernel_launches, ambiguous;
   double host_precompute_s, device_ms, frame_s;
 } nmv_frame_info;
@@ -192,6 +205,9 @@ NM_API const char* nmv_last_error(const nmv_view* v);
 NM_API int nmv_set_view(nmv_view* v, int N, const char* sz_re, const char* sz_im, const char* c_re,
                         const char* c_im, double tol);
 NM_API int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, int device, int host_threads);
+/* force: 1 evaluate the series in floatexp, 2 also floatexp eps + scaled delta states, even where doubles
+ * suffice (both are automatic once the view needs them); 0 automatic */
+NM_API int nmv_set_floatexp(nmv_view* v, int force);
 NM_API int nmv_rows(const nmv_view* v);
 NM_API int nmv_cols(const nmv_view* v);
 NM_API int nmv_use_hardware(nmv_view* v);                          /* mandelbrot.cpp:256-259 */
@@ -220,6 +236,10 @@ NM_API int nmv_resolve(nmv_view* v, const uint8_t* pal_rgb, int n_pal, int sc, i
  * nmv_host_table (which: 0 x_hi[2*(M+has_escape)], 1 x_lo[2M], 2 a, 3 b, 4 c, 5 eps_re[nc], 6 eps_im[nr]). */
 NM_API int nmv_host_tables(nmv_view* v, int row, int col, int* has_escape, int* probe_row, int* probe_col);
 NM_API int nmv_host_table(const nmv_view* v, int which, double* out);
+/* floatexp form of the coefficients: nmv_host_table which 7/8/9 = mantissas of a/b/c (0.5 <= |m| < 1),
+ * nmv_host_table_exp which 2/3/4 = their binary exponents [2M]; likewise 10/11 = eps_re[nc] / eps_im[nr]
+ * mantissas and exponents */
+NM_API int nmv_host_table_exp(const nmv_view* v, int which, int32_t* out);
 NM_API int nmv_host_coords(nmv_view* v, double* c_re, double* c_im);       /* mandelbrot.cpp:271, 275, 234 */
 NM_API int nmv_host_cardioid(nmv_view* v, uint8_t* mask_or_null);          /* returns NM_CARDIOID_* */
 NM_API int nmv_host_in_cardioid(nmv_view* v, int r, int c);                /* mandelbrot.cpp:63-71 */

@@ -62,6 +62,7 @@ namespace newman_b200 {
 class Engine;  // GPU context + last frame; shared between copies of a Mandelbrot
 struct FrameInfo {
   bool hardware = false;
+  int floatexp = 0;                 // 0 double series, 1 floatexp series, 2 floatexp series + scaled deltas
   int precision_bits = 64, orbit_len = 0, probe_row = -1, probe_col = -1;
   int references = 0;               // reference orbits used (1 + secondary rounds)
   unsigned long long executed_iters = 0, series_evals = 0, skipped_pixels = 0, glitched = 0, rebased = 0,
@@ -92,6 +93,8 @@ public:
   int max_secondary;        // secondary reference rounds before the final rebasing pass
   int device;               // CUDA device ordinal
   int host_threads;         // probe-search threads (0 = hardware concurrency)
+  int force_floatexp;       // 0 automatic; 1 floatexp series, 2 also floatexp eps + scaled deltas, even where
+                            // doubles suffice (verification: same raster wherever both are defined)
 
   Mandelbrot();
   Mandelbrot(int nr, int nc);

@@ -32,6 +32,8 @@ class DeepTables(C.Structure):
         ("M", C.c_int32), ("N", C.c_int32), ("has_escape", C.c_int32), ("reserved", C.c_int32),
         ("tol", C.c_double), ("glitch_tol", C.c_double),
         ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
+        ("a_exp", C.c_void_p), ("b_exp", C.c_void_p), ("c_exp", C.c_void_p),      # floatexp series (or NULL)
+        ("eps_re_exp", C.c_void_p), ("eps_im_exp", C.c_void_p),                    # floatexp eps => scaled deltas
     ]
 
 

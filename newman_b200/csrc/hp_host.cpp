@@ -259,16 +259,26 @@ void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out) {
   // ---- computeSeries (mandelbrot.cpp:112-131), descending as we go --------------------------------
   // Note the reference's recurrences use the NEW A[i] in B[i] and the new A[i], B[i] in C[i].
   out.a.resize(2 * (size_t)M); out.b.resize(2 * (size_t)M); out.c.resize(2 * (size_t)M);
+  out.a_m.resize(2 * (size_t)M); out.b_m.resize(2 * (size_t)M); out.c_m.resize(2 * (size_t)M);
+  out.a_e.resize(2 * (size_t)M); out.b_e.resize(2 * (size_t)M); out.c_e.resize(2 * (size_t)M);
   {
     Mp ar(P), ai(P), br(P), bi(P), cr(P), ci(P), nar(P), nai(P), nbr(P), nbi(P), ncr(P), nci(P);
     Mp p1(P), p2(P), s(P), u(P), two(64), one(64);
     mpf_set_d(two.v, 2.0);
     mpf_set_d(one.v, 1.0);
     mpf_set_d(ar.v, 1.0);  // A[0] = 1, B[0] = C[0] = 0
+    auto split = [](mpf_srcptr x, double& m, int32_t& e) {  // x = m * 2^e, 0.5 <= |m| < 1, truncating
+      long ex = 0;
+      m = mpf_get_d_2exp(&ex, x);
+      e = (int32_t)ex;
+    };
     auto store = [&](int i) {
       out.a[2 * i] = mpf_get_d(ar.v); out.a[2 * i + 1] = mpf_get_d(ai.v);
       out.b[2 * i] = mpf_get_d(br.v); out.b[2 * i + 1] = mpf_get_d(bi.v);
       out.c[2 * i] = mpf_get_d(cr.v); out.c[2 * i + 1] = mpf_get_d(ci.v);
+      split(ar.v, out.a_m[2 * i], out.a_e[2 * i]); split(ai.v, out.a_m[2 * i + 1], out.a_e[2 * i + 1]);
+      split(br.v, out.b_m[2 * i], out.b_e[2 * i]); split(bi.v, out.b_m[2 * i + 1], out.b_e[2 * i + 1]);
+      split(cr.v, out.c_m[2 * i], out.c_e[2 * i]); split(ci.v, out.c_m[2 * i + 1], out.c_e[2 * i + 1]);
     };
     store(0);
     for (int i = 1; i < M; i++) {
@@ -309,20 +319,25 @@ void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out) {
     if (!std::isfinite(out.a[i]) || !std::isfinite(out.b[i]) || !std::isfinite(out.c[i])) out.finite = false;
 
   // ---- eps arrays: trunc((pixel - X[0])) per column / per row (mandelbrot.cpp:155-159) ------------
-  out.eps_re.resize(v.nc);
-  out.eps_im.resize(v.nr);
+  out.eps_re.resize(v.nc); out.eps_re_m.resize(v.nc); out.eps_re_e.resize(v.nc);
+  out.eps_im.resize(v.nr); out.eps_im_m.resize(v.nr); out.eps_im_e.resize(v.nr);
   {
     Mp p(P), y(P);
+    long ex = 0;
     for (int c = 0; c < v.nc; c++) {
       pixel_re(v, c, tmp.v, p.v);
       mpf_sub(y.v, p.v, X[0].re);
       out.eps_re[c] = mpf_get_d(y.v);
+      out.eps_re_m[c] = mpf_get_d_2exp(&ex, y.v); out.eps_re_e[c] = (int32_t)ex;
     }
     for (int r = 0; r < v.nr; r++) {
       pixel_im(v, r, tmp.v, p.v);
       mpf_sub(y.v, p.v, X[0].im);
       out.eps_im[r] = mpf_get_d(y.v);
+      out.eps_im_m[r] = mpf_get_d_2exp(&ex, y.v); out.eps_im_e[r] = (int32_t)ex;
     }
+    mpf_get_d_2exp(&ex, v.sz_re);
+    out.pitch_exp = (int)ex;
   }
   for (auto& x : X) { mpf_clear(x.re); mpf_clear(x.im); }
 }

@@ -29,7 +29,15 @@ struct DeepTablesHost {
   bool has_escape = false;
   int probe_row = -1, probe_col = -1;
   std::vector<double> x_hi, x_lo, a, b, c;  // interleaved re,im
+  // the same coefficients as mantissa (0.5 <= |m| < 1, truncated like descend) * 2^exponent: the
+  // floatexp form the device uses once `finite` is false
+  std::vector<double> a_m, b_m, c_m;
+  std::vector<int32_t> a_e, b_e, c_e;
   std::vector<double> eps_re, eps_im;
+  // eps as mantissa * 2^exponent (mpf_get_d_2exp, truncating): what scaled frames hand to the device
+  std::vector<double> eps_re_m, eps_im_m;
+  std::vector<int32_t> eps_re_e, eps_im_e;
+  int pitch_exp = 0;   // binary exponent of the pixel pitch sz.re
   bool finite = true;  // false: some descended coefficient is inf/nan (reference would SIGFPE)
 };
 

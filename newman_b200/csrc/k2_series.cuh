@@ -39,6 +39,7 @@
 // transforms and one round-toward-zero add; it can differ from the mpf value only if the exact sum
 // lies within 2^-106 (relative) of a double, where the mpf digits below lo would decide.
 #pragma once
+#include "floatexp.cuh"
 #include "k3_checked.cuh"
 
 namespace nm {
@@ -55,15 +56,17 @@ struct K2Filter {  // per-index thresholds in units of log2|eps| (length M each)
 };
 
 struct K2Params {
-  const double2* A;
+  const double2* A;     // descended coefficients; in floatexp mode: their mantissas (0.5 <= |m| < 1) ...
   const double2* B;
   const double2* C;
+  const int2* Ae;       // ... and binary exponents (floatexp mode only)
+  const int2* Be;
+  const int2* Ce;
   const double2* Z;     // Z[0]=0, Z[j]=X[j-1] (truncated doubles)
   const double2* Xlo;   // [M] low parts of X[i]
   int M, N;
   double tol;
-  const double* eps_re;
-  const double* eps_im;
+  EpsTab eps;           // per-column / per-row pixel offsets (mantissa + exponent in scaled frames)
   int nc;
   const int32_t* pix_list;  // nullptr: work index == pixel id
   long long W;              // number of work items
@@ -118,6 +121,14 @@ __device__ __forceinline__ double trunc_add3(double hi, double lo, double d) {
 struct SeriesEval {
   double er, ei, e2r, e2i, e3r, e3i;
   const double2 *A, *B, *C;
+  __device__ __forceinline__ void init(double r, double i) {
+    er = r; ei = i;
+    // eps2 = sq(eps): (re*re - im*im, 2.0*re*im); eps3 = eps*eps2   (mandelbrot.cpp:160-161)
+    e2r = er * er - ei * ei;
+    e2i = (2.0 * er) * ei;
+    Cplx e3 = cmul(er, ei, e2r, e2i);
+    e3r = e3.re; e3i = e3.im;
+  }
   __device__ __forceinline__ Cplx d_at(int j) const {
     Cplx r;
     if (j == 0) { r.re = er; r.im = ei; return r; }
@@ -138,6 +149,82 @@ struct SeriesEval {
     double cmag = tc.re * tc.re + tc.im * tc.im;
     return bmag * tol < cmag;
   }
+};
+
+// The same evaluator with A/B/C, eps^2, eps^3 and every intermediate in floatexp: bit-identical to
+// SeriesEval whenever the double computation neither overflows nor underflows, and defined beyond
+// (pixel pitch < 1e-97, where the reference's doubles overflow and it dies with SIGFPE).
+struct SeriesEvalFE {
+  fec eps, e2, e3;
+  const double2 *A, *B, *C;
+  const int2 *Ae, *Be, *Ce;
+  __device__ __forceinline__ void init(double er, double ei) {
+    eps.re = fe_from_double(er); eps.im = fe_from_double(ei);
+    e2 = fec_sq(eps);
+    e3 = fec_mul(eps, e2);
+  }
+  __device__ __forceinline__ void init_fe(fe er, fe ei) {
+    eps.re = er; eps.im = ei;
+    e2 = fec_sq(eps);
+    e3 = fec_mul(eps, e2);
+  }
+  __device__ __forceinline__ fec d_fe(int j) const {
+    if (j == 0) return eps;
+    fec ta = fec_mul(load(A, Ae, j), eps);
+    fec tb = fec_mul(load(B, Be, j), e2);
+    fec tc = fec_mul(load(C, Ce, j), e3);
+    return fec_add(fec_add(ta, tb), tc);
+  }
+  __device__ __forceinline__ static fec load(const double2* m, const int2* e, int i) {
+    double2 mm = m[i]; int2 ee = e[i];
+    fec r; r.re = fe_from_parts(mm.x, ee.x); r.im = fe_from_parts(mm.y, ee.y);
+    return r;
+  }
+  __device__ __forceinline__ Cplx d_at(int j) const {
+    Cplx r;
+    if (j == 0) { r.re = fe_to_double(eps.re); r.im = fe_to_double(eps.im); return r; }
+    fec ta = fec_mul(load(A, Ae, j), eps);
+    fec tb = fec_mul(load(B, Be, j), e2);
+    fec tc = fec_mul(load(C, Ce, j), e3);
+    fec d = fec_add(fec_add(ta, tb), tc);
+    r.re = fe_to_double(d.re); r.im = fe_to_double(d.im);
+    return r;
+  }
+  __device__ __forceinline__ bool unstable(int i, double tol) const {
+    fe bmag = fec_sqmag(fec_mul(load(B, Be, i), e2));
+    fe cmag = fec_sqmag(fec_mul(load(C, Ce, i), e3));
+    return fe_lt_nonneg(fe_mul(bmag, fe_from_double(tol)), cmag);
+  }
+};
+
+template <bool FE> struct SeriesSelect;
+template <> struct SeriesSelect<false> {
+  typedef SeriesEval type;
+  __device__ __forceinline__ static void bind(SeriesEval&, const int2*, const int2*, const int2*) {}
+};
+template <> struct SeriesSelect<true> {
+  typedef SeriesEvalFE type;
+  __device__ __forceinline__ static void bind(SeriesEvalFE& s, const int2* a, const int2* b, const int2* c) { s.Ae = a; s.Be = b; s.Ce = c; }
+};
+
+// eps-dependent set-up of the evaluator for plain (double eps) and scaled (floatexp eps) frames
+template <bool SCALED> struct K2Init;
+template <> struct K2Init<false> {
+  template <class SE> __device__ __forceinline__ static void init(SE& se, const EpsVal<false>& e) { se.init(e.r0, e.i0); }
+  __device__ __forceinline__ static bool is_zero(const EpsVal<false>& e) { return e.r0 == 0.0 && e.i0 == 0.0; }
+  __device__ __forceinline__ static double log2_eps(const EpsVal<false>& e) { return log2_abs(e.r0, e.i0); }
+  template <class SE> __device__ __forceinline__ static pstate state(const SE&, int) { pstate s; s.dr = s.di = 0.0; s.e = 0; return s; }
+};
+template <> struct K2Init<true> {
+  __device__ __forceinline__ static void init(SeriesEvalFE& se, const EpsVal<true>& e) { se.init_fe(e.r, e.i); }
+  __device__ __forceinline__ static bool is_zero(const EpsVal<true>& e) { return e.r.m == 0.0 && e.i.m == 0.0; }
+  // log2|eps| of a floatexp eps: bring both components to the larger exponent first
+  __device__ __forceinline__ static double log2_eps(const EpsVal<true>& e) {
+    const int E = e.r.m == 0.0 ? e.i.e : (e.i.m == 0.0 ? e.r.e : (e.r.e > e.i.e ? e.r.e : e.i.e));
+    const double a = e.r.m == 0.0 ? 0.0 : fe_scale(e.r.m, e.r.e - E), b = e.i.m == 0.0 ? 0.0 : fe_scale(e.i.m, e.i.e - E);
+    return log2_abs(a, b) + (double)E;
+  }
+  __device__ __forceinline__ static pstate state(const SeriesEvalFE& se, int j) { return state_from_fec(se.d_fe(j)); }
 };
 
 // first i in [1, M) with arr[i] <= key (arr non-increasing), else M
@@ -167,8 +254,12 @@ __device__ __forceinline__ int first_gt(const double* arr, int M, double key) {
   return lo;
 }
 
-template <bool LITERAL>
+// FEM: 0 = double series, 1 = floatexp series (double eps, plain K3 states), 2 = floatexp series +
+// floatexp eps + scaled K3 states.
+template <bool LITERAL, int FEM>
 __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
+  constexpr bool FE = FEM != 0;
+  constexpr bool SCALED = FEM == 2;
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned long long evals = 0, skipped = 0, aligned_steps = 0;
@@ -187,27 +278,24 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
         p.fresh.j[w] = -1;
         skipped++;
       } else {
-        int r = pix / p.nc, c = pix - r * p.nc;
-        SeriesEval se;
+        EpsVal<SCALED> epsv;
+        epsv.load(p.eps, pix);
+        const double eps_r = epsv.r0, eps_i = epsv.i0;  // eps as doubles (flushed to 0 below the normal range when SCALED)
+        typename SeriesSelect<FE>::type se;
         se.A = p.A; se.B = p.B; se.C = p.C;
-        se.er = p.eps_re[c];
-        se.ei = p.eps_im[r];
-        // eps2 = sq(eps): (re*re - im*im, 2.0*re*im); eps3 = eps*eps2
-        se.e2r = se.er * se.er - se.ei * se.ei;
-        se.e2i = (2.0 * se.er) * se.ei;
-        Cplx e3 = cmul(se.er, se.ei, se.e2r, se.e2i);
-        se.e3r = e3.re; se.e3i = e3.im;
+        SeriesSelect<FE>::bind(se, p.Ae, p.Be, p.Ce);
+        K2Init<SCALED>::init(se, epsv);
 
         // ---- phase 1: first unstable index --------------------------------------------------------
         int first = p.M;  // index at which the test first fires (M: never)
         bool literal = LITERAL;
         double le = 0.0;
         if (!LITERAL) {
-          if (se.er == 0.0 && se.ei == 0.0) {
+          if (K2Init<SCALED>::is_zero(epsv)) {
             literal = false;  // b = c = 0 at every index: `0*tol < 0` never fires
           } else {
-            le = log2_abs(se.er, se.ei);
-            literal = !(le >= K2_LE_MIN) || !isfinite(le);
+            le = K2Init<SCALED>::log2_eps(epsv);
+            literal = (!FE && !(le >= K2_LE_MIN)) || !isfinite(le);
             if (!literal) {
               int i0 = first_le(p.f.pmin_rlog, p.M, le + K2_ETA);
               int i1 = first_lt(p.f.pmin_ov, p.M, le);
@@ -274,11 +362,15 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
         } else {
           // ---- hand over to K3: delta paired with Z[L] = X[L-1] ---------------------------------
           double dr = d.re, di = d.im;
-          int j = L, off = -1;
+          int j = L, off = -1, e = 0;
+          if (SCALED) {  // the floatexp value of d[found]: normalised (dr, di) * 2^e
+            pstate ps = K2Init<SCALED>::state(se, found);
+            dr = ps.dr; di = ps.di; e = ps.e;
+          }
           bool cont = true;
           if (p.align4) {  // k3_fast works on indices that are multiples of 4: take up to 3 exact steps here
             int steps = 0;
-            cont = advance_checked(p.ck, pix, se.er, se.ei, off, dr, di, j, (4 - (L & 3)) & 3, &steps);
+            cont = advance_checked<SCALED>(p.ck, pix, epsv, off, dr, di, e, j, (4 - (L & 3)) & 3, &steps);
             aligned_steps += (unsigned long long)steps;
           }
           if (cont) {
@@ -286,6 +378,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
             p.fresh.j[w] = j;
             p.fresh.off[w] = off;
             p.fresh.pix[w] = pix;
+            if (SCALED) p.fresh.e[w] = e;
             handoff_L = j;
           } else {
             p.fresh.j[w] = -1;
@@ -314,61 +407,68 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
 }
 
 // Per-index filter thresholds (pixel-independent, O(M) once per frame): any grid.
-__global__ void __launch_bounds__(256) k2_prepare(const double2* B, const double2* C, int M, double tol, K2Filter f) {
+template <bool FE>
+__global__ void __launch_bounds__(256) k2_prepare(const double2* B, const double2* C, const int2* Be, const int2* Ce, int M,
+                                                  double tol, K2Filter f) {
   const double lt = log2(tol);
   const double lt_neg = fmin(lt, 0.0), lt_pos = fmax(lt, 0.0);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     double rlog = INFINITY, a = INFINITY, b = -INFINITY, ov = INFINITY;
     if (i >= 1) {
       double2 Bi = B[i], Ci = C[i];
-      double lb = log2_abs(Bi.x, Bi.y), lc = log2_abs(Ci.x, Ci.y);
+      double lb, lc;
+      if (FE) {  // |m| * 2^e with per-component exponents: bring both components to the larger exponent
+        int2 be = Be[i], ce = Ce[i];
+        int eb = max(Bi.x != 0.0 ? be.x : INT_MIN / 2, Bi.y != 0.0 ? be.y : INT_MIN / 2);
+        int ec = max(Ci.x != 0.0 ? ce.x : INT_MIN / 2, Ci.y != 0.0 ? ce.y : INT_MIN / 2);
+        lb = (Bi.x == 0.0 && Bi.y == 0.0) ? -INFINITY
+                                          : log2_abs(fe_scale(Bi.x, max(be.x - eb, -2000)), fe_scale(Bi.y, max(be.y - eb, -2000))) + eb;
+        lc = (Ci.x == 0.0 && Ci.y == 0.0) ? -INFINITY
+                                          : log2_abs(fe_scale(Ci.x, max(ce.x - ec, -2000)), fe_scale(Ci.y, max(ce.y - ec, -2000))) + ec;
+      } else {
+        lb = log2_abs(Bi.x, Bi.y); lc = log2_abs(Ci.x, Ci.y);
+      }
       if (lc != -INFINITY) {            // C_i == 0: |c|^2 == 0, the test cannot fire
         rlog = (lb == -INFINITY) ? -INFINITY : 0.5 * lt + lb - lc;
-        a = (-545.0 - lc) / 3.0;
-        b = (lb == -INFINITY) ? INFINITY : (-990.0 - lt_neg - 2.0 * lb) / 4.0;
-        double c1 = (lb == -INFINITY) ? INFINITY : (1000.0 - lt_pos - 2.0 * lb) / 4.0;
-        double c2 = (1000.0 - 2.0 * lc) / 6.0;
-        ov = fmin(c1, c2);
+        if (!FE) {                      // floatexp has no denormal/overflow ranges: candidates only
+          a = (-545.0 - lc) / 3.0;
+          b = (lb == -INFINITY) ? INFINITY : (-990.0 - lt_neg - 2.0 * lb) / 4.0;
+          double c1 = (lb == -INFINITY) ? INFINITY : (1000.0 - lt_pos - 2.0 * lb) / 4.0;
+          double c2 = (1000.0 - 2.0 * lc) / 6.0;
+          ov = fmin(c1, c2);
+        }
       }
     }
     f.rlog[i] = rlog; f.a[i] = a; f.b[i] = b; f.ov[i] = ov;
   }
 }
 
-// Their prefix minima/maxima: one CTA, each thread owns a contiguous segment, segment totals are
-// combined with a warp-shuffle scan.
+// Their prefix minima/maxima: one CTA walks the M entries in coalesced tiles of 1024; inside a tile a
+// warp-shuffle scan + one shared-memory hop, between tiles a running carry.
 __global__ void __launch_bounds__(1024) k2_prefix(int M, K2Filter f) {
-  __shared__ double s_rlog[32], s_ov[32], s_a[32], s_b[32];
-  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, wid = t >> 5;
-  const int seg = (M + nt - 1) / nt;
-  const int i0 = min(M, t * seg), i1 = min(M, i0 + seg);
-  double m_rlog = INFINITY, m_ov = INFINITY, m_a = INFINITY, m_b = -INFINITY;
-  for (int i = i0; i < i1; ++i) {
-    m_rlog = fmin(m_rlog, f.rlog[i]); m_ov = fmin(m_ov, f.ov[i]); m_a = fmin(m_a, f.a[i]); m_b = fmax(m_b, f.b[i]);
-    f.pmin_rlog[i] = m_rlog; f.pmin_ov[i] = m_ov; f.pmin_a[i] = m_a; f.pmax_b[i] = m_b;
-  }
-  // inclusive scan of the segment totals inside each warp, then across warps
-  double w_rlog = m_rlog, w_ov = m_ov, w_a = m_a, w_b = m_b;
-  for (int o = 1; o < 32; o <<= 1) {
-    double r = __shfl_up_sync(FULL_MASK, w_rlog, o), v = __shfl_up_sync(FULL_MASK, w_ov, o);
-    double a = __shfl_up_sync(FULL_MASK, w_a, o), b = __shfl_up_sync(FULL_MASK, w_b, o);
-    if (lane >= o) { w_rlog = fmin(w_rlog, r); w_ov = fmin(w_ov, v); w_a = fmin(w_a, a); w_b = fmax(w_b, b); }
-  }
-  if (lane == 31) { s_rlog[wid] = w_rlog; s_ov[wid] = w_ov; s_a[wid] = w_a; s_b[wid] = w_b; }
+  __shared__ double s_w[4][32];
+  __shared__ double s_carry[4];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t < 4) s_carry[t] = (t == 3) ? -INFINITY : INFINITY;
   __syncthreads();
-  // carry-in of this thread = totals of all earlier threads
-  double c_rlog = INFINITY, c_ov = INFINITY, c_a = INFINITY, c_b = -INFINITY;
-  for (int w = 0; w < wid; ++w) {
-    c_rlog = fmin(c_rlog, s_rlog[w]); c_ov = fmin(c_ov, s_ov[w]); c_a = fmin(c_a, s_a[w]); c_b = fmax(c_b, s_b[w]);
-  }
-  double e_rlog = __shfl_up_sync(FULL_MASK, w_rlog, 1), e_ov = __shfl_up_sync(FULL_MASK, w_ov, 1);
-  double e_a = __shfl_up_sync(FULL_MASK, w_a, 1), e_b = __shfl_up_sync(FULL_MASK, w_b, 1);
-  if (lane > 0) { c_rlog = fmin(c_rlog, e_rlog); c_ov = fmin(c_ov, e_ov); c_a = fmin(c_a, e_a); c_b = fmax(c_b, e_b); }
-  for (int i = i0; i < i1; ++i) {
-    f.pmin_rlog[i] = fmin(f.pmin_rlog[i], c_rlog);
-    f.pmin_ov[i] = fmin(f.pmin_ov[i], c_ov);
-    f.pmin_a[i] = fmin(f.pmin_a[i], c_a);
-    f.pmax_b[i] = fmax(f.pmax_b[i], c_b);
+  for (int base = 0; base < M; base += 1024) {
+    const int i = base + t;
+    double v0 = INFINITY, v1 = INFINITY, v2 = INFINITY, v3 = -INFINITY;
+    if (i < M) { v0 = f.rlog[i]; v1 = f.ov[i]; v2 = f.a[i]; v3 = f.b[i]; }
+    for (int o = 1; o < 32; o <<= 1) {
+      double u0 = __shfl_up_sync(FULL_MASK, v0, o), u1 = __shfl_up_sync(FULL_MASK, v1, o);
+      double u2 = __shfl_up_sync(FULL_MASK, v2, o), u3 = __shfl_up_sync(FULL_MASK, v3, o);
+      if (lane >= o) { v0 = fmin(v0, u0); v1 = fmin(v1, u1); v2 = fmin(v2, u2); v3 = fmax(v3, u3); }
+    }
+    if (lane == 31) { s_w[0][wid] = v0; s_w[1][wid] = v1; s_w[2][wid] = v2; s_w[3][wid] = v3; }
+    __syncthreads();
+    double c0 = s_carry[0], c1 = s_carry[1], c2 = s_carry[2], c3 = s_carry[3];
+    for (int w = 0; w < wid; ++w) { c0 = fmin(c0, s_w[0][w]); c1 = fmin(c1, s_w[1][w]); c2 = fmin(c2, s_w[2][w]); c3 = fmax(c3, s_w[3][w]); }
+    v0 = fmin(v0, c0); v1 = fmin(v1, c1); v2 = fmin(v2, c2); v3 = fmax(v3, c3);
+    if (i < M) { f.pmin_rlog[i] = v0; f.pmin_ov[i] = v1; f.pmin_a[i] = v2; f.pmax_b[i] = v3; }
+    __syncthreads();
+    if (t == 1023) { s_carry[0] = v0; s_carry[1] = v1; s_carry[2] = v2; s_carry[3] = v3; }
+    __syncthreads();
   }
 }
 
@@ -376,26 +476,30 @@ __global__ void __launch_bounds__(1024) k2_prefix(int M, K2Filter f) {
 // per-lane pixel group of k3_fast): offs[L] .. offs[L+1] holds the samples that start at L, padded
 // with -1. One CTA, each thread owns a contiguous segment of the n bins.
 __global__ void __launch_bounds__(1024) k2_scan(const unsigned* hist, unsigned* offs, unsigned* cursor, int n, unsigned G) {
-  __shared__ unsigned s_tot[32];
-  const int t = threadIdx.x, nt = blockDim.x, lane = t & 31, wid = t >> 5;
-  const int seg = (n + nt - 1) / nt;
-  const int i0 = min(n, t * seg), i1 = min(n, i0 + seg);
-  unsigned acc = 0;
-  for (int i = i0; i < i1; ++i) acc += (hist[i] + G - 1) / G * G;
-  unsigned incl = acc;  // inclusive scan over the warp
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned v = __shfl_up_sync(FULL_MASK, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_tot[wid] = incl;
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned s_carry;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t == 0) s_carry = 0;
   __syncthreads();
-  unsigned base = incl - acc;
-  for (int w = 0; w < wid; ++w) base += s_tot[w];
-  for (int i = i0; i < i1; ++i) {
-    offs[i] = base; cursor[i] = base;
-    base += (hist[i] + G - 1) / G * G;
+  for (int base = 0; base < n; base += 1024) {  // coalesced tiles of 1024 bins
+    const int i = base + t;
+    const unsigned v = i < n ? (hist[i] + G - 1) / G * G : 0u;
+    unsigned incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned u = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_w[wid] = incl;
+    __syncthreads();
+    unsigned b = s_carry;
+    for (int w = 0; w < wid; ++w) b += s_w[w];
+    const unsigned excl = b + incl - v;
+    if (i < n) { offs[i] = excl; cursor[i] = excl; }
+    __syncthreads();
+    if (t == 1023) s_carry = excl + v;
+    __syncthreads();
   }
-  if (i1 == n) offs[n] = base;  // last owner and any empty tail thread agree on the grand total
+  if (t == 0) offs[n] = s_carry;
 }
 
 // Scatter fresh work indices into start-index-sorted order (warp-aggregated slot reservation).

@@ -34,7 +34,8 @@ namespace nm {
 
 constexpr int K3F_THREADS = 256;
 
-__global__ void __launch_bounds__(256) k3_events(CheckedParams p, const double* eps_re, const double* eps_im, int nc,
+template <bool SCALED>
+__global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab,
                                                  const PixState* events, const unsigned long long* count,
                                                  FreshArrays carry, unsigned long long* carry_count, unsigned* hist) {
   const unsigned long long n = *count;
@@ -42,15 +43,17 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, const double* 
   unsigned long long executed = 0;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     PixState e = events[i];
-    const int r = e.pix / nc, c = e.pix - r * nc;
+    EpsVal<SCALED> eps;
+    eps.load(eps_tab, e.pix);
     int steps = 0;
-    if (advance_checked(p, e.pix, eps_re[c], eps_im[r], e.off, e.dr, e.di, e.j, 4, &steps)) {
+    if (advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, 4, &steps)) {
       // carried into the next sweep (index is a multiple of 4 again: 0 after a rebase, block start + 4 else)
       unsigned long long slot = atomicAdd(carry_count, 1ULL);
       carry.d[slot] = make_double2(e.dr, e.di);
       carry.j[slot] = e.j;
       carry.off[slot] = e.off;
       carry.pix[slot] = e.pix;
+      if (SCALED) carry.e[slot] = e.e;
       atomicAdd(&hist[e.j], 1u);
     }
     executed += (unsigned long long)steps;
@@ -62,8 +65,11 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, const double* 
   }
 }
 
-template <int P>
-__global__ void __launch_bounds__(K3F_THREADS, (P == 4 ? 2 : 3))
+// SCALED: states carry a scale exponent (floatexp.cuh). A lane's slots share j, so "re-normalise
+// before the step from j = 0 (mod 64)" is one test per lane and block; the per-slot scale S = 2^e and
+// eps / 2^e live in registers between re-normalisations.
+template <int P, bool SCALED>
+__global__ void __launch_bounds__(K3F_THREADS, ((P == 4 && !SCALED) ? 2 : (P == 4 ? 1 : (SCALED ? 2 : 3))))
 k3_fast(K3Params p, PixState* events) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
@@ -106,15 +112,15 @@ k3_fast(K3Params p, PixState* events) {
   const int jcap = jend < p.Jmax ? jend : p.Jmax;  // a pass can never step beyond this index
 
   // slot state: 0 empty/parked, 1 live, 2 exported (ev_* hold the state to hand to k3_events)
-  double dr[P], di[P], er[P], ei[P], ev_dr[P], ev_di[P];
-  int pix[P], off[P], st[P], ev_j[P];
+  double dr[P], di[P], er[P], ei[P], ev_dr[P], ev_di[P], S[P];
+  int pix[P], off[P], st[P], ev_j[P], sc[P], ev_e[P];
   bool drained = false;
   int j = 0;
   unsigned long long executed = 0;
 #pragma unroll
   for (int s = 0; s < P; ++s) {
-    dr[s] = di[s] = er[s] = ei[s] = ev_dr[s] = ev_di[s] = 0.0;
-    pix[s] = -1; off[s] = -1; st[s] = 0; ev_j[s] = 0;
+    dr[s] = di[s] = er[s] = ei[s] = ev_dr[s] = ev_di[s] = 0.0; S[s] = 1.0;
+    pix[s] = -1; off[s] = -1; st[s] = 0; ev_j[s] = 0; sc[s] = 0; ev_e[s] = 0;
   }
 
   mbar_wait(&bar, 0);
@@ -135,24 +141,27 @@ k3_fast(K3Params p, PixState* events) {
         if (g < g_total) {
 #pragma unroll
           for (int s = 0; s < P; ++s) {
-            dr[s] = di[s] = er[s] = ei[s] = 0.0; pix[s] = -1; off[s] = -1; st[s] = 0;
+            dr[s] = di[s] = er[s] = ei[s] = 0.0; pix[s] = -1; off[s] = -1; st[s] = 0; sc[s] = 0; S[s] = 1.0;
             if (g < g_cur) {
               unsigned long long idx = g * P + s;
               if (idx < n_cur) {
                 PixState q = p.cur[idx];
-                dr[s] = q.dr; di[s] = q.di; pix[s] = q.pix; off[s] = q.off; j = q.j;
+                dr[s] = q.dr; di[s] = q.di; pix[s] = q.pix; off[s] = q.off; j = q.j; sc[s] = SCALED ? q.e : 0;
               }
             } else {
               int w = p.fresh_ids[fresh_begin + (unsigned)((g - g_cur) * P + s)];
               if (w >= 0) {
                 double2 d0 = p.fresh.d[w];
                 dr[s] = d0.x; di[s] = d0.y; off[s] = p.fresh.off[w]; j = p.fresh.j[w]; pix[s] = p.fresh.pix[w];
+                if (SCALED) sc[s] = p.fresh.e[w];
               }
             }
             if (pix[s] >= 0) {
-              int r = pix[s] / p.nc, c = pix[s] - r * p.nc;
-              er[s] = p.eps_re[c];
-              ei[s] = p.eps_im[r];
+              EpsVal<SCALED> eps;
+              eps.load(p.eps, pix[s]);
+              er[s] = eps.re_at(sc[s]);
+              ei[s] = eps.im_at(sc[s]);
+              if (SCALED) S[s] = pow2d(sc[s]);
               st[s] = 1;
               lane_active = true;
             }
@@ -178,7 +187,7 @@ k3_fast(K3Params p, PixState* events) {
           const int room = (lim - j) >> 2;
           if (room > 0) { any_live = true; if (room < nb) nb = room; }
           else if (!(j == jend && j < p.Jmax && jN > j)) {
-            st[s] = 2; ev_dr[s] = dr[s]; ev_di[s] = di[s]; ev_j[s] = j;
+            st[s] = 2; ev_dr[s] = dr[s]; ev_di[s] = di[s]; ev_j[s] = j; ev_e[s] = sc[s];
             executed += (unsigned long long)(j - j_in);
             dr[s] = di[s] = er[s] = ei[s] = 0.0;
           }
@@ -190,6 +199,21 @@ k3_fast(K3Params p, PixState* events) {
       // lane-mates keep going (their limits can only be farther away, so nb stays valid)
       for (int b = 0; __any_sync(FULL_MASK, b < nb); ++b) {
         if (b < nb) {
+          if (SCALED && (j & RENORM_MASK) == 0) {
+#pragma unroll
+            for (int s = 0; s < P; ++s)
+              if (st[s] == 1) {
+                pstate ps; ps.dr = dr[s]; ps.di = di[s]; ps.e = sc[s];
+                state_renorm(ps);
+                if (ps.e != sc[s]) {
+                  EpsVal<SCALED> eps;
+                  eps.load(p.eps, pix[s]);
+                  er[s] = eps.re_at(ps.e); ei[s] = eps.im_at(ps.e);
+                  S[s] = pow2d(ps.e);
+                }
+                dr[s] = ps.dr; di[s] = ps.di; sc[s] = ps.e;
+              }
+          }
           double dr0[P], di0[P];
 #pragma unroll
           for (int s = 0; s < P; ++s) { dr0[s] = dr[s]; di0[s] = di[s]; }
@@ -203,14 +227,18 @@ k3_fast(K3Params p, PixState* events) {
             const int jl = j + t + 1 - jbase;
             const double2 y = sZ[jl];
             const int g = sG[2 * jl + 1];
+            const double x2r = 2.0 * x.x, x2i = 2.0 * x.y;  // SCALED only (dead code otherwise)
 #pragma unroll
             for (int s = 0; s < P; ++s) {
-              double wr = __fma_rn(2.0, x.x, dr[s]);
-              double wi = __fma_rn(2.0, x.y, di[s]);
+              double wr, wi;
+              if (SCALED) { wr = __fma_rn(S[s], dr[s], x2r); wi = __fma_rn(S[s], di[s], x2i); }
+              else { wr = __fma_rn(2.0, x.x, dr[s]); wi = __fma_rn(2.0, x.y, di[s]); }
               double ndr = __fma_rn(-di[s], wi, __fma_rn(dr[s], wr, er[s]));
               double ndi = __fma_rn(di[s], wr, __fma_rn(dr[s], wi, ei[s]));
               dr[s] = ndr; di[s] = ndi;
-              double zr = y.x + ndr, zi = y.y + ndi;
+              double zr, zi;
+              if (SCALED) { zr = __fma_rn(S[s], ndr, y.x); zi = __fma_rn(S[s], ndi, y.y); }
+              else { zr = y.x + ndr; zi = y.y + ndi; }
               double zmag = __fma_rn(zi, zi, zr * zr);
               int hi = __double2hiint(zmag);
               bad[s] = bad[s] || (hi <= g);
@@ -225,7 +253,7 @@ k3_fast(K3Params p, PixState* events) {
 #pragma unroll
             for (int s = 0; s < P; ++s)
               if (st[s] == 1 && bad[s]) {
-                st[s] = 2; ev_dr[s] = dr0[s]; ev_di[s] = di0[s]; ev_j[s] = j;
+                st[s] = 2; ev_dr[s] = dr0[s]; ev_di[s] = di0[s]; ev_j[s] = j; ev_e[s] = sc[s];
                 executed += (unsigned long long)(j - j_in);
                 dr[s] = di[s] = er[s] = ei[s] = 0.0;
               }
@@ -243,12 +271,12 @@ k3_fast(K3Params p, PixState* events) {
       if (toNext) executed += (unsigned long long)(j - j_in);
       unsigned long long slot = warp_reserve(p.next_count, toNext);
       if (toNext) {
-        PixState q; q.dr = dr[s]; q.di = di[s]; q.pix = pix[s]; q.j = j; q.off = off[s]; q.pad = 0;
+        PixState q; q.dr = dr[s]; q.di = di[s]; q.pix = pix[s]; q.j = j; q.off = off[s]; q.e = SCALED ? sc[s] : 0;
         p.next[slot] = q;
       }
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
-        PixState q; q.dr = ev_dr[s]; q.di = ev_di[s]; q.pix = pix[s]; q.j = ev_j[s]; q.off = off[s]; q.pad = 0;
+        PixState q; q.dr = ev_dr[s]; q.di = ev_di[s]; q.pix = pix[s]; q.j = ev_j[s]; q.off = off[s]; q.e = SCALED ? ev_e[s] : 0;
         events[slot] = q;
       }
       st[s] = 0; pix[s] = -1;

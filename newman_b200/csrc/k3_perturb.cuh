@@ -28,7 +28,7 @@
 // the next level's queue. Escaped pixels write their EscapeValue; glitched pixels go to the
 // re-queue list for a secondary reference; pixels that outlive the orbit are rebased onto Z[0].
 #pragma once
-#include "nm_common.cuh"
+#include "k3_checked.cuh"
 
 namespace nm {
 
@@ -37,7 +37,7 @@ struct __align__(16) PixState {
   int32_t pix;
   int32_t j;
   int32_t off;
-  int32_t pad;
+  int32_t e;   // scale exponent: delta = (dr, di) * 2^e (0 in plain frames)
 };
 
 struct K3Params {
@@ -46,8 +46,7 @@ struct K3Params {
   const double* gb;      // full doubles (slow-path exact check)
   int Jmax;              // last valid table index
   int N, CH, k;
-  const double* eps_re;
-  const double* eps_im;
+  EpsTab eps;
   int nc;
   const PixState* cur;
   const unsigned long long* cur_count;
@@ -102,7 +101,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // MODE: NM_MODE_REQUEUE (flag glitches) or NM_MODE_REBASE (rebase when |z|^2 < |delta|^2).
-template <int MODE>
+// SCALED: states carry a scale exponent (floatexp.cuh); bursts then stop at every index = 0 (mod 64),
+// where the state is re-normalised before the next step.
+template <int MODE, bool SCALED>
 __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
@@ -144,8 +145,10 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
   const int jend = jbase + CH;  // states reaching jend move to the next level
 
   bool active = false, drained = false;
-  double dr = 0, di = 0, er = 0, ei = 0;
-  int j = 0, off = -1, pix = 0;
+  double dr = 0, di = 0, er = 0, ei = 0, S = 1.0;
+  int j = 0, off = -1, pix = 0, e = 0;
+  EpsVal<SCALED> eps;
+  eps.r0 = eps.i0 = 0.0;
   unsigned long long executed = 0, rebased = 0;
 
   mbar_wait(&bar, 0);
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
           bool got = true;
           if (idx < n_cur) {
             PixState s = p.cur[idx];
-            dr = s.dr; di = s.di; pix = s.pix; j = s.j; off = s.off;
+            dr = s.dr; di = s.di; pix = s.pix; j = s.j; off = s.off; e = SCALED ? s.e : 0;
           } else {
             int w = p.fresh_ids[fresh_begin + (unsigned)(idx - n_cur)];
             got = w >= 0;
@@ -178,12 +181,13 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
               j = p.fresh.j[w];
               off = p.fresh.off[w];
               pix = p.fresh.pix[w];
+              e = SCALED ? p.fresh.e[w] : 0;
             }
           }
           if (got) {
-            int r = pix / p.nc, c = pix - r * p.nc;
-            er = p.eps_re[c];
-            ei = p.eps_im[r];
+            eps.load(p.eps, pix);
+            er = eps.re_at(e); ei = eps.im_at(e);
+            if (SCALED) S = pow2d(e);
             active = true;
           }
         }
@@ -203,31 +207,43 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
       if (p.Jmax < jstop) jstop = p.Jmax;
       int jlim = j + K3_BURST;
       if (jstop < jlim) jlim = jstop;
+      if (SCALED) {
+        const int jr = (j | RENORM_MASK) + 1;  // next re-normalisation index above j
+        if (jr < jlim) jlim = jr;
+      }
       if (j < jlim) {
         stepped = true;
         const int j0 = j;
+        if (SCALED && (j & RENORM_MASK) == 0) {
+          pstate ps; ps.dr = dr; ps.di = di; ps.e = e;
+          state_renorm(ps);
+          dr = ps.dr; di = ps.di; e = ps.e;
+          S = pow2d(e); er = eps.re_at(e); ei = eps.im_at(e);
+        }
         double2 x = sZ[j - jbase];
         double xr = x.x, xi = x.y;
         for (;;) {
           const int jl = j + 1 - jbase;
           double2 y = sZ[jl];
           int g = sG[jl];
-          double wr = __fma_rn(2.0, xr, dr);
-          double wi = __fma_rn(2.0, xi, di);
+          double wr, wi;
+          if (SCALED) { wr = __fma_rn(S, dr, 2.0 * xr); wi = __fma_rn(S, di, 2.0 * xi); }
+          else { wr = __fma_rn(2.0, xr, dr); wi = __fma_rn(2.0, xi, di); }
           double ndr = __fma_rn(-di, wi, __fma_rn(dr, wr, er));
           double ndi = __fma_rn(di, wr, __fma_rn(dr, wi, ei));
           dr = ndr; di = ndi;
           xr = y.x; xi = y.y;
           ++j;
-          zr = xr + dr;
-          zi = xi + di;
+          if (SCALED) { zr = __fma_rn(S, dr, xr); zi = __fma_rn(S, di, xi); }
+          else { zr = xr + dr; zi = xi + di; }
           zmag = __fma_rn(zi, zi, zr * zr);
           int hi = __double2hiint(zmag);
           bool cand = (hi >= ESC_HI);
           if (MODE == NM_MODE_REQUEUE) {
             cand = cand || (hi <= g);
           } else {
-            dmag = __fma_rn(di, di, dr * dr);
+            if (SCALED) { const double tr = S * dr, ti = S * di; dmag = __fma_rn(ti, ti, tr * tr); }
+            else dmag = __fma_rn(di, di, dr * dr);
             cand = cand || (hi <= __double2hiint(dmag));
           }
           if (cand || j == jlim) break;
@@ -281,6 +297,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
       off = j + off;
       j = 0;
       dr = zr; di = zi;
+      if (SCALED) { e = 0; S = 1.0; er = eps.r0; ei = eps.i0; }
       if (p.k != 0) {
         // chunk 0 is not resident: park the state for the next sweep
       } else {
@@ -290,7 +307,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
     {
       unsigned long long slot = warp_reserve(p.restart_count, rebase);
       if (rebase) {
-        PixState s; s.dr = dr; s.di = di; s.pix = pix; s.j = 0; s.off = off; s.pad = 0;
+        PixState s; s.dr = dr; s.di = di; s.pix = pix; s.j = 0; s.off = off; s.e = 0;
         p.restart[slot] = s;
         active = false;
       }
@@ -298,7 +315,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
     {
       unsigned long long slot = warp_reserve(p.next_count, toNext);
       if (toNext) {
-        PixState s; s.dr = dr; s.di = di; s.pix = pix; s.j = j; s.off = off; s.pad = 0;
+        PixState s; s.dr = dr; s.di = di; s.pix = pix; s.j = j; s.off = off; s.e = e;
         p.next[slot] = s;
         active = false;
       }

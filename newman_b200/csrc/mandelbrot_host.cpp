@@ -60,7 +60,8 @@ mp_bitcnt_t max_prec(const HPComplex& a, const HPComplex& b) {
 Mandelbrot::Mandelbrot() : Mandelbrot(1, 1) {}
 
 Mandelbrot::Mandelbrot(int nr, int nc)
-    : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(1), device(0), host_threads(0) {
+    : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(1), device(0), host_threads(0),
+      force_floatexp(0) {
   // default full view (mandelbrot.cpp:13-14)
   center.re = -0.5;
   center.im = 0.0;
@@ -197,15 +198,24 @@ void Mandelbrot::renderFrame() {
     std::vector<int32_t> rq_pix, rq_iter;
     int round = 0;
     for (;;) {
-      if (!T.finite)
-        throw std::runtime_error("newman_b200: series coefficients exceed double range (view beyond the reference's "
-                                 "depth limit, SURVEY.md finding 3)");
+      // Coefficients beyond double range (pixel pitch < ~1e-97, where the reference dies with SIGFPE):
+      // hand them over as mantissa + exponent and let K2 evaluate the series in floatexp (level 1).
+      // Below a pitch of 2^-380 (~4e-115) delta*delta, and later delta and eps themselves, leave double
+      // range too: eps goes over as mantissa + exponent and K3 iterates scaled states (level 2).
+      int fe = T.finite ? 0 : 1;
+      if (T.pitch_exp < -380) fe = 2;
+      if (force_floatexp > fe) fe = force_floatexp > 2 ? 2 : force_floatexp;
       nm_deep_tables t;
       t.M = T.M; t.N = N; t.has_escape = T.has_escape ? 1 : 0; t.reserved = 0;
       t.tol = error_tolerance; t.glitch_tol = glitch_tolerance;
-      t.x_hi = T.x_hi.data(); t.x_lo = T.x_lo.data(); t.a = T.a.data(); t.b = T.b.data(); t.c = T.c.data();
+      t.x_hi = T.x_hi.data(); t.x_lo = T.x_lo.data();
+      t.a = fe ? T.a_m.data() : T.a.data(); t.b = fe ? T.b_m.data() : T.b.data(); t.c = fe ? T.c_m.data() : T.c.data();
+      t.a_exp = fe ? T.a_e.data() : nullptr; t.b_exp = fe ? T.b_e.data() : nullptr; t.c_exp = fe ? T.c_e.data() : nullptr;
+      t.eps_re_exp = fe == 2 ? T.eps_re_e.data() : nullptr; t.eps_im_exp = fe == 2 ? T.eps_im_e.data() : nullptr;
+      info_.floatexp = fe;
       const bool last = round >= max_secondary;
-      eng.check(nm_frame_deep(ctx, &t, T.eps_re.data(), v.nc, T.eps_im.data(), v.nr, cmode,
+      eng.check(nm_frame_deep(ctx, &t, fe == 2 ? T.eps_re_m.data() : T.eps_re.data(), v.nc,
+                              fe == 2 ? T.eps_im_m.data() : T.eps_im.data(), v.nr, cmode,
                               cmode == NM_CARDIOID_MASK ? mask.data() : nullptr, round ? rq_pix.data() : nullptr,
                               round ? (int64_t)rq_pix.size() : 0, last ? NM_MODE_REBASE : NM_MODE_REQUEUE),
                 "nm_frame_deep");

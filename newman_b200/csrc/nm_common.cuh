@@ -45,6 +45,7 @@ struct FreshArrays {
   int32_t* j;     // table index, or -1: not a K3 state
   int32_t* off;   // it = j + off
   int32_t* pix;   // pixel id
+  int32_t* e;     // scale exponent of delta (scaled frames only; 0 = plain state)
 };
 
 struct FixupRec {  // smoothing value to be re-evaluated with the host libm

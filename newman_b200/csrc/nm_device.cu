@@ -66,10 +66,11 @@ struct nm_ctx {
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
   DevBuf Z, ghi, gb, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events;
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
+  int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
-  int occ_k3f[2] = {0, 0};
+  int occ_k3f[2] = {0, 0}, occ_k3fs[2] = {0, 0};
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
   double tol = 0, gtol = 0;
 
@@ -78,7 +79,7 @@ struct nm_ctx {
   unsigned long long* h_ctr = nullptr;  // pinned mirror of the counters
   unsigned long long* h_flag = nullptr; // pinned cancel flag source
   double log_bailout = 0;
-  int occ_k1 = 0, occ_k3[2] = {0, 0};
+  int occ_k1 = 0, occ_k3[2] = {0, 0}, occ_k3s[2] = {0, 0};
 };
 
 namespace {
@@ -220,10 +221,17 @@ int launch_hw(nm_ctx* ctx) {
   return NM_OK;
 }
 
-template <int MODE>
+template <int MODE, bool SCALED>
 cudaError_t launch_level(nm_ctx* ctx, const K3Params& p, unsigned blocks, size_t smem) {
-  k3_level<MODE><<<blocks, K3_THREADS, smem, ctx->stream>>>(p);
+  k3_level<MODE, SCALED><<<blocks, K3_THREADS, smem, ctx->stream>>>(p);
   return cudaGetLastError();
+}
+
+template <bool LITERAL>
+void launch_k2(nm_ctx* ctx, const K2Params& k2, unsigned blocks) {
+  if (ctx->use_fe == 2) k2_series<LITERAL, 2><<<blocks, K2_THREADS, 0, ctx->stream>>>(k2);
+  else if (ctx->use_fe == 1) k2_series<LITERAL, 1><<<blocks, K2_THREADS, 0, ctx->stream>>>(k2);
+  else k2_series<LITERAL, 0><<<blocks, K2_THREADS, 0, ctx->stream>>>(k2);
 }
 
 FreshArrays fresh_set(nm_ctx* ctx, int which) {
@@ -233,6 +241,7 @@ FreshArrays fresh_set(nm_ctx* ctx, int which) {
   f.j = ctx->fa_i[which].as<int32_t>();
   f.off = f.j + Wn;
   f.pix = f.j + 2 * Wn;
+  f.e = f.j + 3 * Wn;
   return f;
 }
 
@@ -266,9 +275,15 @@ int launch_deep(nm_ctx* ctx) {
   // ---- K2 ---------------------------------------------------------------------------------------
   K2Params k2;
   k2.A = ctx->a.as<double2>(); k2.B = ctx->b.as<double2>(); k2.C = ctx->c.as<double2>();
+  k2.Ae = ctx->aexp.as<int2>(); k2.Be = ctx->bexp.as<int2>(); k2.Ce = ctx->cexp.as<int2>();
   k2.Z = ctx->Z.as<double2>(); k2.Xlo = ctx->xlo.as<double2>();
   k2.M = ctx->M; k2.N = ctx->N; k2.tol = ctx->tol;
-  k2.eps_re = ctx->cre.as<double>(); k2.eps_im = ctx->cim.as<double>(); k2.nc = ctx->nc;
+  EpsTab eps;
+  eps.re = ctx->cre.as<double>(); eps.im = ctx->cim.as<double>(); eps.nc = ctx->nc;
+  eps.re_e = ctx->use_fe == 2 ? ctx->cre_e.as<int32_t>() : nullptr;
+  eps.im_e = ctx->use_fe == 2 ? ctx->cim_e.as<int32_t>() : nullptr;
+  const bool scaled = ctx->use_fe == 2;
+  k2.eps = eps; k2.nc = ctx->nc;
   k2.pix_list = ctx->have_list ? ctx->list.as<int32_t>() : nullptr;
   k2.W = ctx->W;
   k2.cardioid_mode = ctx->cardioid_mode;
@@ -291,14 +306,15 @@ int launch_deep(nm_ctx* ctx) {
     const size_t Mn = (size_t)ctx->M;
     k2.f.rlog = fb; k2.f.a = fb + Mn; k2.f.b = fb + 2 * Mn; k2.f.ov = fb + 3 * Mn;
     k2.f.pmin_rlog = fb + 4 * Mn; k2.f.pmin_ov = fb + 5 * Mn; k2.f.pmin_a = fb + 6 * Mn; k2.f.pmax_b = fb + 7 * Mn;
-    k2_prepare<<<(ctx->M + 255) / 256, 256, 0, st>>>(k2.B, k2.C, ctx->M, ctx->tol, k2.f);
+    if (ctx->use_fe) k2_prepare<true><<<(ctx->M + 255) / 256, 256, 0, st>>>(k2.B, k2.C, k2.Be, k2.Ce, ctx->M, ctx->tol, k2.f);
+    else k2_prepare<false><<<(ctx->M + 255) / 256, 256, 0, st>>>(k2.B, k2.C, k2.Be, k2.Ce, ctx->M, ctx->tol, k2.f);
     NM_CUDA(ctx, cudaGetLastError());
     k2_prefix<<<1, 1024, 0, st>>>(ctx->M, k2.f);
     NM_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 2;
-    k2_series<false><<<(unsigned)b2, K2_THREADS, 0, st>>>(k2);
+    launch_k2<false>(ctx, k2, (unsigned)b2);
   } else {
-    k2_series<true><<<(unsigned)b2, K2_THREADS, 0, st>>>(k2);
+    launch_k2<true>(ctx, k2, (unsigned)b2);
   }
   NM_CUDA(ctx, cudaGetLastError());
   ctx->stats.kernel_launches++;
@@ -308,7 +324,7 @@ int launch_deep(nm_ctx* ctx) {
   K3Params p;
   p.Z = ctx->Z.as<double2>(); p.ghi = ctx->ghi.as<int32_t>(); p.gb = ctx->gb.as<double>();
   p.Jmax = ctx->Jmax; p.N = ctx->N; p.CH = CH;
-  p.eps_re = ctx->cre.as<double>(); p.eps_im = ctx->cim.as<double>(); p.nc = ctx->nc;
+  p.eps = eps; p.nc = ctx->nc;
   p.fresh_ids = ctx->fresh.as<int32_t>();
   p.out = ctx->out.as<nm_escape>();
   p.ctr = ctr;
@@ -317,9 +333,9 @@ int launch_deep(nm_ctx* ctx) {
   p.log_bailout = ctx->log_bailout;
 
   const size_t smem = (size_t)(CH + 4) * (sizeof(double2) + sizeof(double));
-  int occ = ctx->occ_k3[ctx->mode == NM_MODE_REBASE ? 1 : 0];
-  if (G == 2) occ = ctx->occ_k3f[0];
-  if (G == 4) occ = ctx->occ_k3f[1];
+  int occ = (scaled ? ctx->occ_k3s : ctx->occ_k3)[ctx->mode == NM_MODE_REBASE ? 1 : 0];
+  if (G == 2) occ = (scaled ? ctx->occ_k3fs : ctx->occ_k3f)[0];
+  if (G == 4) occ = (scaled ? ctx->occ_k3fs : ctx->occ_k3f)[1];
   const unsigned blocks = (unsigned)(ctx->sm_count * occ);
   NM_CUDA(ctx, cudaMemsetAsync(ccount, 0, 2 * sizeof(unsigned long long), st));
 
@@ -358,17 +374,27 @@ int launch_deep(nm_ctx* ctx) {
       p.head = &head[k];
       p.fresh_off = have_fresh ? ctx->offs.as<unsigned>() : nullptr;
       cudaError_t e;
-      if (G == 4) { k3_fast<4><<<blocks, K3F_THREADS, smem, st>>>(p, ctx->events.as<PixState>()); e = cudaGetLastError(); }
-      else if (G == 2) { k3_fast<2><<<blocks, K3F_THREADS, smem, st>>>(p, ctx->events.as<PixState>()); e = cudaGetLastError(); }
-      else e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE>(ctx, p, blocks, smem)
-                                           : launch_level<NM_MODE_REQUEUE>(ctx, p, blocks, smem);
+      PixState* evq = ctx->events.as<PixState>();
+      if (G == 4 && scaled) { k3_fast<4, true><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
+      else if (G == 4) { k3_fast<4, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
+      else if (G == 2 && scaled) { k3_fast<2, true><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
+      else if (G == 2) { k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
+      else if (scaled) e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, true>(ctx, p, blocks, smem)
+                                                       : launch_level<NM_MODE_REQUEUE, true>(ctx, p, blocks, smem);
+      else e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, false>(ctx, p, blocks, smem)
+                                           : launch_level<NM_MODE_REQUEUE, false>(ctx, p, blocks, smem);
       if (e != cudaSuccess) return fail(ctx, NM_ECUDA, "k3 level launch: %s", cudaGetErrorString(e));
       ctx->stats.kernel_launches++;
     }
     if (fast) {  // resolve what the branch-free kernel exported: escapes, glitches, limits, rebases, false alarms
-      k3_events<<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(ck, p.eps_re, p.eps_im, p.nc, ctx->events.as<PixState>(),
-                                                            &ctr[CTR_EVENTS], fresh_set(ctx, par ^ 1), &ccount[par ^ 1],
-                                                            ctx->hist.as<unsigned>());
+      if (scaled)
+        k3_events<true><<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(ck, eps, ctx->events.as<PixState>(), &ctr[CTR_EVENTS],
+                                                                      fresh_set(ctx, par ^ 1), &ccount[par ^ 1],
+                                                                      ctx->hist.as<unsigned>());
+      else
+        k3_events<false><<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(ck, eps, ctx->events.as<PixState>(), &ctr[CTR_EVENTS],
+                                                                       fresh_set(ctx, par ^ 1), &ccount[par ^ 1],
+                                                                       ctx->hist.as<unsigned>());
       NM_CUDA(ctx, cudaGetLastError());
       ctx->stats.kernel_launches++;
     }
@@ -464,21 +490,22 @@ int nm_create(int device, nm_ctx** out) {
   *ctx->h_flag = 1ULL;
   ctx->log_bailout = log(1024.0);
   const size_t smem = (size_t)(ctx->CH + 4) * (sizeof(double2) + sizeof(double));
-  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_level<NM_MODE_REQUEUE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_level<NM_MODE_REBASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NM_CREATE_CUDA(cudaFuncSetAttribute(k3_fast<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3f[0], k3_fast<2>, K3F_THREADS, smem));
-  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3f[1], k3_fast<4>, K3F_THREADS, smem));
+#define NM_K3_SETUP(fn, threads, occ_out)                                                                     \
+  NM_CREATE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(occ_out), fn, threads, smem));                \
+  if ((occ_out) < 1) (occ_out) = 1;
+  NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, false>), K3_THREADS, ctx->occ_k3[0]);
+  NM_K3_SETUP((k3_level<NM_MODE_REBASE, false>), K3_THREADS, ctx->occ_k3[1]);
+  NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, true>), K3_THREADS, ctx->occ_k3s[0]);
+  NM_K3_SETUP((k3_level<NM_MODE_REBASE, true>), K3_THREADS, ctx->occ_k3s[1]);
+  NM_K3_SETUP((k3_fast<2, false>), K3F_THREADS, ctx->occ_k3f[0]);
+  NM_K3_SETUP((k3_fast<4, false>), K3F_THREADS, ctx->occ_k3f[1]);
+  NM_K3_SETUP((k3_fast<2, true>), K3F_THREADS, ctx->occ_k3fs[0]);
+  NM_K3_SETUP((k3_fast<4, true>), K3F_THREADS, ctx->occ_k3fs[1]);
+#undef NM_K3_SETUP
   NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k1, k1_escape, K1_THREADS, 0));
-  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3[0], k3_level<NM_MODE_REQUEUE>, K3_THREADS, smem));
-  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k3[1], k3_level<NM_MODE_REBASE>, K3_THREADS, smem));
 #undef NM_CREATE_CUDA
   if (ctx->occ_k1 < 1) ctx->occ_k1 = 1;
-  if (ctx->occ_k3[0] < 1) ctx->occ_k3[0] = 1;
-  if (ctx->occ_k3[1] < 1) ctx->occ_k3[1] = 1;
-  if (ctx->occ_k3f[0] < 1) ctx->occ_k3f[0] = 1;
-  if (ctx->occ_k3f[1] < 1) ctx->occ_k3f[1] = 1;
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
   return NM_OK;
@@ -491,7 +518,7 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events};
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -574,6 +601,13 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   ctx->launched = ctx->finished = false;
   memset(&ctx->stats, 0, sizeof ctx->stats);
   ctx->M = t->M; ctx->has_escape = t->has_escape ? 1 : 0;
+  ctx->use_fe = (t->a_exp && t->b_exp && t->c_exp) ? 1 : 0;
+  if (!ctx->use_fe && (t->a_exp || t->b_exp || t->c_exp)) return fail(ctx, NM_EINVAL, "floatexp tables need all of a_exp, b_exp, c_exp");
+  if (t->eps_re_exp || t->eps_im_exp) {
+    if (!ctx->use_fe || !t->eps_re_exp || !t->eps_im_exp)
+      return fail(ctx, NM_EINVAL, "floatexp eps needs both eps_re_exp and eps_im_exp and floatexp series tables");
+    ctx->use_fe = 2;
+  }
   ctx->Jmax = t->M + ctx->has_escape;
   ctx->K = (ctx->Jmax + ctx->CH - 1) / ctx->CH;
   ctx->tol = t->tol; ctx->gtol = t->glitch_tol;
@@ -595,7 +629,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->filt.ensure((size_t)M * 8 * sizeof(double)));
   for (int i = 0; i < 2; i++) {
     NM_CUDA(ctx, ctx->fa_d[i].ensure(Wn * sizeof(double2)));
-    NM_CUDA(ctx, ctx->fa_i[i].ensure(Wn * 3 * sizeof(int32_t)));
+    NM_CUDA(ctx, ctx->fa_i[i].ensure(Wn * 4 * sizeof(int32_t)));
   }
   NM_CUDA(ctx, ctx->fresh.ensure((Wn + (size_t)4 * (J1 + 2)) * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->hist.ensure((size_t)(J1 + 4) * sizeof(unsigned)));
@@ -617,8 +651,22 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->a.p, t->a, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->b.p, t->b, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->c.p, t->c, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
+  if (ctx->use_fe) {
+    NM_CUDA(ctx, ctx->aexp.ensure((size_t)M * sizeof(int2)));
+    NM_CUDA(ctx, ctx->bexp.ensure((size_t)M * sizeof(int2)));
+    NM_CUDA(ctx, ctx->cexp.ensure((size_t)M * sizeof(int2)));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->aexp.p, t->a_exp, (size_t)M * sizeof(int2), cudaMemcpyDefault, s));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->bexp.p, t->b_exp, (size_t)M * sizeof(int2), cudaMemcpyDefault, s));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->cexp.p, t->c_exp, (size_t)M * sizeof(int2), cudaMemcpyDefault, s));
+  }
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->cre.p, eps_re, (size_t)nc * sizeof(double), cudaMemcpyDefault, s));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->cim.p, eps_im, (size_t)nr * sizeof(double), cudaMemcpyDefault, s));
+  if (ctx->use_fe == 2) {
+    NM_CUDA(ctx, ctx->cre_e.ensure((size_t)nc * sizeof(int32_t)));
+    NM_CUDA(ctx, ctx->cim_e.ensure((size_t)nr * sizeof(int32_t)));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->cre_e.p, t->eps_re_exp, (size_t)nc * sizeof(int32_t), cudaMemcpyDefault, s));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->cim_e.p, t->eps_im_exp, (size_t)nr * sizeof(int32_t), cudaMemcpyDefault, s));
+  }
   if (cardioid_mode == NM_CARDIOID_MASK) {
     NM_CUDA(ctx, ctx->mask.ensure((size_t)ctx->pixels));
     NM_CUDA(ctx, cudaMemcpyAsync(ctx->mask.p, cardioid_mask, (size_t)ctx->pixels, cudaMemcpyDefault, s));

@@ -91,6 +91,12 @@ int nmv_set_view(nmv_view* v, int N, const char* sz_re, const char* sz_im, const
   });
 }
 
+int nmv_set_floatexp(nmv_view* v, int force) {
+  if (!v) return NM_EINVAL;
+  v->m.force_floatexp = force < 0 ? 0 : (force > 2 ? 2 : force);
+  return NM_OK;
+}
+
 int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, int device, int host_threads) {
   if (!v) return NM_EINVAL;
   if (glitch_tol >= 0) v->m.glitch_tolerance = glitch_tol;
@@ -166,7 +172,7 @@ int nmv_view_string(const nmv_view* v, int which, char* buf, int cap) {
 int nmv_frame_info_get(const nmv_view* v, nmv_frame_info* out) {
   if (!v || !out) return NM_EINVAL;
   const newman_b200::FrameInfo& f = v->m.frameInfo();
-  out->hardware = f.hardware; out->precision_bits = f.precision_bits; out->orbit_len = f.orbit_len;
+  out->hardware = f.hardware ? 1 : (f.floatexp ? 1 + f.floatexp : 0); out->precision_bits = f.precision_bits; out->orbit_len = f.orbit_len;
   out->probe_row = f.probe_row; out->probe_col = f.probe_col; out->references = f.references;
   out->executed_iters = f.executed_iters; out->series_evals = f.series_evals; out->skipped_pixels = f.skipped_pixels;
   out->glitched = f.glitched; out->rebased = f.rebased; out->fixups = f.fixups; out->kernel_launches = f.kernel_launches;
@@ -205,9 +211,23 @@ int nmv_host_table(const nmv_view* v, int which, double* out) {
     case 4: src = &v->tabs.c; break;
     case 5: src = &v->tabs.eps_re; break;
     case 6: src = &v->tabs.eps_im; break;
+    case 7: src = &v->tabs.a_m; break;
+    case 8: src = &v->tabs.b_m; break;
+    case 9: src = &v->tabs.c_m; break;
+    case 10: src = &v->tabs.eps_re_m; break;
+    case 11: src = &v->tabs.eps_im_m; break;
     default: return NM_EINVAL;
   }
   std::memcpy(out, src->data(), src->size() * sizeof(double));
+  return (int)src->size();
+}
+
+int nmv_host_table_exp(const nmv_view* v, int which, int32_t* out) {
+  if (!v || !out) return NM_EINVAL;
+  const std::vector<int32_t>* src = which == 2 ? &v->tabs.a_e : which == 3 ? &v->tabs.b_e : which == 4 ? &v->tabs.c_e
+                                    : which == 10 ? &v->tabs.eps_re_e : which == 11 ? &v->tabs.eps_im_e : nullptr;
+  if (!src) return NM_EINVAL;
+  std::memcpy(out, src->data(), src->size() * sizeof(int32_t));
   return (int)src->size();
 }
 

@@ -25,6 +25,7 @@ VIEW_API = {
     "nmv_last_error": (C.c_char_p, [C.c_void_p]),
     "nmv_set_view": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double]),
     "nmv_set_options": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "nmv_set_floatexp": (C.c_int, [C.c_void_p, C.c_int]),
     "nmv_rows": (C.c_int, [C.c_void_p]),
     "nmv_cols": (C.c_int, [C.c_void_p]),
     "nmv_use_hardware": (C.c_int, [C.c_void_p]),
@@ -47,6 +48,7 @@ VIEW_API = {
     "nmv_host_tables": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int)]),
     "nmv_host_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nmv_host_table_exp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "nmv_host_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmv_host_cardioid": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nmv_host_in_cardioid": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -105,6 +107,10 @@ class Mandelbrot:
 
     def set_options(self, glitch_tol=-1.0, max_secondary=-1, device=-1, host_threads=-1):
         self.lib.nmv_set_options(self.h, glitch_tol, max_secondary, device, host_threads)
+
+    def set_floatexp(self, force):
+        """0 automatic; 1 floatexp series; 2 also floatexp eps + scaled deltas (even where doubles suffice)."""
+        self._ck(self.lib.nmv_set_floatexp(self.h, int(force)))
 
     def rows(self):
         return self.lib.nmv_rows(self.h)
@@ -199,7 +205,16 @@ class Mandelbrot:
             arrs.append(a)
         keys = ("x_hi", "x_lo", "a", "b", "c", "eps_re", "eps_im")
         d = dict(zip(keys, arrs))
+        # floatexp form (mantissa in [0.5, 1) and binary exponent, as mpf_get_d_2exp returns them)
+        for which, key, n in ((7, "a", 2 * M), (8, "b", 2 * M), (9, "c", 2 * M), (10, "eps_re", self.cols()),
+                              (11, "eps_im", self.rows())):
+            m = np.zeros(n)
+            e = np.zeros(n, dtype=np.int32)
+            self._ck(self.lib.nmv_host_table(self.h, which, L.ptr(m)))
+            self._ck(self.lib.nmv_host_table_exp(self.h, which - 5 if which < 10 else which, L.ptr(e)))
+            d[key + "_m"], d[key + "_e"] = m, e
         d.update(M=M, has_escape=he.value, probe=(pr.value, pc.value))
+        d["finite"] = bool(np.isfinite(d["a"]).all() and np.isfinite(d["b"]).all() and np.isfinite(d["c"]).all())
         return d
 
     def host_coords(self):

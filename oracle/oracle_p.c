@@ -76,40 +76,136 @@ double oraclep_trunc_add3(double hi, double lo, double d) {
   return add_rz(h, l);
 }
 
+/* ---- floatexp: double mantissa + int exponent (mirrors newman_b200/csrc/floatexp.cuh one for one) ----
+ * Every operation is ONE IEEE double operation on exactly scaled operands, so wherever the same
+ * computation in plain double neither overflows nor underflows the result is bit-identical to it. */
+typedef struct { double m; int e; } fe_t;      /* value = m * 2^e; m == 0 or 1 <= |m| < 2 */
+typedef struct { fe_t re, im; } fec_t;
+
+static fe_t fe_norm(double m, int e) {
+  fe_t r;
+  if (m == 0.0 || m != m) { r.m = m; r.e = 0; return r; }
+  int k;
+  double f = frexp(m, &k); /* f in [0.5, 1) */
+  r.m = f * 2.0; r.e = e + k - 1;
+  return r;
+}
+static fe_t fe_from_double(double x) { return fe_norm(x, 0); }
+static double fe_scale(double m, int k) { /* m * 2^k, k <= 0; flushed to (signed) zero below 2^-1000 */
+  if (k < -1000) return 0.0 * m;
+  return ldexp(m, k);
+}
+static double fe_to_double(fe_t a) { /* no denormal results: flushed to (signed) zero below 2^-1022 */
+  if (a.m == 0.0) return a.m;
+  if (a.e > 1023) return a.m > 0 ? INFINITY : -INFINITY;
+  if (a.e < -1022) return 0.0 * a.m;
+  return ldexp(a.m, a.e);
+}
+static fe_t fe_mul(fe_t a, fe_t b) { return fe_norm(a.m * b.m, a.e + b.e); }
+static fe_t fe_neg(fe_t a) { a.m = -a.m; return a; }
+static fe_t fe_add(fe_t a, fe_t b) {
+  if (a.m == 0.0) return b;
+  if (b.m == 0.0) return a;
+  if (a.e >= b.e) return fe_norm(a.m + fe_scale(b.m, b.e - a.e), a.e);
+  return fe_norm(fe_scale(a.m, a.e - b.e) + b.m, b.e);
+}
+static fe_t fe_sub(fe_t a, fe_t b) { return fe_add(a, fe_neg(b)); }
+static int fe_lt_nonneg(fe_t a, fe_t b) {
+  if (b.m == 0.0) return 0;
+  if (a.m == 0.0) return 1;
+  if (a.e != b.e) return a.e < b.e;
+  return a.m < b.m;
+}
+static fec_t fec_mul(fec_t a, fec_t b) { /* complex.h:29-31 */
+  fec_t r;
+  r.re = fe_sub(fe_mul(a.re, b.re), fe_mul(a.im, b.im));
+  r.im = fe_add(fe_mul(a.re, b.im), fe_mul(a.im, b.re));
+  return r;
+}
+static fec_t fec_sq(fec_t a) { /* complex.h:19-21 */
+  fec_t r;
+  r.re = fe_sub(fe_mul(a.re, a.re), fe_mul(a.im, a.im));
+  fe_t two_re = a.re; two_re.e += (a.re.m != 0.0);
+  r.im = fe_mul(two_re, a.im);
+  return r;
+}
+static fec_t fec_add(fec_t a, fec_t b) { fec_t r; r.re = fe_add(a.re, b.re); r.im = fe_add(a.im, b.im); return r; }
+static fe_t fec_sqmag(fec_t a) { return fe_add(fe_mul(a.re, a.re), fe_mul(a.im, a.im)); }
+
+/* ---- series phase ------------------------------------------------------------------------------- */
 typedef struct {
-  double er, ei, e2r, e2i, e3r, e3i;
+  double er, ei, e2r, e2i, e3r, e3i; /* double mode */
+  fec_t eps, e2, e3;                 /* floatexp mode */
+  int fe;
   const op_tables* t;
 } series_t;
 
-static void series_init(series_t* s, const op_tables* t, double er, double ei) {
-  s->t = t; s->er = er; s->ei = ei;
+static int tables_fe(const op_tables* t) { return t->a_exp && t->b_exp && t->c_exp; }
+
+static fec_t load_fe(const double* m, const int32_t* e, int i) {
+  fec_t r; r.re = fe_norm(m[2 * i], e[2 * i]); r.im = fe_norm(m[2 * i + 1], e[2 * i + 1]); return r;
+}
+
+/* eps: the pixel's offset as floatexp; (er, ei): the same as plain doubles (what the double mode uses) */
+static void series_init(series_t* s, const op_tables* t, fec_t eps, double er, double ei) {
+  s->t = t; s->fe = tables_fe(t);
+  s->eps = eps;
+  s->er = er; s->ei = ei;
+  if (s->fe) {
+    s->e2 = fec_sq(eps);
+    s->e3 = fec_mul(eps, s->e2);
+    return;
+  }
   s->e2r = er * er - ei * ei;  /* eps2 = sq(eps), mandelbrot.cpp:160 */
   s->e2i = 2.0 * er * ei;
   cplx e3 = cmul(er, ei, s->e2r, s->e2i); /* eps3 = eps * eps2, :161 */
   s->e3r = e3.re; s->e3i = e3.im;
 }
 
-static cplx series_d(const series_t* s, int j) { /* d[j], mandelbrot.cpp:164, 166-172, 180 */
-  cplx r;
-  if (j == 0) { r.re = s->er; r.im = s->ei; return r; }
+static fec_t series_d_fe(const series_t* s, int j) { /* d[j], mandelbrot.cpp:164, 166-172, 180 */
   const op_tables* t = s->t;
+  fec_t r;
+  if (j == 0) return s->eps;
+  if (s->fe) {
+    fec_t a = fec_mul(load_fe(t->a, t->a_exp, j), s->eps);
+    fec_t b = fec_mul(load_fe(t->b, t->b_exp, j), s->e2);
+    fec_t c = fec_mul(load_fe(t->c, t->c_exp, j), s->e3);
+    return fec_add(fec_add(a, b), c);
+  }
   cplx a = cmul(t->a[2 * j], t->a[2 * j + 1], s->er, s->ei);
   cplx b = cmul(t->b[2 * j], t->b[2 * j + 1], s->e2r, s->e2i);
   cplx c = cmul(t->c[2 * j], t->c[2 * j + 1], s->e3r, s->e3i);
-  r.re = (a.re + b.re) + c.re;
-  r.im = (a.im + b.im) + c.im;
+  r.re = fe_from_double((a.re + b.re) + c.re);
+  r.im = fe_from_double((a.im + b.im) + c.im);
   return r;
+}
+
+static cplx series_d(const series_t* s, int j) {
+  if (j == 0 && !s->fe) { cplx r0; r0.re = s->er; r0.im = s->ei; return r0; }
+  fec_t d = series_d_fe(s, j);
+  cplx r; r.re = fe_to_double(d.re); r.im = fe_to_double(d.im);
+  return r;
+}
+
+static int series_unstable(const series_t* s, int i) { /* isUnstable, mandelbrot.cpp:138-142 */
+  const op_tables* t = s->t;
+  if (s->fe) {
+    fe_t bmag = fec_sqmag(fec_mul(load_fe(t->b, t->b_exp, i), s->e2));
+    fe_t cmag = fec_sqmag(fec_mul(load_fe(t->c, t->c_exp, i), s->e3));
+    return fe_lt_nonneg(fe_mul(bmag, fe_from_double(t->tol)), cmag);
+  }
+  cplx b = cmul(t->b[2 * i], t->b[2 * i + 1], s->e2r, s->e2i);
+  cplx c = cmul(t->c[2 * i], t->c[2 * i + 1], s->e3r, s->e3i);
+  double bmag = b.re * b.re + b.im * b.im;
+  double cmag = c.re * c.re + c.im * c.im;
+  return bmag * t->tol < cmag;
 }
 
 static int series_scan(const series_t* s, uint64_t* evals) { /* mandelbrot.cpp:165-181 -> d.size() */
   const op_tables* t = s->t;
   for (int i = 1; i < t->M; i++) {
-    cplx b = cmul(t->b[2 * i], t->b[2 * i + 1], s->e2r, s->e2i);
-    cplx c = cmul(t->c[2 * i], t->c[2 * i + 1], s->e3r, s->e3i);
-    double bmag = b.re * b.re + b.im * b.im; /* isUnstable, :138-142 */
-    double cmag = c.re * c.re + c.im * c.im;
     (*evals)++;
-    if (bmag * t->tol < cmag) {
+    if (series_unstable(s, i)) {
       int good = i - 3;
       if (good < 1) good = 1;
       return good;
@@ -118,9 +214,22 @@ static int series_scan(const series_t* s, uint64_t* evals) { /* mandelbrot.cpp:1
   return t->M;
 }
 
+static fec_t eps_of(const op_tables* t, const double* eps_re, const double* eps_im, int r, int c) {
+  fec_t e;
+  if (t->eps_re_exp && t->eps_im_exp) { /* mantissa + exponent as mpf_get_d_2exp returns them */
+    e.re = fe_norm(eps_re[c], t->eps_re_exp[c]);
+    e.im = fe_norm(eps_im[r], t->eps_im_exp[r]);
+  } else {
+    e.re = fe_from_double(eps_re[c]);
+    e.im = fe_from_double(eps_im[r]);
+  }
+  return e;
+}
+
 int oraclep_series_L(const op_tables* t, double er, double ei, double* d_re, double* d_im) {
   series_t s; uint64_t ev = 0;
-  series_init(&s, t, er, ei);
+  fec_t eps; eps.re = fe_from_double(er); eps.im = fe_from_double(ei);
+  series_init(&s, t, eps, er, ei);
   int L = series_scan(&s, &ev);
   cplx d = series_d(&s, L - 1);
   if (d_re) *d_re = d.re;
@@ -136,6 +245,56 @@ static double bailed_mag(const series_t* s, int j, double* yr, double* yi) {
   return *yr * *yr + *yi * *yi;
 }
 
+/* ---- scaled perturbation state (mirrors newman_b200/csrc/k3_scaled.cuh) ---------------------------
+ * delta = (dr, di) * 2^e. e == 0: a plain state, iterated exactly as before. e != 0: "scaled" state
+ * with max(|dr|, |di|) in [1, 2) at every re-normalisation point; used while |delta| is below what a
+ * double product can hold (pixel pitch < ~1e-150: delta*delta underflows; < 1e-308: delta itself).
+ * The step is the same expression for both (S = 2^e, S == 1 for plain states):
+ *      w  = fma(S, d, 2*Z[j])           (== fma(2, Z[j], d) bit for bit when S == 1)
+ *      d' = fma(-+di, wi, fma(dr, wr, eps/2^e))
+ *      z  = fma(S, d', Z[j+1])          (== Z[j+1] + d' when S == 1)
+ * States are re-normalised when created and before the step from every index j = 0 (mod 64). */
+#define E_TO_PLAIN (-300) /* a normalised state with exponent above this becomes plain */
+#define E_TO_SCALED (-400) /* a plain state whose larger component is below 2^this becomes scaled */
+#define RENORM_MASK 63
+
+typedef struct { double dr, di; int e; } pstate;
+
+static double pow2d(int e) { /* 2^e, flushed to zero below the normal range */
+  if (e < -1022) return 0.0;
+  if (e > 1023) return INFINITY;
+  return ldexp(1.0, e);
+}
+
+static pstate state_from_fec(fec_t d) {
+  pstate s;
+  if (d.re.m == 0.0 && d.im.m == 0.0) { s.dr = d.re.m; s.di = d.im.m; s.e = 0; return s; }
+  int E = d.re.m == 0.0 ? d.im.e : (d.im.m == 0.0 ? d.re.e : (d.re.e > d.im.e ? d.re.e : d.im.e));
+  if (E > E_TO_PLAIN) { s.dr = fe_to_double(d.re); s.di = fe_to_double(d.im); s.e = 0; return s; }
+  s.dr = d.re.m == 0.0 ? d.re.m : fe_scale(d.re.m, d.re.e - E);
+  s.di = d.im.m == 0.0 ? d.im.m : fe_scale(d.im.m, d.im.e - E);
+  s.e = E;
+  return s;
+}
+
+static void state_renorm(pstate* s) {
+  if (s->e == 0) {
+    double m = fmax(fabs(s->dr), fabs(s->di));
+    if (!(m < ldexp(1.0, E_TO_SCALED)) || m == 0.0) return;
+  }
+  fec_t d; d.re = fe_norm(s->dr, s->e); d.im = fe_norm(s->di, s->e);
+  *s = state_from_fec(d);
+}
+
+static double eps_scaled(fe_t eps, double eps0, int e) { /* eps / 2^e as a double; eps0: its plain value */
+  if (e == 0) return eps0;
+  if (eps.m == 0.0) return eps.m;
+  int k = eps.e - e;
+  if (k < -1000) return 0.0 * eps.m;
+  if (k > 1000) return eps.m > 0 ? INFINITY : -INFINITY;
+  return ldexp(eps.m, k);
+}
+
 int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, const double* eps_im, int nr,
                             int cardioid_mode, const uint8_t* mask, const int32_t* pix_list, int64_t n_list,
                             int mode, op_escape* out, int32_t* rq_pix, int32_t* rq_iter, op_stats* st) {
@@ -144,6 +303,7 @@ int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, co
   const int64_t W = pix_list ? n_list : (int64_t)nr * nc;
   int64_t n_rq = 0;
   uint64_t executed = 0, evals = 0, skipped = 0, rebased = 0;
+  const int scaled = t->eps_re_exp && t->eps_im_exp; /* floatexp eps => scaled delta states */
 
   /* Z[0] = 0, Z[j] = X[j-1]; gb[j] = glitch_tol * |Z[j]|^2 (0 at j = 0 and at the escaped iterate) */
   double* Z = (double*)calloc((size_t)2 * (Jmax + 1), sizeof(double));
@@ -162,7 +322,11 @@ int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, co
     }
     int r = pix / nc, c = pix - r * nc;
     series_t s;
-    series_init(&s, t, eps_re[c], eps_im[r]);
+    const fec_t eps = eps_of(t, eps_re, eps_im, r, c);
+    /* eps of a plain (e == 0) state: the host's double, or the floatexp value flushed into double range */
+    const double er0 = scaled ? fe_to_double(eps.re) : eps_re[c];
+    const double ei0 = scaled ? fe_to_double(eps.im) : eps_im[r];
+    series_init(&s, t, eps, er0, ei0);
     int L = series_scan(&s, &evals);
 
     /* phase 2, mandelbrot.cpp:183-207 */
@@ -183,21 +347,27 @@ int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, co
     if (L >= N) { e->iterations = N; e->smoothing = 0.0f; continue; } /* :212 loop is empty */
 
     /* phase 3 as perturbation: state (j, delta) pairs delta with Z[j]; it = j + off */
-    cplx d0 = series_d(&s, found);
-    double dr = d0.re, di = d0.im;
-    const double er = s.er, ei = s.ei;
+    pstate ps;
+    if (scaled) ps = state_from_fec(series_d_fe(&s, found));
+    else { cplx d0 = series_d(&s, found); ps.dr = d0.re; ps.di = d0.im; ps.e = 0; }
+    double S = pow2d(ps.e), er = eps_scaled(eps.re, er0, ps.e), ei = eps_scaled(eps.im, ei0, ps.e);
     int j = L, off = -1;
     for (;;) {
+      if (scaled && (j & RENORM_MASK) == 0) {
+        state_renorm(&ps);
+        S = pow2d(ps.e); er = eps_scaled(eps.re, er0, ps.e); ei = eps_scaled(eps.im, ei0, ps.e);
+      }
+      double dr = ps.dr, di = ps.di;
       double xr = Z[2 * j], xi = Z[2 * j + 1];
-      double wr = fma(2.0, xr, dr);
-      double wi = fma(2.0, xi, di);
+      double wr = fma(S, dr, 2.0 * xr);   /* == fma(2.0, xr, dr) when S == 1 */
+      double wi = fma(S, di, 2.0 * xi);
       double ndr = fma(-di, wi, fma(dr, wr, er));
       double ndi = fma(di, wr, fma(dr, wi, ei));
-      dr = ndr; di = ndi;
+      ps.dr = dr = ndr; ps.di = di = ndi;
       ++j;
       executed++;
-      double zr = Z[2 * j] + dr;
-      double zi = Z[2 * j + 1] + di;
+      double zr = fma(S, dr, Z[2 * j]);   /* == Z + d when S == 1 */
+      double zi = fma(S, di, Z[2 * j + 1]);
       double zmag = fma(zi, zi, zr * zr);
       if (zmag > BAILOUT2) { /* bailedOut, :61, :216-219 */
         e->iterations = j + off;
@@ -212,12 +382,17 @@ int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, co
           break;
         }
       } else {
-        double dmag = fma(di, di, dr * dr);
+        double tr = S * dr, ti = S * di; /* delta itself (exact when S == 1) */
+        double dmag = fma(ti, ti, tr * tr);
         rebase = zmag < dmag;
       }
       if (j + off + 1 >= N) { e->iterations = N; e->smoothing = 0.0f; break; } /* :226-228 */
       if (j == Jmax) rebase = 1; /* outlived the reference orbit */
-      if (rebase) { rebased++; off = j + off; j = 0; dr = zr; di = zi; }
+      if (rebase) {
+        rebased++; off = j + off; j = 0;
+        ps.dr = zr; ps.di = zi; ps.e = 0;
+        S = 1.0; er = er0; ei = ei0;
+      }
     }
   }
   free(Z); free(gb);

@@ -22,6 +22,8 @@ typedef struct {
   int32_t M, N, has_escape, reserved;
   double tol, glitch_tol;
   const double *x_hi, *x_lo, *a, *b, *c; /* same layout as nm_deep_tables */
+  const int32_t *a_exp, *b_exp, *c_exp;  /* floatexp series: a/b/c are mantissas, these the exponents */
+  const int32_t *eps_re_exp, *eps_im_exp; /* floatexp eps (=> scaled delta states): eps_* are mantissas */
 } op_tables;
 
 typedef struct {

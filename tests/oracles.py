@@ -33,7 +33,9 @@ def sha(a):
 class OpTables(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("has_escape", C.c_int32), ("reserved", C.c_int32),
                 ("tol", C.c_double), ("glitch_tol", C.c_double),
-                ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p)]
+                ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
+                ("a_exp", C.c_void_p), ("b_exp", C.c_void_p), ("c_exp", C.c_void_p),
+                ("eps_re_exp", C.c_void_p), ("eps_im_exp", C.c_void_p)]
 
 
 class OpStats(C.Structure):
@@ -75,17 +77,36 @@ def vp(a):
 class Tables:
     """Host-side deep tables (numpy, float64, interleaved re/im) as both oracles and the device want them."""
 
-    def __init__(self, x_hi, x_lo, a, b, c, N, tol, glitch_tol=1e-6):
+    def __init__(self, x_hi, x_lo, a, b, c, N, tol, glitch_tol=1e-6, exps=None, eps_exps=None):
+        """exps = (a_exp, b_exp, c_exp): floatexp series, a/b/c are then mantissas (0.5 <= |m| < 1).
+        eps_exps = (eps_re_exp, eps_im_exp): floatexp eps (the eps arrays handed to the render call
+        are then mantissas) => scaled delta states."""
         self.x_hi, self.x_lo, self.a, self.b, self.c = [np.ascontiguousarray(v, dtype=np.float64) for v in
                                                         (x_hi, x_lo, a, b, c)]
         self.M = len(self.a) // 2
         self.has_escape = 1 if len(self.x_hi) // 2 == self.M + 1 else 0
         self.N, self.tol, self.glitch_tol = N, tol, glitch_tol
+        self.exps = None if exps is None else [np.ascontiguousarray(v, dtype=np.int32) for v in exps]
+        self.eps_exps = None if eps_exps is None else [np.ascontiguousarray(v, dtype=np.int32) for v in eps_exps]
 
     def op(self):
+        ex = [None] * 3 if self.exps is None else [v.ctypes.data for v in self.exps]
+        ee = [None] * 2 if self.eps_exps is None else [v.ctypes.data for v in self.eps_exps]
         return OpTables(M=self.M, N=self.N, has_escape=self.has_escape, reserved=0, tol=self.tol,
                         glitch_tol=self.glitch_tol, x_hi=self.x_hi.ctypes.data, x_lo=self.x_lo.ctypes.data,
-                        a=self.a.ctypes.data, b=self.b.ctypes.data, c=self.c.ctypes.data)
+                        a=self.a.ctypes.data, b=self.b.ctypes.data, c=self.c.ctypes.data,
+                        a_exp=ex[0], b_exp=ex[1], c_exp=ex[2], eps_re_exp=ee[0], eps_im_exp=ee[1])
+
+    def floatexp(self, eps_re=None, eps_im=None):
+        """The same tables in floatexp form (numpy frexp == mpf_get_d_2exp for doubles): for tests that
+        run both modes on one view. With eps arrays: also returns their (mantissa, exponent) split."""
+        ms, es = zip(*[np.frexp(v) for v in (self.a, self.b, self.c)])
+        t = Tables(self.x_hi, self.x_lo, ms[0], ms[1], ms[2], self.N, self.tol, self.glitch_tol, exps=es)
+        if eps_re is None:
+            return t
+        (mr, er), (mi, ei) = np.frexp(eps_re), np.frexp(eps_im)
+        t.eps_exps = [np.ascontiguousarray(er, dtype=np.int32), np.ascontiguousarray(ei, dtype=np.int32)]
+        return t, np.ascontiguousarray(mr), np.ascontiguousarray(mi)
 
 
 def p_render_deep(t, eps_re, eps_im, cardioid_mode=0, mask=None, pix_list=None, mode=0, out=None):
@@ -275,9 +296,18 @@ class OracleDevice:
 
     def frame_deep(self, tables, eps_re, eps_im, cardioid_mode=0, mask=None, pix_list=None, mode=0):
         keep = tables._keep
-        arr = keep if isinstance(keep, dict) else dict(zip(("x_hi", "x_lo", "a", "b", "c"), keep))
+        if isinstance(keep[0], dict):     # pipeline.TableSet.tables(): (arrays, row-restricted eps_im exponents)
+            arr, eps_im_e = keep
+            exps = [np.asarray(arr[k]) for k in ("a_e", "b_e", "c_e")] if "a_e" in arr else None
+            eps_exps = None
+            if "eps_re_e" in arr:
+                eps_exps = [np.asarray(arr["eps_re_e"]), np.asarray(arr["eps_im_e"] if eps_im_e is None else eps_im_e)]
+        else:                              # Device.make_tables(): (x_hi, x_lo, a, b, c, exps, eps_exps)
+            arr = dict(zip(("x_hi", "x_lo", "a", "b", "c"), keep[:5]))
+            exps = None if keep[5][0] is None else [np.asarray(v) for v in keep[5]]
+            eps_exps = None if keep[6][0] is None else [np.asarray(v) for v in keep[6]]
         self._t = Tables(np.asarray(arr["x_hi"]), np.asarray(arr["x_lo"]), np.asarray(arr["a"]), np.asarray(arr["b"]),
-                         np.asarray(arr["c"]), tables.N, tables.tol, tables.glitch_tol)
+                         np.asarray(arr["c"]), tables.N, tables.tol, tables.glitch_tol, exps=exps, eps_exps=eps_exps)
         self._args = (np.ascontiguousarray(eps_re), np.ascontiguousarray(eps_im), cardioid_mode, mask,
                       None if pix_list is None else np.ascontiguousarray(pix_list, dtype=np.int32), mode)
         self.nr, self.nc = len(eps_im), len(eps_re)
