@@ -96,12 +96,57 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _have_ref():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles
+    return oracles.have_ref()
+
+
 def view_for(cfg):
     import newman_b200
     return newman_b200.Mandelbrot(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
 
 
 # ---------------------------------------------------------------------------------------------
+_PORT = {}
+
+
+def _port_worker(pix):
+    """Oracle-P (the CPU restatement, oracle/oracle_p.c) on a pixel list: the CPU baseline for views the
+    compiled reference cannot render (pixel pitch < ~1e-97: SIGFPE, SURVEY.md finding 3)."""
+    import oracles
+    t, er, ei = _PORT["args"]
+    t0 = time.perf_counter()
+    out, rq_pix, rq_it, st = oracles.p_render_deep(t, er, ei, pix_list=np.ascontiguousarray(pix, dtype=np.int32), mode=1)
+    secs = time.perf_counter() - t0
+    return out.reshape(-1)[pix], st["executed_iters"], secs
+
+
+def cpu_port_sample(cfg, h, fe, n_pix, procs):
+    """cpu_baseline kind "port": Oracle-P, one process per core, strided sample, single rebasing pass."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracles
+    oracles.oraclep()
+    total = cfg["nr"] * cfg["nc"]
+    pix = (np.arange(n_pix, dtype=np.int64) * (total // n_pix) + (total // n_pix) // 3).astype(np.int32)
+    exps = (h["a_e"], h["b_e"], h["c_e"]) if fe >= 1 else None
+    a, b, c = (h["a_m"], h["b_m"], h["c_m"]) if fe >= 1 else (h["a"], h["b"], h["c"])
+    t = oracles.Tables(h["x_hi"], h["x_lo"], a, b, c, cfg["N"], cfg["tol"], exps=exps,
+                       eps_exps=(h["eps_re_e"], h["eps_im_e"]) if fe == 2 else None)
+    _PORT["args"] = (t, h["eps_re_m"] if fe == 2 else h["eps_re"], h["eps_im_m"] if fe == 2 else h["eps_im"])
+    chunks = [pix[i::procs] for i in range(procs)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_port_worker, chunks)
+    wall = time.perf_counter() - t0
+    it = np.zeros(n_pix, dtype=np.int32)
+    for i, (o, _, _) in enumerate(res):
+        it[i::procs] = o["iterations"]
+    return dict(pix=pix, it=it, executed=int(sum(r[1] for r in res)), busy=max(r[2] for r in res), wall=wall, procs=procs,
+                kind="port")
+
+
 def cpu_reference_sample(cfg, probe, n_pix, procs):
     """Time the reference's own per-pixel code (Oracle-R: /root/reference/mandelbrot.cpp compiled
     unmodified) on a strided sample of the workload, one process per core (the reference is
@@ -133,7 +178,7 @@ def cpu_reference_sample(cfg, probe, n_pix, procs):
     else:           # loop 'for (i = d.size(); i < N; i++)' (mandelbrot.cpp:212): it-L+1 trips if escaped, N-L if not
         executed = int(np.where(it >= Ls, np.where(it < N, it - Ls + 1, N - Ls), 0).sum(dtype=np.int64))
     return dict(pix=pix, it=it, sm=sm, L=Ls, executed=executed, effective=int(np.minimum(it, N).sum()), wall=wall,
-                busy=busy, setup=setup, procs=procs)
+                busy=busy, setup=setup, procs=procs, kind="reference")
 
 
 def _ref_worker(a):
@@ -168,32 +213,42 @@ def run_reference(args):
     procs = os.cpu_count() or 1
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracles
-    if not oracles.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnewman_ref.so not built (needs /root/reference once)"}))
-        return 0
+    from newman_b200 import pipeline
     t0 = time.perf_counter()
-    probe = (0, 0)
+    probe, h, fe = (0, 0), None, 0
     if cfg["sz"] is not None:
-        h = view_for(cfg).host_tables()
+        h = view_for(cfg).host_tables(*(cfg.get("probe") or (-1, -1)))
         probe = h["probe"]
+        fe = pipeline.floatexp_level(h)
     pre_s = time.perf_counter() - t0
+    # the compiled reference where it is defined; the CPU port where it is not (SIGFPE below ~1e-97) or
+    # where oracle/_ref was not built
+    use_port = fe >= 1 or not oracles.have_ref()
+    if use_port and h is None:
+        use_port = False
+        if not oracles.have_ref():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built and the plain-double workload has no port leg"}))
+            return 0
     n_pix = max(procs, args.cpu_sample // 2)
     vals, walls = [], []
     for s in range(args.warmup + args.steps):
-        r = cpu_reference_sample(cfg, probe, n_pix, procs)
+        r = cpu_port_sample(cfg, h, fe, n_pix, procs) if use_port else cpu_reference_sample(cfg, probe, n_pix, procs)
         if s >= args.warmup:
             vals.append(r["executed"] / r["busy"] / 1e9)
             walls.append(r["busy"])
     value = statistics.mean(vals)
     frac = n_pix / (cfg["nr"] * cfg["nc"])
+    kind = "port" if use_port else "reference"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(walls), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "mpf+f64", "data": "synthetic",
         "config": {"workload": cfg["label"], "grid": [cfg["nr"], cfg["nc"]], "N": cfg["N"], "tol": cfg["tol"]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
                          "sample": f"{n_pix} strided samples of the {cfg['nr']}x{cfg['nc']} raster per step "
-                                   f"({frac:.2e} of a frame), per-pixel getIterations; probe search excluded"},
+                                   f"({frac:.2e} of a frame), " +
+                                   ("Oracle-P (series scan + FP64 perturbation; the compiled reference cannot render this view)"
+                                    if use_port else "per-pixel getIterations") + "; probe search excluded"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "frame_s_extrapolated": statistics.mean(walls) / frac, "host_precompute_s": pre_s, "gpu_launches": 0,
     }
@@ -311,7 +366,8 @@ def run_ours(args):
         primary = None
     else:
         # ---- deep workload: tables (rank 0 -> broadcast), discover the secondary-reference chain ----
-        primary = bcast_tables(-1, -1)
+        pr = cfg.get("probe") or (-1, -1)    # pinned findProbe winner (workloads.py) or run the search
+        primary = bcast_tables(pr[0], pr[1])
         chain_dev = []
 
         def discover(gp):
@@ -459,15 +515,20 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             procs = os.cpu_count() or 1
             probe = (0, 0) if hw else primary.probe
-            r = cpu_reference_sample(cfg, probe, max(procs, args.cpu_sample), procs)
+            if not hw and (primary.fe >= 1 or not _have_ref()):
+                r = cpu_port_sample(cfg, view.host_tables(probe[0], probe[1]), primary.fe, max(procs, args.cpu_sample), procs)
+            else:
+                r = cpu_reference_sample(cfg, probe, max(procs, args.cpu_sample), procs)
             if r is not None:
                 pix = r["pix"]
                 mine = grid.reshape(-1)[pix]
                 eq = float((mine["iterations"] == r["it"]).mean())
                 line["cpu_baseline"] = {
-                    "value": r["executed"] / r["busy"] / 1e9, "unit": UNIT, "cores": r["procs"], "kind": "reference",
-                    "sample": f"{len(pix)} strided samples of the {nr}x{nc} raster ({len(pix) / (nr * nc):.2e} of a frame), "
-                              f"reference getIterations per pixel, {r['busy']:.1f}s busy on the slowest core; probe search excluded",
+                    "value": r["executed"] / r["busy"] / 1e9, "unit": UNIT, "cores": r["procs"], "kind": r["kind"],
+                    "sample": f"{len(pix)} strided samples of the {nr}x{nc} raster ({len(pix) / (nr * nc):.2e} of a frame), " +
+                              ("reference getIterations per pixel" if r["kind"] == "reference" else
+                               "Oracle-P per pixel (the compiled reference cannot render this view: SIGFPE below ~1e-97)") +
+                              f", {r['busy']:.1f}s busy on the slowest core; probe search excluded",
                     "frame_s_extrapolated": r["busy"] * (nr * nc) / len(pix),
                     "parity_on_sample": {"equal_count_frac": eq, "n": int(len(pix))}}
             else:

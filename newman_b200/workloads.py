@@ -13,6 +13,20 @@ CFG2_CENTER = ("-0.74364388703715870430384830821904672021612495145852386428093",
                "0.13182590420531197076319081924762009190133695173845852602774")
 
 
+# The same filament followed on to 1e-100 (tools/zoom_view.py, 50 more decades of greedy high-count
+# zoom): M ~ 1.34e5, escape counts 1.33e5..1.39e5, no interior samples. Pixel pitch 2.6e-104 — beyond
+# the reference's depth limit (SURVEY finding 3): floatexp series, double deltas.
+CFG3_CENTER = ("-0.74364388703715870430384830821904672021612495145852387494331251251878512463051109529950754825484219375",
+               "0.13182590420531197076319081924762009190133695173845845225394611001630987887560439346518997163860480250")
+
+
+# findProbe winners (mandelbrot.cpp:73-95: first probe in scan order with the longest orbit) for the
+# cfg3 grids the bench uses, found once with the product's own find_probe (27 360 candidate orbits of
+# ~1.3e5 arbitrary-precision iterations each: minutes of host time, so the bench does not repeat it).
+# {(nr, nc): (row, col)}; grids not listed run the probe search.
+CFG3_PROBE = {(8640, 15360): (6480, 5760)}   # M = 144 219; 212 s on 8 host cores
+
+
 def _dec(fr, digits=40):
     """Fraction -> scientific decimal string (exact to `digits` significant digits)."""
     if fr == 0:
@@ -26,6 +40,11 @@ def _dec(fr, digits=40):
     m = (f.numerator * 10 ** digits) // f.denominator
     s = str(m)
     return f"{s[0]}.{s[1:]}e{e}"
+
+
+def _probe_for(table, nr, nc, y_mult):
+    p = table.get((nr, nc))
+    return None if p is None else (p[0] * y_mult + y_mult - 1, p[1])
 
 
 def config(name, scale=1, y_mult=1):
@@ -44,4 +63,12 @@ def config(name, scale=1, y_mult=1):
         sz = (_dec(4 * d / nc), _dec(3 * d / (nr * y_mult)))
         return dict(nr=nr * y_mult, nc=nc, N=N, sz=sz, center=CFG2_CENTER, tol=1e-10, sc=sc,
                     label="cfg2: 1920x1080 zoom at 1e-50, N=65536, series+perturbation tol 1e-10, 2x multisampling")
+    if name == "cfg3":
+        nr, nc, N, sc = 8640 // scale, 15360 // scale, 1 << 20, 4
+        d = Fraction(1, 10 ** 100)
+        sz = (_dec(4 * d / nc), _dec(3 * d / (nr * y_mult)))
+        return dict(nr=nr * y_mult, nc=nc, N=N, sz=sz, center=CFG3_CENTER, tol=1e-10, sc=sc,
+                    # weak-scaling variants (y_mult x the rows): the same reference POINT, i.e. row r*y + y - 1
+                    probe=_probe_for(CFG3_PROBE, nr, nc, y_mult),
+                    label="cfg3: 3840x2160 beauty render at 1e-100, N=2^20, 4x multisampling (floatexp series)")
     raise KeyError(name)
