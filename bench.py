@@ -61,30 +61,45 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Spawn the sampler (nvidia-smi takes a few 100 ms to deliver its first line: call this well
+        before the timed region and bracket the region itself with mark_begin()/mark_end())."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.03]   # a line reports the ~20 ms before it arrives
+        if not inside and self.rows:                                    # region shorter than a sampling period
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - t1))[1]]
         sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -396,6 +411,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ------------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         frame(True)
 
@@ -405,16 +422,16 @@ def run_ours(args):
     dev.sync()
 
     # ---- timed: device-resident ---------------------------------------------------------------------
-    sampler = ClockSampler(local)
     stats_total.clear()
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         frame(True)
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     st_dev = dict(stats_total)
