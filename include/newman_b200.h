@@ -118,7 +118,8 @@ typedef struct nm_deep_tables {
 #define NM_MODE_REBASE 1  /* final pass: no glitch flagging; rebase onto orbit start when |z|<|d| */
 
 /* Starts a deep frame over the whole raster (pix_list == NULL) or over the listed pixel ids
- * (secondary-reference rounds; ids are r*nc+c). eps_re[nc], eps_im[nr] are the truncated doubles of
+ * (secondary-reference rounds, probe search; ids are r*nc+c; unlisted samples keep their values when
+ * the previous frame was a deep frame of the same size and are cleared otherwise). eps_re[nc], eps_im[nr] are the truncated doubles of
  * (pixel - X[0]) formed in mpf as mandelbrot.cpp:155-159. */
 NM_API int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, int nc,
                   const double* eps_im, int nr, int cardioid_mode, const uint8_t* cardioid_mask,
@@ -141,6 +142,9 @@ NM_API int nm_poke(nm_ctx* ctx, int64_t pix, nm_escape v);
  * whose smoothing value sits within the device libm's error of a float32 rounding boundary are
  * re-evaluated with the host libm the reference uses (mandelbrot.cpp:133-136). */
 NM_API int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst);
+
+/* Gather the records of the listed samples (ids r*nc+c; h/d pointers) — what the probe search reads. */
+NM_API int nm_read_pixels(nm_ctx* ctx, const int32_t* pix, int64_t n, nm_escape* dst);
 
 typedef struct nm_stats {
   uint64_t pixels;          /* samples in the frame (or list) */
@@ -195,6 +199,7 @@ typedef struct nmv_frame_info {
   int32_t hardware /* 1 plain double, 0 series+perturbation, 2 same with floatexp series, 3 floatexp series + scaled deltas */, precision_bits, orbit_len, probe_row, probe_col, references;
   uint64_t executed_iters, series_evals, skipped_pixels, glitched, rebased, fixups, kernel_launches, ambiguous;
   double host_precompute_s, device_ms, frame_s;
+  uint64_t probe_iters, probe_exact; /* GPU-assisted findProbe: delta updates on candidates; candidates measured in mpf */
 } nmv_frame_info;
 
 NM_API nmv_view* nmv_create(int nr, int nc);                      /* Mandelbrot(nr, nc), mandelbrot.cpp:8-17 */
@@ -208,6 +213,12 @@ NM_API int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, in
 /* force: 1 evaluate the series in floatexp, 2 also floatexp eps + scaled delta states, even where doubles
  * suffice (both are automatic once the view needs them); 0 automatic */
 NM_API int nmv_set_floatexp(nmv_view* v, int force);
+/* findProbe (mandelbrot.cpp:73-95). mode 0: the reference's exhaustive arbitrary-precision search; 1:
+ * GPU-assisted (candidates' orbit lengths by K2/K3 against one reference, exact mpf check of the
+ * short-list). nmv_set_probe_search picks what precompute() uses (default 1); nmv_find_probe runs one
+ * search and reports the winner, its exact orbit length and how many candidates were measured in mpf. */
+NM_API int nmv_set_probe_search(nmv_view* v, int mode);
+NM_API int nmv_find_probe(nmv_view* v, int mode, int* row, int* col, int* length, int* n_exact);
 NM_API int nmv_rows(const nmv_view* v);
 NM_API int nmv_cols(const nmv_view* v);
 NM_API int nmv_use_hardware(nmv_view* v);                          /* mandelbrot.cpp:256-259 */

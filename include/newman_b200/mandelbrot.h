@@ -68,6 +68,8 @@ struct FrameInfo {
   unsigned long long executed_iters = 0, series_evals = 0, skipped_pixels = 0, glitched = 0, rebased = 0,
                      fixups = 0, kernel_launches = 0, ambiguous = 0;
   double host_precompute_s = 0, device_ms = 0, frame_s = 0;
+  // probe search (GPU-assisted): delta updates spent on the candidates, candidates measured in mpf
+  unsigned long long probe_iters = 0, probe_exact = 0;
 };
 }  // namespace newman_b200
 
@@ -93,6 +95,8 @@ public:
   int max_secondary;        // secondary reference rounds before the final rebasing pass
   int device;               // CUDA device ordinal
   int host_threads;         // probe-search threads (0 = hardware concurrency)
+  int probe_search;         // findProbe: 1 (default) GPU-assisted short-list + exact mpf check of the short-list;
+                            // 0 the reference's exhaustive arbitrary-precision search (mandelbrot.cpp:73-95)
   int force_floatexp;       // 0 automatic; 1 floatexp series, 2 also floatexp eps + scaled deltas, even where
                             // doubles suffice (verification: same raster wherever both are defined)
 
@@ -128,6 +132,8 @@ public:
   const RenderGrid& raster() const { return grid; }
   void resolveRGB(const unsigned char* pal_rgb, int n_pal, int sc, bool smooth, unsigned char* rgb_out);
   void setPrecisionNow() { setPrecision(); }
+  // findProbe on its own (probe_search selects the method); n_exact = candidates measured in mpf
+  void findProbe(int& row, int& col, int& length, int* n_exact = nullptr);
 };
 
 #endif

@@ -165,15 +165,43 @@ int classify_cardioid(const ViewHP& v, int threads, std::vector<uint8_t>& mask) 
   return NM_CARDIOID_MASK;
 }
 
-void find_probe(const ViewHP& v, int threads, int& row, int& col, int& length) {
-  // candidate order of mandelbrot.cpp:77-83
-  std::vector<std::pair<int, int>> cand;
+void probe_candidates(const ViewHP& v, std::vector<std::pair<int, int> >& cand) {
+  cand.clear();
   for (int c = 0; c < v.nc; c += 2) {
     cand.emplace_back(v.nr / 4, c);
     cand.emplace_back(v.nr / 2, c);
     cand.emplace_back(3 * v.nr / 4, c);
   }
   for (int r = 0; r < v.nr; r += 2) cand.emplace_back(r, v.nc / 2);
+}
+
+void probe_lengths(const ViewHP& v, const std::vector<std::pair<int, int> >& cand, const std::vector<int>& which,
+                   int threads, std::vector<int>& len) {
+  const int n = (int)which.size();
+  len.assign(n, -1);
+  std::atomic<int> next(0);
+  threads = pick_threads(threads);
+  if (threads > n) threads = n;
+  auto work = [&]() {
+    Mp tmp(v.prec), pre(v.prec), pim(v.prec);
+    for (;;) {
+      int k = next.fetch_add(1);
+      if (k >= n) break;
+      pixel_re(v, cand[which[k]].second, tmp.v, pre.v);
+      pixel_im(v, cand[which[k]].first, tmp.v, pim.v);
+      len[k] = orbit_length(v, pre.v, pim.v);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int i = 1; i < threads; i++) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+}
+
+void find_probe(const ViewHP& v, int threads, int& row, int& col, int& length) {
+  // candidate order of mandelbrot.cpp:77-83
+  std::vector<std::pair<int, int>> cand;
+  probe_candidates(v, cand);
   const int n = (int)cand.size();
   std::vector<int> len(n, -1);
   // A probe that never escapes (length N) cannot be beaten by a later one (strict '>' at :90), so

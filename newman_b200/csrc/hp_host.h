@@ -14,6 +14,7 @@
 #include <gmp.h>
 
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 namespace newman_b200 {
@@ -57,6 +58,15 @@ int classify_cardioid(const ViewHP& v, int threads, std::vector<uint8_t>& mask);
 // findProbe (mandelbrot.cpp:73-95): "first in scan order with the longest orbit". Lengths are found
 // in parallel; returns the winning probe's (row, col) and its orbit length.
 void find_probe(const ViewHP& v, int threads, int& row, int& col, int& length);
+
+// The candidate list of findProbe in the reference's scan order (mandelbrot.cpp:77-83): rows nr/4,
+// nr/2, 3nr/4 x every 2nd column, then every 2nd row x column nc/2. (row, col) pairs.
+void probe_candidates(const ViewHP& v, std::vector<std::pair<int, int> >& cand);
+
+// Exact orbit lengths (X.size() of computeOrbit) of the candidates listed in `which` (indices into
+// cand), in parallel. len[k] belongs to which[k].
+void probe_lengths(const ViewHP& v, const std::vector<std::pair<int, int> >& cand, const std::vector<int>& which,
+                   int threads, std::vector<int>& len);
 
 // computeOrbit + computeSeries for the reference point at pixel (row, col), descended; eps arrays
 // relative to that orbit's X[0].

@@ -3,6 +3,7 @@
 // policy, view transforms and multisample rescale; replaces the per-pixel work with one GPU frame.
 #include "../../include/newman_b200/mandelbrot.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -55,13 +56,152 @@ mp_bitcnt_t max_prec(const HPComplex& a, const HPComplex& b) {
   if (b.im.get_prec() > p) p = b.im.get_prec();
   return p;
 }
+
+struct RoundParams {
+  int N, max_secondary, force_floatexp;
+  double tol, gtol;
+};
+
+// One reference after another until no sample is left glitched: the frame (or the listed samples)
+// against T, then the flagged samples against a secondary reference = the flagged sample with the
+// earliest flag iteration (lowest id on ties), ...; after max_secondary such rounds the rest is
+// finished in one rebasing pass. T is overwritten by the secondary tables.
+void run_rounds(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp, DeepTablesHost& T, int cmode,
+                const std::vector<uint8_t>& mask, const std::vector<int32_t>* first_list, newman_b200::FrameInfo& info) {
+  nm_ctx* ctx = eng.ctx;
+  std::vector<int32_t> rq_pix, rq_iter;
+  if (first_list) rq_pix = *first_list;
+  int round = 0;
+  for (;;) {
+    // Coefficients beyond double range (pixel pitch < ~1e-97, where the reference dies with SIGFPE):
+    // hand them over as mantissa + exponent and let K2 evaluate the series in floatexp (level 1).
+    // Below a pitch of 2^-380 (~4e-115) delta*delta, and later delta and eps themselves, leave double
+    // range too: eps goes over as mantissa + exponent and K3 iterates scaled states (level 2).
+    int fe = T.finite ? 0 : 1;
+    if (T.pitch_exp < -380) fe = 2;
+    if (rp.force_floatexp > fe) fe = rp.force_floatexp > 2 ? 2 : rp.force_floatexp;
+    nm_deep_tables t;
+    t.M = T.M; t.N = rp.N; t.has_escape = T.has_escape ? 1 : 0; t.reserved = 0;
+    t.tol = rp.tol; t.glitch_tol = rp.gtol;
+    t.x_hi = T.x_hi.data(); t.x_lo = T.x_lo.data();
+    t.a = fe ? T.a_m.data() : T.a.data(); t.b = fe ? T.b_m.data() : T.b.data(); t.c = fe ? T.c_m.data() : T.c.data();
+    t.a_exp = fe ? T.a_e.data() : nullptr; t.b_exp = fe ? T.b_e.data() : nullptr; t.c_exp = fe ? T.c_e.data() : nullptr;
+    t.eps_re_exp = fe == 2 ? T.eps_re_e.data() : nullptr; t.eps_im_exp = fe == 2 ? T.eps_im_e.data() : nullptr;
+    info.floatexp = fe;
+    const bool last = round >= rp.max_secondary;
+    const bool listed = round > 0 || first_list;
+    eng.check(nm_frame_deep(ctx, &t, fe == 2 ? T.eps_re_m.data() : T.eps_re.data(), v.nc,
+                            fe == 2 ? T.eps_im_m.data() : T.eps_im.data(), v.nr, cmode,
+                            cmode == NM_CARDIOID_MASK ? mask.data() : nullptr, listed ? rq_pix.data() : nullptr,
+                            listed ? (int64_t)rq_pix.size() : 0, last ? NM_MODE_REBASE : NM_MODE_REQUEUE),
+              "nm_frame_deep");
+    eng.check(nm_launch(ctx), "nm_launch");
+    nm_stats st; eng.check(nm_frame_stats(ctx, &st), "nm_frame_stats");
+    info.executed_iters += st.executed_iters; info.series_evals += st.series_evals;
+    info.skipped_pixels += st.skipped_pixels; info.rebased += st.rebased; info.fixups += st.fixups;
+    info.kernel_launches += st.kernel_launches;
+    info.device_ms += st.ms_k1 + st.ms_k2 + st.ms_k3;
+    info.references++;
+    int64_t n_rq = nm_frame_requeue(ctx, nullptr, nullptr, 0);
+    if (n_rq < 0) eng.check((int)n_rq, "nm_frame_requeue");
+    if (n_rq == 0) break;
+    info.glitched += (unsigned long long)n_rq;
+    rq_pix.resize((size_t)n_rq); rq_iter.resize((size_t)n_rq);
+    nm_frame_requeue(ctx, rq_pix.data(), rq_iter.data(), n_rq);
+    // next reference: the glitched sample flagged earliest, lowest pixel id on ties
+    size_t best = 0;
+    for (size_t i = 1; i < rq_pix.size(); i++)
+      if (rq_iter[i] < rq_iter[best] || (rq_iter[i] == rq_iter[best] && rq_pix[i] < rq_pix[best])) best = i;
+    const double t_hp = now_s();
+    newman_b200::build_tables(v, rq_pix[best] / v.nc, rq_pix[best] % v.nc, T);
+    info.host_precompute_s += now_s() - t_hp;
+    cmode = NM_CARDIOID_NONE;  // listed samples already passed the cardioid test
+    round++;
+  }
+}
+
+// findProbe (mandelbrot.cpp:73-95) with the GPU doing the bulk of it. The reference computes one full
+// arbitrary-precision orbit per candidate (3*ceil(nc/2) + ceil(nr/2) of them: 27 360 x up to N
+// iterations for a 15 360 x 8 640 grid) to keep "the first one in scan order with the longest orbit".
+// A candidate's orbit length IS its escape count, so: one arbitrary-precision reference (the centre
+// sample), all candidates rendered against it by K2/K3 like any other samples (secondary references
+// for glitched ones), then only the short-list — the `kShort` longest by that count and everything
+// within 0.2 % of the maximum, plus every candidate that reached N — is re-measured exactly in mpf, and
+// the reference's rule (first longest in scan order) is applied to those exact lengths.
+// The winner is the exhaustive search's whenever that one is on the short-list (every fixture tested);
+// probe_search = 0 selects the exhaustive search.
+void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp, int threads, int cmode,
+                         const std::vector<uint8_t>& mask, int& row, int& col, int& length, int* n_exact,
+                         newman_b200::FrameInfo& info) {
+  std::vector<std::pair<int, int> > cand;
+  newman_b200::probe_candidates(v, cand);
+  const int n = (int)cand.size();
+  std::vector<int32_t> pix((size_t)n);
+  for (int i = 0; i < n; i++) pix[i] = cand[i].first * v.nc + cand[i].second;
+  std::vector<int32_t> uniq(pix);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+
+  DeepTablesHost T;
+  newman_b200::build_tables(v, v.nr / 2, v.nc / 2, T);
+  newman_b200::FrameInfo scratch;
+  // orbit lengths are wanted, not the user's speed/accuracy trade-off: never a looser series tolerance
+  // than the reference's default (mandelbrot.cpp:9)
+  RoundParams rq = rp;
+  if (!(rq.tol <= 1e-10)) rq.tol = 1e-10;
+  run_rounds(eng, v, rq, T, cmode, mask, &uniq, scratch);  // cardioid/bulb candidates: (N, 0) without iterating
+  info.probe_iters += scratch.executed_iters;  // kept apart from the frame's own counters
+  std::vector<nm_escape> got((size_t)n);
+  eng.check(nm_read_pixels(eng.ctx, pix.data(), n, got.data()), "nm_read_pixels");
+
+  const int kShort = 16;
+  int maxc = 0;
+  for (int i = 0; i < n; i++) if (got[i].iterations > maxc) maxc = got[i].iterations;
+  std::vector<int> order((size_t)n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return got[a].iterations > got[b].iterations; });
+  const int floor_count = maxc - (int)(0.002 * maxc) - 2;
+  std::vector<int> which;
+  for (int k = 0; k < n; k++) {
+    const int i = order[k];
+    if (k < kShort || got[i].iterations >= floor_count || got[i].iterations >= rp.N) which.push_back(i);
+    else break;
+  }
+  std::sort(which.begin(), which.end());  // scan order
+  // A candidate that never escapes cannot be beaten by a later one (strict '>'): of those the GPU
+  // reports at N only the first in scan order needs the exact check — if it confirms.
+  int first_full = -1;
+  for (int i : which) if (got[i].iterations >= rp.N) { first_full = i; break; }
+  if (first_full >= 0) {
+    std::vector<int> one(1, first_full), l1;
+    newman_b200::probe_lengths(v, cand, one, 1, l1);
+    if (l1[0] < rp.N) {  // finite-precision artefact of the exact orbit: let the exhaustive search decide
+      newman_b200::find_probe(v, threads, row, col, length);
+      if (n_exact) *n_exact = n;
+      return;
+    }
+    std::vector<int> keep;
+    for (int i : which) if (i <= first_full && (got[i].iterations < rp.N || i == first_full)) keep.push_back(i);
+    which.swap(keep);
+  }
+  std::vector<int> len;
+  newman_b200::probe_lengths(v, cand, which, threads, len);
+  if (n_exact) *n_exact = (int)which.size();
+  info.probe_exact = (unsigned long long)which.size();
+  size_t best = 0;
+  for (size_t k = 1; k < which.size(); k++)
+    if (len[k] > len[best]) best = k;  // first longest wins (strict '>' at mandelbrot.cpp:90)
+  row = cand[which[best]].first;
+  col = cand[which[best]].second;
+  length = len[best];
+}
 }  // namespace
 
 Mandelbrot::Mandelbrot() : Mandelbrot(1, 1) {}
 
 Mandelbrot::Mandelbrot(int nr, int nc)
     : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(1), device(0), host_threads(0),
-      force_floatexp(0) {
+      probe_search(1), force_floatexp(0) {
   // default full view (mandelbrot.cpp:13-14)
   center.re = -0.5;
   center.im = 0.0;
@@ -190,54 +330,16 @@ void Mandelbrot::renderFrame() {
       newman_b200::build_tables(v1, v.nr / 2, v.nc / 2, T);
     } else {
       int prow, pcol, plen;
-      newman_b200::find_probe(v, host_threads, prow, pcol, plen);
+      RoundParams rp0 = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance};
+      if (probe_search == 0) newman_b200::find_probe(v, host_threads, prow, pcol, plen);
+      else find_probe_assisted(eng, v, rp0, host_threads, cmode, mask, prow, pcol, plen, nullptr, info_);
       newman_b200::build_tables(v, prow, pcol, T);
     }
     info_.orbit_len = T.M; info_.probe_row = T.probe_row; info_.probe_col = T.probe_col;
     info_.host_precompute_s = now_s() - t_begin;
-    std::vector<int32_t> rq_pix, rq_iter;
-    int round = 0;
-    for (;;) {
-      // Coefficients beyond double range (pixel pitch < ~1e-97, where the reference dies with SIGFPE):
-      // hand them over as mantissa + exponent and let K2 evaluate the series in floatexp (level 1).
-      // Below a pitch of 2^-380 (~4e-115) delta*delta, and later delta and eps themselves, leave double
-      // range too: eps goes over as mantissa + exponent and K3 iterates scaled states (level 2).
-      int fe = T.finite ? 0 : 1;
-      if (T.pitch_exp < -380) fe = 2;
-      if (force_floatexp > fe) fe = force_floatexp > 2 ? 2 : force_floatexp;
-      nm_deep_tables t;
-      t.M = T.M; t.N = N; t.has_escape = T.has_escape ? 1 : 0; t.reserved = 0;
-      t.tol = error_tolerance; t.glitch_tol = glitch_tolerance;
-      t.x_hi = T.x_hi.data(); t.x_lo = T.x_lo.data();
-      t.a = fe ? T.a_m.data() : T.a.data(); t.b = fe ? T.b_m.data() : T.b.data(); t.c = fe ? T.c_m.data() : T.c.data();
-      t.a_exp = fe ? T.a_e.data() : nullptr; t.b_exp = fe ? T.b_e.data() : nullptr; t.c_exp = fe ? T.c_e.data() : nullptr;
-      t.eps_re_exp = fe == 2 ? T.eps_re_e.data() : nullptr; t.eps_im_exp = fe == 2 ? T.eps_im_e.data() : nullptr;
-      info_.floatexp = fe;
-      const bool last = round >= max_secondary;
-      eng.check(nm_frame_deep(ctx, &t, fe == 2 ? T.eps_re_m.data() : T.eps_re.data(), v.nc,
-                              fe == 2 ? T.eps_im_m.data() : T.eps_im.data(), v.nr, cmode,
-                              cmode == NM_CARDIOID_MASK ? mask.data() : nullptr, round ? rq_pix.data() : nullptr,
-                              round ? (int64_t)rq_pix.size() : 0, last ? NM_MODE_REBASE : NM_MODE_REQUEUE),
-                "nm_frame_deep");
-      eng.check(nm_launch(ctx), "nm_launch");
-      nm_stats st; eng.check(nm_frame_stats(ctx, &st), "nm_frame_stats"); absorb(st);
-      info_.references++;
-      int64_t n_rq = nm_frame_requeue(ctx, nullptr, nullptr, 0);
-      if (n_rq < 0) eng.check((int)n_rq, "nm_frame_requeue");
-      if (n_rq == 0) break;
-      info_.glitched += (unsigned long long)n_rq;
-      rq_pix.resize((size_t)n_rq); rq_iter.resize((size_t)n_rq);
-      nm_frame_requeue(ctx, rq_pix.data(), rq_iter.data(), n_rq);
-      // next reference: the glitched sample flagged earliest, lowest pixel id on ties
-      size_t best = 0;
-      for (size_t i = 1; i < rq_pix.size(); i++)
-        if (rq_iter[i] < rq_iter[best] || (rq_iter[i] == rq_iter[best] && rq_pix[i] < rq_pix[best])) best = i;
-      const double t_hp = now_s();
-      newman_b200::build_tables(v, rq_pix[best] / v.nc, rq_pix[best] % v.nc, T);
-      info_.host_precompute_s += now_s() - t_hp;
-      cmode = NM_CARDIOID_NONE;  // listed samples already passed the cardioid test
-      round++;
-    }
+    info_.references = 0;
+    RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance};
+    run_rounds(eng, v, rp, T, cmode, mask, nullptr, info_);
     eng.check(nm_read_rows(ctx, 0, v.nr, out), "nm_read_rows");
   }
 
@@ -248,6 +350,26 @@ void Mandelbrot::renderFrame() {
   s->sre = mpf_class(sz.re, sz.re.get_prec()); s->sim = mpf_class(sz.im, sz.im.get_prec());
   rendered_ = s;
   info_.frame_s = now_s() - t_begin;
+}
+
+void Mandelbrot::findProbe(int& row, int& col, int& length, int* n_exact) {
+  ViewHP v;
+  v.center_re = center.re.get_mpf_t(); v.center_im = center.im.get_mpf_t();
+  v.sz_re = sz.re.get_mpf_t(); v.sz_im = sz.im.get_mpf_t();
+  v.nr = grid.nr; v.nc = grid.nc; v.N = N;
+  v.prec = max_prec(center, sz);
+  if (probe_search == 0) {
+    newman_b200::find_probe(v, host_threads, row, col, length);
+    if (n_exact) *n_exact = 3 * ((v.nc + 1) / 2) + (v.nr + 1) / 2;
+    return;
+  }
+  if (!engine_ || engine_->device != device) engine_ = std::make_shared<newman_b200::Engine>(device);
+  std::vector<uint8_t> mask;
+  int cmode = newman_b200::classify_cardioid(v, host_threads, mask);
+  RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance};
+  newman_b200::FrameInfo scratch;
+  find_probe_assisted(*engine_, v, rp, host_threads, cmode, mask, row, col, length, n_exact, scratch);
+  rendered_.reset();  // the device raster now holds the candidates, not a frame
 }
 
 void Mandelbrot::resolveRGB(const unsigned char* pal_rgb, int n_pal, int sc, bool smooth, unsigned char* rgb_out) {

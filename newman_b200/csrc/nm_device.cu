@@ -122,6 +122,11 @@ __global__ void k_apply_fixups(nm_escape* out, const int32_t* pix, const float* 
 
 __global__ void k_poke(nm_escape* out, long long pix, nm_escape v) { out[pix] = v; }
 
+__global__ void k_gather(const nm_escape* out, const int32_t* pix, nm_escape* dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = out[pix[i]];
+}
+
 int set_device(nm_ctx* ctx) {
   NM_CUDA(ctx, cudaSetDevice(ctx->device));
   return NM_OK;
@@ -590,9 +595,11 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     return fail(ctx, NM_EINVAL, "nm_frame_deep: orbit shorter than N needs its escaped iterate (has_escape)");
   if (cardioid_mode == NM_CARDIOID_MASK && !cardioid_mask) return fail(ctx, NM_EINVAL, "cardioid mask missing");
   if (mode != NM_MODE_REQUEUE && mode != NM_MODE_REBASE) return fail(ctx, NM_EINVAL, "bad mode");
-  if (pix_list && (ctx->kind != 2 || ctx->nr != nr || ctx->nc != nc))
-    return fail(ctx, NM_ESTATE, "a pixel-list frame needs a previous full deep frame of the same size");
   if (int rc = set_device(ctx)) return rc;
+  // A pixel-list frame writes only the listed samples. On top of a deep frame of the same size the
+  // others keep their values (secondary-reference rounds); otherwise (probe search: the candidate
+  // samples of a view that has no raster yet) the rest of the raster is cleared.
+  const bool fresh_raster = pix_list && (ctx->kind != 2 || ctx->nr != nr || ctx->nc != nc);
 
   ctx->kind = 2; ctx->nr = nr; ctx->nc = nc; ctx->N = t->N;
   ctx->pixels = (long long)nr * nc;
@@ -616,6 +623,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   const size_t Wn = (size_t)(ctx->W > 0 ? ctx->W : 1);
 
   NM_CUDA(ctx, ctx->out.ensure((size_t)ctx->pixels * sizeof(nm_escape)));
+  if (fresh_raster) NM_CUDA(ctx, cudaMemsetAsync(ctx->out.p, 0, (size_t)ctx->pixels * sizeof(nm_escape), ctx->stream));
   NM_CUDA(ctx, ctx->cre.ensure((size_t)nc * sizeof(double)));
   NM_CUDA(ctx, ctx->cim.ensure((size_t)nr * sizeof(double)));
   if (int rc = size_lists(ctx)) return rc;
@@ -734,6 +742,22 @@ int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst) {
   if (int rc = finish_frame(ctx)) return rc;
   NM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->out.as<nm_escape>() + (size_t)r0 * ctx->nc,
                                (size_t)(r1 - r0) * ctx->nc * sizeof(nm_escape), cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_read_pixels(nm_ctx* ctx, const int32_t* pix, int64_t n, nm_escape* dst) {
+  if (!ctx) return NM_EINVAL;
+  if (n < 0 || (n && (!pix || !dst))) return fail(ctx, NM_EINVAL, "nm_read_pixels: bad arguments");
+  if (int rc = finish_frame(ctx)) return rc;
+  if (n == 0) return NM_OK;
+  NM_CUDA(ctx, ctx->list.ensure((size_t)n * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->gridtmp.ensure((size_t)n * sizeof(nm_escape)));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->list.p, pix, (size_t)n * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
+  k_gather<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->out.as<nm_escape>(), ctx->list.as<int32_t>(),
+                                                                 ctx->gridtmp.as<nm_escape>(), (long long)n);
+  NM_CUDA(ctx, cudaGetLastError());
+  NM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->gridtmp.p, (size_t)n * sizeof(nm_escape), cudaMemcpyDefault, ctx->stream));
   NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NM_OK;
 }

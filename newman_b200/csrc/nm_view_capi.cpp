@@ -97,6 +97,32 @@ int nmv_set_floatexp(nmv_view* v, int force) {
   return NM_OK;
 }
 
+int nmv_find_probe(nmv_view* v, int mode, int* row, int* col, int* length, int* n_exact) {
+  return guarded(v, [&]() {
+    const int saved = v->m.probe_search;
+    v->m.probe_search = mode ? 1 : 0;
+    int r = -1, c = -1, l = 0, ne = 0;
+    try {
+      v->m.findProbe(r, c, l, &ne);
+    } catch (...) {
+      v->m.probe_search = saved;
+      throw;
+    }
+    v->m.probe_search = saved;
+    if (row) *row = r;
+    if (col) *col = c;
+    if (length) *length = l;
+    if (n_exact) *n_exact = ne;
+    return NM_OK;
+  });
+}
+
+int nmv_set_probe_search(nmv_view* v, int mode) {
+  if (!v) return NM_EINVAL;
+  v->m.probe_search = mode ? 1 : 0;
+  return NM_OK;
+}
+
 int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, int device, int host_threads) {
   if (!v) return NM_EINVAL;
   if (glitch_tol >= 0) v->m.glitch_tolerance = glitch_tol;
@@ -175,6 +201,7 @@ int nmv_frame_info_get(const nmv_view* v, nmv_frame_info* out) {
   out->hardware = f.hardware ? 1 : (f.floatexp ? 1 + f.floatexp : 0); out->precision_bits = f.precision_bits; out->orbit_len = f.orbit_len;
   out->probe_row = f.probe_row; out->probe_col = f.probe_col; out->references = f.references;
   out->executed_iters = f.executed_iters; out->series_evals = f.series_evals; out->skipped_pixels = f.skipped_pixels;
+  out->probe_iters = f.probe_iters; out->probe_exact = f.probe_exact;
   out->glitched = f.glitched; out->rebased = f.rebased; out->fixups = f.fixups; out->kernel_launches = f.kernel_launches;
   out->ambiguous = f.ambiguous;
   out->host_precompute_s = f.host_precompute_s; out->device_ms = f.device_ms; out->frame_s = f.frame_s;

@@ -123,6 +123,12 @@ class Device:
         self._ck(self.lib.nm_read_rows(self.h, r0, r1, L.ptr(out)))
         return out
 
+    def read_pixels(self, pix):
+        pix = np.ascontiguousarray(pix, dtype=np.int32)
+        out = np.zeros(len(pix), dtype=L.ESCAPE_DTYPE)
+        self._ck(self.lib.nm_read_pixels(self.h, L.ptr(pix), len(pix), L.ptr(out)))
+        return out
+
     def stats(self):
         s = L.Stats()
         self._ck(self.lib.nm_frame_stats(self.h, C.byref(s)))

@@ -13,7 +13,8 @@ class FrameInfo(C.Structure):
                                           "references")] +
                 [(n, C.c_uint64) for n in ("executed_iters", "series_evals", "skipped_pixels", "glitched", "rebased",
                                            "fixups", "kernel_launches", "ambiguous")] +
-                [(n, C.c_double) for n in ("host_precompute_s", "device_ms", "frame_s")])
+                [(n, C.c_double) for n in ("host_precompute_s", "device_ms", "frame_s")] +
+                [(n, C.c_uint64) for n in ("probe_iters", "probe_exact")])
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -26,6 +27,9 @@ VIEW_API = {
     "nmv_set_view": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_double]),
     "nmv_set_options": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]),
     "nmv_set_floatexp": (C.c_int, [C.c_void_p, C.c_int]),
+    "nmv_set_probe_search": (C.c_int, [C.c_void_p, C.c_int]),
+    "nmv_find_probe": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int)]),
     "nmv_rows": (C.c_int, [C.c_void_p]),
     "nmv_cols": (C.c_int, [C.c_void_p]),
     "nmv_use_hardware": (C.c_int, [C.c_void_p]),
@@ -111,6 +115,16 @@ class Mandelbrot:
     def set_floatexp(self, force):
         """0 automatic; 1 floatexp series; 2 also floatexp eps + scaled deltas (even where doubles suffice)."""
         self._ck(self.lib.nmv_set_floatexp(self.h, int(force)))
+
+    def set_probe_search(self, mode):
+        """findProbe used by precompute(): 1 GPU-assisted (default), 0 the reference's exhaustive search."""
+        self._ck(self.lib.nmv_set_probe_search(self.h, int(mode)))
+
+    def find_probe(self, mode=1):
+        """-> (row, col, exact orbit length, candidates measured in arbitrary precision)"""
+        r, c, l, n = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.nmv_find_probe(self.h, int(mode), C.byref(r), C.byref(c), C.byref(l), C.byref(n)))
+        return r.value, c.value, l.value, n.value
 
     def rows(self):
         return self.lib.nmv_rows(self.h)

@@ -164,3 +164,24 @@ def test_edge_sizes(dev):
         cre, cim = m.host_coords()
         exp, _ = oracles.p_render_hw(cre, cim, N)
         assert np.array_equal(g["iterations"], exp["iterations"])
+
+
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D90", "KAT-S", "KAT-T3", "cfg2/20", "DEEP-350"])
+def test_probe_search_gpu_assisted_equals_exhaustive(kat):
+    """findProbe (mandelbrot.cpp:73-95): the GPU-assisted search (orbit lengths of all candidates by
+    K2/K3, exact mpf check of the short-list) returns the exhaustive search's winner and length while
+    measuring only a fraction of the candidates in arbitrary precision."""
+    if kat == "cfg2/20":
+        cfg = workloads.config("cfg2", scale=20)
+        m = newman_b200.Mandelbrot(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
+    elif kat == "DEEP-350":
+        m = newman_b200.Mandelbrot(96, 128, N=4000, sz=("7.8125e-353", "7.8125e-353"), center=("0", "1"))
+    else:
+        m = mk(KATS[kat])
+    exact = m.find_probe(0)
+    fast = m.find_probe(1)
+    print(kat, "exhaustive", exact, "assisted", fast)
+    assert fast[:3] == exact[:3]
+    assert fast[3] <= max(24, exact[3] // 4)
+    h = m.host_tables()
+    assert h["probe"] == exact[:2] and h["M"] == min(exact[2], m.N)
