@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=6144, help="pixels in the timed CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ymult", type=int, default=0, help="debug: force the weak-scaling row multiplier")
+    ap.add_argument("--floatexp", type=int, default=0, help="force the floatexp level (1 series, 2 + scaled deltas)")
+    ap.add_argument("--k3-group", type=int, default=-1, help="pixels per lane in k3_fast (4, 2; 0 = simple kernel)")
     return ap.parse_args()
 
 
@@ -294,6 +296,10 @@ def run_ours(args):
     dev.set_stream(stream.cuda_stream)
 
     cfg = workloads.config(args.workload, scale=args.scale, y_mult=args.ymult or world)
+    if args.floatexp:
+        cfg["floatexp"] = args.floatexp
+    if args.k3_group >= 0:
+        dev.set_option(newman_b200._lib.OPT_K3_GROUP, args.k3_group)
     nr, nc, N = cfg["nr"], cfg["nc"], cfg["N"]
     hw = cfg["sz"] is None
     rows = pipeline.local_rows(nr, rank, world)
@@ -381,7 +387,21 @@ def run_ours(args):
         primary = None
     else:
         # ---- deep workload: tables (rank 0 -> broadcast), discover the secondary-reference chain ----
-        pr = cfg.get("probe") or (-1, -1)    # pinned findProbe winner (workloads.py) or run the search
+        # findProbe (mandelbrot.cpp:73-95), GPU-assisted: rank 0 renders the candidates and checks the
+        # short-list in arbitrary precision; where workloads.py pins the exhaustive search's winner for
+        # this grid the two are compared (probe_matches_exhaustive)
+        probe_info = {}
+        if rank == 0:
+            t0 = time.perf_counter()
+            pr = view.find_probe(1)
+            host_pre[0] += time.perf_counter() - t0
+            probe_info = {"probe": [pr[0], pr[1]], "orbit_len": pr[2], "probe_exact_checks": pr[3],
+                          "probe_search_s": time.perf_counter() - t0}
+            if cfg.get("probe") and (args.ymult or world) == 1:
+                probe_info["probe_matches_exhaustive"] = tuple(cfg["probe"]) == (pr[0], pr[1])
+            pr = (pr[0], pr[1])
+        else:
+            pr = (0, 0)                       # ignored: rank 0's tables are broadcast
         primary = bcast_tables(pr[0], pr[1])
         chain_dev = []
 
@@ -529,6 +549,11 @@ def run_ours(args):
             "rebased_per_step": st_dev.get("rebased", 0) / args.steps, "fixups_per_step": st_dev.get("fixups", 0) / args.steps,
             "host_precompute_s": host_pre[0],
         }
+        if not hw:
+            line.update(probe_info)
+            line["floatexp_level"] = primary.fe
+            if args.k3_group >= 0:
+                line["config"]["k3_group"] = args.k3_group
         if world == 1 and not args.no_cpu_baseline:
             procs = os.cpu_count() or 1
             probe = (0, 0) if hw else primary.probe

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
 // before the step from j = 0 (mod 64)" is one test per lane and block; the per-slot scale S = 2^e and
 // eps / 2^e live in registers between re-normalisations.
 template <int P, bool SCALED>
-__global__ void __launch_bounds__(K3F_THREADS, ((P == 4 && !SCALED) ? 2 : (P == 4 ? 1 : (SCALED ? 2 : 3))))
+__global__ void __launch_bounds__(K3F_THREADS, (P == 4 ? 2 : (SCALED ? 2 : 3)))
 k3_fast(K3Params p, PixState* events) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
@@ -113,14 +113,14 @@ k3_fast(K3Params p, PixState* events) {
 
   // slot state: 0 empty/parked, 1 live, 2 exported (ev_* hold the state to hand to k3_events)
   double dr[P], di[P], er[P], ei[P], ev_dr[P], ev_di[P], S[P];
-  int pix[P], off[P], st[P], ev_j[P], sc[P], ev_e[P];
+  int pix[P], off[P], st[P], ev_j[P], sc[P];
   bool drained = false;
   int j = 0;
   unsigned long long executed = 0;
 #pragma unroll
   for (int s = 0; s < P; ++s) {
     dr[s] = di[s] = er[s] = ei[s] = ev_dr[s] = ev_di[s] = 0.0; S[s] = 1.0;
-    pix[s] = -1; off[s] = -1; st[s] = 0; ev_j[s] = 0; sc[s] = 0; ev_e[s] = 0;
+    pix[s] = -1; off[s] = -1; st[s] = 0; ev_j[s] = 0; sc[s] = 0;
   }
 
   mbar_wait(&bar, 0);
@@ -187,7 +187,7 @@ k3_fast(K3Params p, PixState* events) {
           const int room = (lim - j) >> 2;
           if (room > 0) { any_live = true; if (room < nb) nb = room; }
           else if (!(j == jend && j < p.Jmax && jN > j)) {
-            st[s] = 2; ev_dr[s] = dr[s]; ev_di[s] = di[s]; ev_j[s] = j; ev_e[s] = sc[s];
+            st[s] = 2; ev_dr[s] = dr[s]; ev_di[s] = di[s]; ev_j[s] = j;
             executed += (unsigned long long)(j - j_in);
             dr[s] = di[s] = er[s] = ei[s] = 0.0;
           }
@@ -253,7 +253,7 @@ k3_fast(K3Params p, PixState* events) {
 #pragma unroll
             for (int s = 0; s < P; ++s)
               if (st[s] == 1 && bad[s]) {
-                st[s] = 2; ev_dr[s] = dr0[s]; ev_di[s] = di0[s]; ev_j[s] = j; ev_e[s] = sc[s];
+                st[s] = 2; ev_dr[s] = dr0[s]; ev_di[s] = di0[s]; ev_j[s] = j;
                 executed += (unsigned long long)(j - j_in);
                 dr[s] = di[s] = er[s] = ei[s] = 0.0;
               }
@@ -276,7 +276,7 @@ k3_fast(K3Params p, PixState* events) {
       }
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
-        PixState q; q.dr = ev_dr[s]; q.di = ev_di[s]; q.pix = pix[s]; q.j = ev_j[s]; q.off = off[s]; q.e = SCALED ? ev_e[s] : 0;
+        PixState q; q.dr = ev_dr[s]; q.di = ev_di[s]; q.pix = pix[s]; q.j = ev_j[s]; q.off = off[s]; q.e = SCALED ? sc[s] : 0;  // an exported slot is parked: its exponent is never re-normalised
         events[slot] = q;
       }
       st[s] = 0; pix[s] = -1;
