@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=6144, help="pixels in the timed CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ymult", type=int, default=0, help="debug: force the weak-scaling row multiplier")
+    ap.add_argument("--frames", type=int, default=24, help="cfg5: key frames rendered per step (evenly spaced over the 600)")
     ap.add_argument("--floatexp", type=int, default=0, help="force the floatexp level (1 series, 2 + scaled deltas)")
     ap.add_argument("--k3-group", type=int, default=-1, help="pixels per lane in k3_fast (4, 2; 0 = simple kernel)")
     return ap.parse_args()
@@ -226,7 +227,10 @@ def run_reference(args):
     if rank != 0:
         return 0
     from newman_b200 import workloads
-    cfg = workloads.config(args.workload, scale=args.scale, y_mult=1)
+    if args.workload == "cfg5":   # one representative key frame of the video (depth 1e-75), bounded sample
+        cfg = workloads.video_frame(workloads.VIDEO_FRAMES // 2 - 1, scale=args.scale)
+    else:
+        cfg = workloads.config(args.workload, scale=args.scale, y_mult=1)
     procs = os.cpu_count() or 1
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracles
@@ -582,7 +586,196 @@ def run_ours(args):
         dist.destroy_process_group()
     return 0
 
+# ---------------------------------------------------------------------------------------------
+def run_video(args):
+    """--workload cfg5: key frames of the zoom video (BASELINE.json configs[4]; video.cpp / viewer.cpp:
+    441-453, 271-285 render one key frame per zoom step). Frames are independent views, so they are
+    sharded over the ranks round-robin with NO collective on the data path ("scaling": "strong": the
+    same set of frames whatever N). A step = every rank renders all of its frames once. The host
+    arbitrary-precision work per frame (GPU-assisted probe search, orbit, series) happens once outside
+    the timed region and is reported."""
+    import torch
+    import torch.distributed as dist
+    import newman_b200
+    from newman_b200 import pipeline, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    devt = torch.device("cuda", local)
+    dev = newman_b200.Device(local)
+    stream = torch.cuda.Stream(device=devt)
+    torch.cuda.set_stream(stream)
+    dev.set_stream(stream.cuda_stream)
+
+    all_rows = lambda ts, key: ts.arr[key]   # a rank renders whole frames: no row restriction
+    total_frames = workloads.VIDEO_FRAMES
+    n_sel = min(args.frames, total_frames)
+    sel = sorted(set(int(round(i * (total_frames - 1) / max(n_sel - 1, 1))) for i in range(n_sel)))
+    mine = sel[rank::world]
+    jobs = []
+    host_pre = 0.0
+    for k in mine:
+        cfg = workloads.video_frame(k, scale=args.scale)
+        t0 = time.perf_counter()
+        view = view_for(cfg)
+        view.set_options(device=local)
+        nr, nc, N = cfg["nr"], cfg["nc"], cfg["N"]
+        job = {"k": k, "cfg": cfg, "view": view, "hw": view.useHardware()}
+        if job["hw"]:
+            cre, cim = view.host_coords()
+            job["coords_h"] = [torch.from_numpy(cre).pin_memory(), torch.from_numpy(cim).pin_memory()]
+            job["coords_d"] = [t.to(devt) for t in job["coords_h"]]
+        else:
+            pr = view.find_probe(1)
+            mk = lambda d: pipeline.TableSet(d, N, cfg["tol"], 1e-6, pipeline.floatexp_level(d))
+            primary = mk(view.host_tables(pr[0], pr[1]))
+            chain = []
+
+            def discover(gp, view=view, mk=mk, chain=chain, nc=nc):
+                chain.append(mk(view.host_tables(gp // nc, gp % nc)))
+                return chain[-1]
+            res0 = pipeline.render_rounds(dev, primary, discover, nc, np.arange(nr), eps_rows=all_rows)
+            to_pin = lambda ts: ts.map(lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory())
+            job.update(primary_h=to_pin(primary), chain_h=[to_pin(t) for t in chain], refs=res0["refs"], orbit_len=pr[2])
+            job["primary_d"] = job["primary_h"].map(lambda t: t.to(devt))
+            job["chain_d"] = [t.map(lambda a: a.to(devt)) for t in job["chain_h"]]
+        job["out_h"] = torch.empty((nr, nc, 2), dtype=torch.int32).pin_memory()
+        job["host_s"] = time.perf_counter() - t0
+        host_pre += job["host_s"]
+        jobs.append(job)
+    torch.cuda.synchronize()
+
+    tot = {}
+
+    def add(st):
+        for k, v in st.items():
+            tot[k] = tot.get(k, 0) + v
+
+    def render(job, resident, read):
+        cfg = job["cfg"]
+        nr, nc, N = cfg["nr"], cfg["nc"], cfg["N"]
+        if job["hw"]:
+            c = job["coords_d"] if resident else job["coords_h"]
+            dev.frame_hw(c[0], c[1], N)
+            dev.launch()
+            for p in dev.ambiguous():
+                if job["view"].host_in_cardioid(int(p) // nc, int(p) % nc):
+                    dev.poke(int(p), N, 0.0)
+            add(dev.stats())
+        else:
+            it = iter(job["chain_d"] if resident else job["chain_h"])
+            res = pipeline.render_rounds(dev, job["primary_d"] if resident else job["primary_h"], lambda gp: next(it), nc,
+                                         np.arange(nr), eps_rows=all_rows)
+            assert res["refs"] == job["refs"]
+            for st in res["stats"]:
+                add(st)
+            if os.environ.get("NM_BENCH_DEBUG") and not job.get("dbg"):
+                job["dbg"] = True
+                print("frame", job["k"], "M", job["orbit_len"], "fe", job["primary_h"].fe, "refs", len(job["refs"]),
+                      [(round(st["ms_k2"], 2), round(st["ms_k3"], 2), st["series_evals"], st["executed_iters"], st["pixels"])
+                       for st in res["stats"]], file=sys.stderr)
+        if read:
+            dev.read_rows(0, nr, job["out_h"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        for job in jobs:
+            render(job, True, False)
+    peak_dfma, _ = dev.fp64_peak(0, 1 << 15)
+    peak_dadd, _ = dev.fp64_peak(1, 1 << 15)
+    dev.sync()
+
+    tot.clear()
+    barrier()
+    sampler.mark_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        for job in jobs:
+            render(job, True, False)
+    ev1.record(stream)
+    barrier()
+    sampler.mark_end()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    st_dev = dict(tot)
+
+    for job in jobs:
+        render(job, False, True)
+    tot.clear()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for job in jobs:
+            render(job, False, True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    st_e2e = dict(tot)
+
+    def allred(x, op=None):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=devt)
+        dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms = allred(ms, dist.ReduceOp.MAX)
+    e2e_s = allred(e2e_s, dist.ReduceOp.MAX)
+    executed = allred(st_dev.get("executed_iters", 0))
+    executed_e2e = allred(st_e2e.get("executed_iters", 0))
+    launches = allred(st_dev.get("kernel_launches", 0))
+    k_ms = allred(st_dev.get("ms_k3", 0.0) + st_dev.get("ms_k1", 0.0), dist.ReduceOp.MAX)
+    k2_ms = allred(st_dev.get("ms_k2", 0.0), dist.ReduceOp.MAX)
+    host_max = allred(host_pre, dist.ReduceOp.MAX)
+    h2d = allred(sum((j["primary_h"].nbytes() + sum(t.nbytes() for t in j["chain_h"])) if not j["hw"] else
+                     8 * (j["cfg"]["nr"] + j["cfg"]["nc"]) for j in jobs))
+    d2h = allred(sum(j["cfg"]["nr"] * j["cfg"]["nc"] * 8 for j in jobs))
+    n_hw = allred(sum(1 for j in jobs if j["hw"]))
+    if rank == 0:
+        # mixed frames: plain-double frames execute 8, perturbation frames 10 FP64 instructions per iteration
+        inst = executed / world * K3_INST_PER_ITER
+        achieved = inst / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        cfg0 = workloads.video_frame(0, scale=args.scale)
+        line = {
+            "metric": METRIC, "value": executed / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cfg5: zoom video, {len(sel)} of {total_frames} key frames {cfg0['nc']}x{cfg0['nr']}, depth 1 -> "
+                                   f"1e-{workloads.VIDEO_DEPTH}, N={workloads.VIDEO_N}, frames sharded round-robin over {world} GPU(s)",
+                       "frames": sel, "plain_double_frames": int(n_hw), "parallelism": f"frames x{world}",
+                       "l2": "each frame's state queues + raster exceed L2 from ~1e-20 on; tables L2/SMEM resident"},
+            "e2e": {"value": executed_e2e / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock, barrier+synchronize both sides"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "fp64_pipe", "kernel": "k3_fast/k3_level (FP64 perturbation) + k1_escape on the shallow frames",
+                         "achieved": achieved, "peak": peak_dadd / 1e9, "unit": "Ginst/s",
+                         "frac": achieved / (peak_dadd / 1e9) if peak_dadd else None, "traffic": None,
+                         "peak_source": "measured live: nm_fp64_peak DADD issue rate", "peak_dfma_ginst": peak_dfma / 1e9,
+                         "kernel_ms_per_step": k_ms / args.steps, "k2_ms_per_step": k2_ms / args.steps},
+            "executed_iters_per_step": executed / args.steps, "frames_per_step": len(sel),
+            "frames_per_s_device": len(sel) / (ms / args.steps * 1e-3), "frames_per_s_e2e": len(sel) / (e2e_s / args.steps),
+            "host_precompute_s": host_max,
+            "host_precompute_note": "slowest rank: GPU-assisted probe search + orbit + series + secondary references of its frames, once",
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
 
 if __name__ == "__main__":
     a = parse()
-    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))
+    if a.impl == "reference":
+        sys.exit(run_reference(a))
+    sys.exit(run_video(a) if a.workload == "cfg5" else run_ours(a))

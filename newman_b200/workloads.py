@@ -20,6 +20,11 @@ CFG3_CENTER = ("-0.7436438870371587043038483082190467202161249514585238749433125
                "0.13182590420531197076319081924762009190133695173845845225394611001630987887560439346518997163860480250")
 
 
+# ... and on to 1e-400 (150 more levels of the same greedy zoom, two decades per level, 12 x 16 samples):
+# the deep end of cfg4 (floatexp series + scaled deltas) and the path the cfg5 zoom video follows.
+CFG4_CENTER = CFG3_CENTER   # placeholder until tools/zoom_view.py has finished
+
+
 # findProbe winners (mandelbrot.cpp:73-95: first probe in scan order with the longest orbit) for the
 # cfg3 grids the bench uses, found once with the product's own find_probe (27 360 candidate orbits of
 # ~1.3e5 arbitrary-precision iterations each: minutes of host time, so the bench does not repeat it).
@@ -40,6 +45,24 @@ def _dec(fr, digits=40):
     m = (f.numerator * 10 ** digits) // f.denominator
     s = str(m)
     return f"{s[0]}.{s[1:]}e{e}"
+
+
+VIDEO_FRAMES = 600      # cfg5: key frames of the zoom video
+VIDEO_DEPTH = 150       # ... from depth 1 down to 1e-150
+VIDEO_N = 1 << 18       # iteration limit of every frame (the reference holds N fixed during a zoom,
+                        # viewer.cpp:283; counts on this zoom path reach ~2e5 at 1e-150)
+
+
+def video_frame(k, scale=1, frames=VIDEO_FRAMES):
+    """Key frame k of cfg5 (BASELINE.json configs[4]): 1280x720, depth D_k = 10^(-150 k / (frames-1)),
+    centred on the deep end of the zoom path (CFG4_CENTER), no multisampling."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 50
+    nr, nc = 720 // scale, 1280 // scale
+    d = Decimal(10) ** (Decimal(-VIDEO_DEPTH * k) / Decimal(frames - 1))
+    sz = (format(Decimal(4) * d / nc, ".40e"), format(Decimal(3) * d / nr, ".40e"))
+    return dict(nr=nr, nc=nc, N=VIDEO_N, sz=sz, center=CFG4_CENTER, tol=1e-10, sc=1, frame=k,
+                label=f"cfg5: zoom video key frame {k}/{frames}, 1280x720, depth 1e-{VIDEO_DEPTH * k / (frames - 1):.1f}")
 
 
 def _probe_for(table, nr, nc, y_mult):
