@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
   const int lane = threadIdx.x & 31;
   const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned long long evals = 0, skipped = 0, aligned_steps = 0;
+  int min_j = 0x7fffffff;
 
   // warp-uniform trip count: the tail of the loop body is warp-aggregated
   for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < p.W; base += stride) {
@@ -391,8 +392,11 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
       int bin = handoff_L;
       unsigned peers = __match_any_sync(FULL_MASK, bin);
       if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&p.hist[bin], (unsigned)__popc(peers));
+      if (bin >= 0 && bin < min_j) min_j = bin;
     }
   }
+  for (int o = 16; o; o >>= 1) min_j = min(min_j, __shfl_xor_sync(FULL_MASK, min_j, o));
+  if (lane == 0 && min_j != 0x7fffffff) atomicMin(&p.ctr[CTR_MINJ], (unsigned long long)min_j);
 
   for (int o = 16; o; o >>= 1) {
     evals += __shfl_xor_sync(FULL_MASK, evals, o);

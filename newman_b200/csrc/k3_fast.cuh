@@ -33,6 +33,7 @@
 namespace nm {
 
 constexpr int K3F_THREADS = 256;
+constexpr int K3_EVENT_BUDGET = 252;  // extra checked steps k3_events grants a freshly rebased state (multiple of 4)
 
 template <bool SCALED>
 __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab,
@@ -46,7 +47,16 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
     EpsVal<SCALED> eps;
     eps.load(eps_tab, e.pix);
     int steps = 0;
-    if (advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, 4, &steps)) {
+    bool cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, 4, &steps);
+    // A state that was just rebased onto the start of the orbit (it outlived the reference: |z| is
+    // large) nearly always escapes within a few steps: finish it here rather than carrying it through
+    // another sweep of (mostly empty) level launches. Same steps, same decisions, same order.
+    if (cont && e.j == 0) {
+      int more = 0;
+      cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, K3_EVENT_BUDGET, &more);
+      steps += more;
+    }
+    if (cont) {
       // carried into the next sweep (index is a multiple of 4 again: 0 after a rebase, block start + 4 else)
       unsigned long long slot = atomicAdd(carry_count, 1ULL);
       carry.d[slot] = make_double2(e.dr, e.di);
@@ -55,6 +65,7 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
       carry.pix[slot] = e.pix;
       if (SCALED) carry.e[slot] = e.e;
       atomicAdd(&hist[e.j], 1u);
+      atomicMin(&p.ctr[CTR_MINJ], (unsigned long long)e.j);
     }
     executed += (unsigned long long)steps;
   }

@@ -269,6 +269,7 @@ int launch_deep(nm_ctx* ctx) {
 
   NM_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
   NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(nbins + 2) * sizeof(unsigned), st));
+  NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_MINJ], 0xFF, sizeof(unsigned long long), st));
 
   CheckedParams ck;
   ck.Z = ctx->Z.as<double2>(); ck.gb = ctx->gb.as<double>(); ck.Jmax = ctx->Jmax; ck.N = ctx->N;
@@ -344,8 +345,17 @@ int launch_deep(nm_ctx* ctx) {
   const unsigned blocks = (unsigned)(ctx->sm_count * occ);
   NM_CUDA(ctx, cudaMemsetAsync(ccount, 0, 2 * sizeof(unsigned long long), st));
 
+  // Lowest table index any state of the coming sweep starts at: the levels below it have no work and
+  // are not launched (an empty launch still costs ~4 us; M/1024 of them per sweep add up on small
+  // frames). One 8-byte read-back + sync after K2; later sweeps piggy-back on the sweep-end read.
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr + 2, &ctr[CTR_MINJ], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  NM_CUDA(ctx, cudaStreamSynchronize(st));
+  unsigned long long min_j = ctx->h_ctr[2];
+
   for (int sweep = 0;; ++sweep) {
     const int par = sweep & 1;
+    int kstart = 0;
+    if (fast || sweep == 0) kstart = min_j >= (unsigned long long)(K * CH) ? K : (int)(min_j / (unsigned long long)CH);
     // chunk-sorted "fresh" list of this sweep: K2's hand-over (sweep 0) or the carried states
     const bool have_fresh = fast || sweep == 0;
     if (have_fresh) {
@@ -362,8 +372,9 @@ int launch_deep(nm_ctx* ctx) {
     NM_CUDA(ctx, cudaMemsetAsync(&rcount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ccount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_EVENTS], 0, sizeof(unsigned long long), st));
+    NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_MINJ], 0xFF, sizeof(unsigned long long), st));
     p.fresh = fresh_set(ctx, par);
-    for (int k = 0; k < K; ++k) {
+    for (int k = kstart; k < K; ++k) {
       p.k = k;
       if (k == 0) {
         p.cur = ctx->rq[par].as<PixState>();
@@ -407,7 +418,9 @@ int launch_deep(nm_ctx* ctx) {
     NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, fast ? &ccount[par ^ 1] : &rcount[par ^ 1], sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
     NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr + 1, &ctr[CTR_CANCEL], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr + 2, &ctr[CTR_MINJ], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     NM_CUDA(ctx, cudaStreamSynchronize(st));
+    min_j = ctx->h_ctr[2];
     if (ctx->h_ctr[0] == 0 || ctx->h_ctr[1] != 0) break;
   }
   NM_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
