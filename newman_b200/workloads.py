@@ -25,11 +25,15 @@ CFG3_CENTER = ("-0.7436438870371587043038483082190467202161249514585238749433125
 CFG4_CENTER = CFG3_CENTER   # placeholder until tools/zoom_view.py has finished
 
 
-# findProbe winners (mandelbrot.cpp:73-95: first probe in scan order with the longest orbit) for the
-# cfg3 grids the bench uses, found once with the product's own find_probe (27 360 candidate orbits of
-# ~1.3e5 arbitrary-precision iterations each: minutes of host time, so the bench does not repeat it).
-# {(nr, nc): (row, col)}; grids not listed run the probe search.
-CFG3_PROBE = {(8640, 15360): (6480, 5760)}   # M = 144 219; 212 s on 8 host cores
+# Winners of the reference's EXHAUSTIVE findProbe (mandelbrot.cpp:73-95: first probe in scan order with
+# the longest arbitrary-precision orbit), found once with the product's own find_probe(0), for
+# comparison with the GPU-assisted search the product uses by default. {(nr, nc): (row, col)}.
+CFG2_PROBE = {(2160, 3840): (1080, 1916)}    # M = 61 513; 6 840 candidates, 13 s on 8 host cores
+# At 1e-100 the criterion itself is ill-conditioned: the winner's orbit is 144 219 long in mpf at the
+# reference's precision but 135 735 by FP64 perturbation (a sample on a filament, where the count changes
+# at sub-pixel scale), while the candidates perturbation ranks highest (141 613 ...) are 138 429 ... in mpf.
+# The GPU-assisted search therefore settles on another probe here (probe search).
+CFG3_PROBE = {(8640, 15360): (6480, 5760)}   # M = 144 219; 27 360 candidates, 212 s on 8 host cores
 
 
 def _dec(fr, digits=40):
@@ -85,6 +89,7 @@ def config(name, scale=1, y_mult=1):
         d = Fraction(1, 10 ** 50)
         sz = (_dec(4 * d / nc), _dec(3 * d / (nr * y_mult)))
         return dict(nr=nr * y_mult, nc=nc, N=N, sz=sz, center=CFG2_CENTER, tol=1e-10, sc=sc,
+                    probe=_probe_for(CFG2_PROBE, nr, nc, y_mult),
                     label="cfg2: 1920x1080 zoom at 1e-50, N=65536, series+perturbation tol 1e-10, 2x multisampling")
     if name == "cfg3":
         nr, nc, N, sc = 8640 // scale, 15360 // scale, 1 << 20, 4
