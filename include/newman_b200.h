@@ -219,6 +219,7 @@ NM_API int nmv_set_floatexp(nmv_view* v, int force);
  * search and reports the winner, its exact orbit length and how many candidates were measured in mpf. */
 NM_API int nmv_set_probe_search(nmv_view* v, int mode);
 NM_API int nmv_find_probe(nmv_view* v, int mode, int* row, int* col, int* length, int* n_exact);
+NM_API int nmv_get_n(const nmv_view* v);                            /* the public field N (loadLegacy sets it) */
 NM_API int nmv_rows(const nmv_view* v);
 NM_API int nmv_cols(const nmv_view* v);
 NM_API int nmv_use_hardware(nmv_view* v);                          /* mandelbrot.cpp:256-259 */

@@ -132,6 +132,7 @@ int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, int devic
   return NM_OK;
 }
 
+int nmv_get_n(const nmv_view* v) { return v ? v->m.N : NM_EINVAL; }
 int nmv_rows(const nmv_view* v) { return v ? v->m.rows() : NM_EINVAL; }
 int nmv_cols(const nmv_view* v) { return v ? v->m.cols() : NM_EINVAL; }
 int nmv_use_hardware(nmv_view* v) { return v ? (v->m.useHardware() ? 1 : 0) : NM_EINVAL; }

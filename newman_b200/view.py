@@ -30,6 +30,7 @@ VIEW_API = {
     "nmv_set_probe_search": (C.c_int, [C.c_void_p, C.c_int]),
     "nmv_find_probe": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int)]),
+    "nmv_get_n": (C.c_int, [C.c_void_p]),
     "nmv_rows": (C.c_int, [C.c_void_p]),
     "nmv_cols": (C.c_int, [C.c_void_p]),
     "nmv_use_hardware": (C.c_int, [C.c_void_p]),
@@ -184,6 +185,11 @@ class Mandelbrot:
 
     def loadLegacy(self, fn):
         self._ck(self.lib.nmv_load_legacy(self.h, fn.encode()))
+        self.N = self.frame_N()
+
+    def frame_N(self):
+        """The C++ object's public field N."""
+        return self.lib.nmv_get_n(self.h)
 
     def save(self, fn):
         self._ck(self.lib.nmv_save(self.h, fn.encode()))

@@ -22,7 +22,9 @@ CFG3_CENTER = ("-0.7436438870371587043038483082190467202161249514585238749433125
 
 # ... and on to 1e-400 (150 more levels of the same greedy zoom, two decades per level, 12 x 16 samples):
 # the deep end of cfg4 (floatexp series + scaled deltas) and the path the cfg5 zoom video follows.
-CFG4_CENTER = CFG3_CENTER   # placeholder until tools/zoom_view.py has finished
+CFG4_CENTER = ("-0.743643887037158704303848308219046720216124951458523874943312512518785124630511095299507548254842193623512699502325002477007376750175249951002576257399759948750098509924740199245100005050232499982475747373769898997349737375520023512450270198510126242474500000000174249926745100487675767400270025017602019899499848482398492450487625994949499825000001020024499926265025249999762649265075232601500126",
+               "0.1318259042053119707631908192476200919013369517384584522539461100163098788756043934651899716386048025742425739925754975745124002473752524245075240125254999999999745099000026262525740000492574744899499848752624745025739923985100507575997573737575747449997499495100252499754974750124240075509899994848487424485000755024992575755098985050257449762600252600759999497625500025007399004975512551239999997575")
+# at 1e-400: M ~ 5.07e5, escape counts 5.05e5..5.09e5, ~9e3 delta updates per sample, no interior samples
 
 
 # Winners of the reference's EXHAUSTIVE findProbe (mandelbrot.cpp:73-95: first probe in scan order with
@@ -99,4 +101,10 @@ def config(name, scale=1, y_mult=1):
                     # weak-scaling variants (y_mult x the rows): the same reference POINT, i.e. row r*y + y - 1
                     probe=_probe_for(CFG3_PROBE, nr, nc, y_mult),
                     label="cfg3: 3840x2160 beauty render at 1e-100, N=2^20, 4x multisampling (floatexp series)")
+    if name == "cfg4":
+        nr, nc, N, sc = 4320 // scale, 7680 // scale, 1 << 22, 1
+        d = Fraction(1, 10 ** 400)
+        sz = (_dec(4 * d / nc), _dec(3 * d / (nr * y_mult)))
+        return dict(nr=nr * y_mult, nc=nc, N=N, sz=sz, center=CFG4_CENTER, tol=1e-10, sc=sc,
+                    label="cfg4: 7680x4320 view at 1e-400, N=4M (floatexp series + scaled floatexp deltas)")
     raise KeyError(name)
