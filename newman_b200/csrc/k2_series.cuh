@@ -453,33 +453,75 @@ __global__ void __launch_bounds__(256) k2_prepare(const double2* B, const double
   }
 }
 
-// Their prefix minima/maxima: one CTA walks the M entries in coalesced tiles of 1024; inside a tile a
-// warp-shuffle scan + one shared-memory hop, between tiles a running carry.
-__global__ void __launch_bounds__(1024) k2_prefix(int M, K2Filter f) {
-  __shared__ double s_w[4][32];
-  __shared__ double s_carry[4];
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  if (t < 4) s_carry[t] = (t == 3) ? -INFINITY : INFINITY;
-  __syncthreads();
-  for (int base = 0; base < M; base += 1024) {
-    const int i = base + t;
-    double v0 = INFINITY, v1 = INFINITY, v2 = INFINITY, v3 = -INFINITY;
-    if (i < M) { v0 = f.rlog[i]; v1 = f.ov[i]; v2 = f.a[i]; v3 = f.b[i]; }
-    for (int o = 1; o < 32; o <<= 1) {
-      double u0 = __shfl_up_sync(FULL_MASK, v0, o), u1 = __shfl_up_sync(FULL_MASK, v1, o);
-      double u2 = __shfl_up_sync(FULL_MASK, v2, o), u3 = __shfl_up_sync(FULL_MASK, v3, o);
-      if (lane >= o) { v0 = fmin(v0, u0); v1 = fmin(v1, u1); v2 = fmin(v2, u2); v3 = fmax(v3, u3); }
-    }
-    if (lane == 31) { s_w[0][wid] = v0; s_w[1][wid] = v1; s_w[2][wid] = v2; s_w[3][wid] = v3; }
-    __syncthreads();
-    double c0 = s_carry[0], c1 = s_carry[1], c2 = s_carry[2], c3 = s_carry[3];
-    for (int w = 0; w < wid; ++w) { c0 = fmin(c0, s_w[0][w]); c1 = fmin(c1, s_w[1][w]); c2 = fmin(c2, s_w[2][w]); c3 = fmax(c3, s_w[3][w]); }
-    v0 = fmin(v0, c0); v1 = fmin(v1, c1); v2 = fmin(v2, c2); v3 = fmax(v3, c3);
-    if (i < M) { f.pmin_rlog[i] = v0; f.pmin_ov[i] = v1; f.pmin_a[i] = v2; f.pmax_b[i] = v3; }
-    __syncthreads();
-    if (t == 1023) { s_carry[0] = v0; s_carry[1] = v1; s_carry[2] = v2; s_carry[3] = v3; }
-    __syncthreads();
+// Their prefix minima/maxima over the M entries, in three small launches (a single CTA walking the
+// whole table took 0.48 ms at M = 61 513, twice per frame):
+//   k2_prefix_tiles   one CTA per tile of 1024: inclusive scan inside the tile (warp shuffles + one
+//                     shared-memory hop), tile totals to tile_tot[4][n_tiles]
+//   k2_prefix_carry   one CTA: exclusive scan of the tile totals (n_tiles <= 4096 here: M <= 2^22)
+//   k2_prefix_apply   fold each tile's carry into its entries
+__device__ __forceinline__ void k2_scan4(double& v0, double& v1, double& v2, double& v3, int lane) {
+  for (int o = 1; o < 32; o <<= 1) {
+    double u0 = __shfl_up_sync(FULL_MASK, v0, o), u1 = __shfl_up_sync(FULL_MASK, v1, o);
+    double u2 = __shfl_up_sync(FULL_MASK, v2, o), u3 = __shfl_up_sync(FULL_MASK, v3, o);
+    if (lane >= o) { v0 = fmin(v0, u0); v1 = fmin(v1, u1); v2 = fmin(v2, u2); v3 = fmax(v3, u3); }
   }
+}
+
+__global__ void __launch_bounds__(1024) k2_prefix_tiles(int M, K2Filter f, double* tile_tot, int n_tiles) {
+  __shared__ double s_w[4][32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int i = blockIdx.x * 1024 + t;
+  double v0 = INFINITY, v1 = INFINITY, v2 = INFINITY, v3 = -INFINITY;
+  if (i < M) { v0 = f.rlog[i]; v1 = f.ov[i]; v2 = f.a[i]; v3 = f.b[i]; }
+  k2_scan4(v0, v1, v2, v3, lane);
+  if (lane == 31) { s_w[0][wid] = v0; s_w[1][wid] = v1; s_w[2][wid] = v2; s_w[3][wid] = v3; }
+  __syncthreads();
+  double c0 = INFINITY, c1 = INFINITY, c2 = INFINITY, c3 = -INFINITY;
+  for (int w = 0; w < wid; ++w) { c0 = fmin(c0, s_w[0][w]); c1 = fmin(c1, s_w[1][w]); c2 = fmin(c2, s_w[2][w]); c3 = fmax(c3, s_w[3][w]); }
+  v0 = fmin(v0, c0); v1 = fmin(v1, c1); v2 = fmin(v2, c2); v3 = fmax(v3, c3);
+  if (i < M) { f.pmin_rlog[i] = v0; f.pmin_ov[i] = v1; f.pmin_a[i] = v2; f.pmax_b[i] = v3; }
+  if (t == 1023) {
+    tile_tot[blockIdx.x] = v0; tile_tot[n_tiles + blockIdx.x] = v1;
+    tile_tot[2 * n_tiles + blockIdx.x] = v2; tile_tot[3 * n_tiles + blockIdx.x] = v3;
+  }
+}
+
+// exclusive scan of the tile totals, in place; each thread owns a contiguous run of tiles
+__global__ void __launch_bounds__(1024) k2_prefix_carry(double* tile_tot, int n_tiles) {
+  __shared__ double s_w[4][32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int per = (n_tiles + 1023) / 1024;
+  const int b0 = min(n_tiles, t * per), b1 = min(n_tiles, b0 + per);
+  double v0 = INFINITY, v1 = INFINITY, v2 = INFINITY, v3 = -INFINITY;
+  for (int b = b0; b < b1; ++b) {
+    v0 = fmin(v0, tile_tot[b]); v1 = fmin(v1, tile_tot[n_tiles + b]);
+    v2 = fmin(v2, tile_tot[2 * n_tiles + b]); v3 = fmax(v3, tile_tot[3 * n_tiles + b]);
+  }
+  double r0 = v0, r1 = v1, r2 = v2, r3 = v3;  // inclusive over this thread's run -> inclusive over threads
+  k2_scan4(r0, r1, r2, r3, lane);
+  if (lane == 31) { s_w[0][wid] = r0; s_w[1][wid] = r1; s_w[2][wid] = r2; s_w[3][wid] = r3; }
+  __syncthreads();
+  double c0 = INFINITY, c1 = INFINITY, c2 = INFINITY, c3 = -INFINITY;  // everything before this thread's run
+  for (int w = 0; w < wid; ++w) { c0 = fmin(c0, s_w[0][w]); c1 = fmin(c1, s_w[1][w]); c2 = fmin(c2, s_w[2][w]); c3 = fmax(c3, s_w[3][w]); }
+  double e0 = __shfl_up_sync(FULL_MASK, r0, 1), e1 = __shfl_up_sync(FULL_MASK, r1, 1);
+  double e2 = __shfl_up_sync(FULL_MASK, r2, 1), e3 = __shfl_up_sync(FULL_MASK, r3, 1);
+  if (lane > 0) { c0 = fmin(c0, e0); c1 = fmin(c1, e1); c2 = fmin(c2, e2); c3 = fmax(c3, e3); }
+  __syncthreads();
+  for (int b = b0; b < b1; ++b) {  // exclusive carry of tile b, then fold the tile in
+    const double t0 = tile_tot[b], t1 = tile_tot[n_tiles + b], t2 = tile_tot[2 * n_tiles + b], t3 = tile_tot[3 * n_tiles + b];
+    tile_tot[b] = c0; tile_tot[n_tiles + b] = c1; tile_tot[2 * n_tiles + b] = c2; tile_tot[3 * n_tiles + b] = c3;
+    c0 = fmin(c0, t0); c1 = fmin(c1, t1); c2 = fmin(c2, t2); c3 = fmax(c3, t3);
+  }
+}
+
+__global__ void __launch_bounds__(1024) k2_prefix_apply(int M, K2Filter f, const double* tile_tot, int n_tiles) {
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i >= M || blockIdx.x == 0) return;
+  const int b = blockIdx.x;
+  f.pmin_rlog[i] = fmin(f.pmin_rlog[i], tile_tot[b]);
+  f.pmin_ov[i] = fmin(f.pmin_ov[i], tile_tot[n_tiles + b]);
+  f.pmin_a[i] = fmin(f.pmin_a[i], tile_tot[2 * n_tiles + b]);
+  f.pmax_b[i] = fmax(f.pmax_b[i], tile_tot[3 * n_tiles + b]);
 }
 
 // Exclusive scan of the start-index histogram with every run rounded up to a multiple of G (the

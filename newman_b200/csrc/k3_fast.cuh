@@ -80,8 +80,7 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
 // before the step from j = 0 (mod 64)" is one test per lane and block; the per-slot scale S = 2^e and
 // eps / 2^e live in registers between re-normalisations.
 template <int P, bool SCALED>
-__global__ void __launch_bounds__(K3F_THREADS, (P == 4 ? 2 : (SCALED ? 2 : 3)))
-k3_fast(K3Params p, PixState* events) {
+__device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
   const int jbase = p.k * CH;
@@ -296,6 +295,23 @@ k3_fast(K3Params p, PixState* events) {
 
   for (int o = 16; o; o >>= 1) executed += __shfl_xor_sync(FULL_MASK, executed, o);
   if (lane == 0 && executed) atomicAdd(&p.ctr[CTR_EXECUTED], executed);
+}
+
+// A level with so few states that every one can have a lane of its own is latency bound: a lane's
+// pass takes 1024 x (P x 10 FP64 instructions issued from ONE warp, ~7 cycles apart) — 146 ns per
+// iteration with P = 4 on the tail levels of cfg2 against 31 ns with one pixel per lane. Such levels
+// (uniformly for the whole grid: the counts are launch-wide) run the same body with P = 1.
+constexpr unsigned long long K3F_SPARSE_MAX = 148ULL * 2 * K3F_THREADS;
+
+template <int P, bool SCALED>
+__global__ void __launch_bounds__(K3F_THREADS, (P == 4 ? 2 : (SCALED ? 2 : 3)))
+k3_fast(K3Params p, PixState* events) {
+  const int jbase = p.k * p.CH;
+  int l1 = jbase + p.CH;
+  if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
+  const unsigned long long n_states = (p.cur_count ? *p.cur_count : 0ULL) + (p.fresh_off[l1] - p.fresh_off[jbase]);
+  if (P > 1 && n_states <= K3F_SPARSE_MAX) k3_fast_body<1, SCALED>(p, events);
+  else k3_fast_body<P, SCALED>(p, events);
 }
 
 }  // namespace nm

@@ -315,8 +315,19 @@ int launch_deep(nm_ctx* ctx) {
     if (ctx->use_fe) k2_prepare<true><<<(ctx->M + 255) / 256, 256, 0, st>>>(k2.B, k2.C, k2.Be, k2.Ce, ctx->M, ctx->tol, k2.f);
     else k2_prepare<false><<<(ctx->M + 255) / 256, 256, 0, st>>>(k2.B, k2.C, k2.Be, k2.Ce, ctx->M, ctx->tol, k2.f);
     NM_CUDA(ctx, cudaGetLastError());
-    k2_prefix<<<1, 1024, 0, st>>>(ctx->M, k2.f);
-    NM_CUDA(ctx, cudaGetLastError());
+    {
+      const int n_tiles = (ctx->M + 1023) / 1024;
+      double* tile_tot = fb + 8 * Mn;  // [4][n_tiles]
+      k2_prefix_tiles<<<n_tiles, 1024, 0, st>>>(ctx->M, k2.f, tile_tot, n_tiles);
+      NM_CUDA(ctx, cudaGetLastError());
+      if (n_tiles > 1) {
+        k2_prefix_carry<<<1, 1024, 0, st>>>(tile_tot, n_tiles);
+        NM_CUDA(ctx, cudaGetLastError());
+        k2_prefix_apply<<<n_tiles, 1024, 0, st>>>(ctx->M, k2.f, tile_tot, n_tiles);
+        NM_CUDA(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 2;
+      }
+    }
     ctx->stats.kernel_launches += 2;
     launch_k2<false>(ctx, k2, (unsigned)b2);
   } else {
@@ -647,7 +658,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->a.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->b.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->c.ensure((size_t)M * sizeof(double2)));
-  NM_CUDA(ctx, ctx->filt.ensure((size_t)M * 8 * sizeof(double)));
+  NM_CUDA(ctx, ctx->filt.ensure(((size_t)M * 8 + 4 * ((size_t)M / 1024 + 1)) * sizeof(double)));
   for (int i = 0; i < 2; i++) {
     NM_CUDA(ctx, ctx->fa_d[i].ensure(Wn * sizeof(double2)));
     NM_CUDA(ctx, ctx->fa_i[i].ensure(Wn * 4 * sizeof(int32_t)));
