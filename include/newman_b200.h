@@ -143,6 +143,11 @@ NM_API int nm_poke(nm_ctx* ctx, int64_t pix, nm_escape v);
  * re-evaluated with the host libm the reference uses (mandelbrot.cpp:133-136). */
 NM_API int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst);
 
+/* Same with a destination row pitch: row r lands at dst + (r - r0) * dst_pitch_bytes. A rank that renders
+ * the interleaved rows rank, rank+N, ... of a frame writes its band straight into the shared (pinned)
+ * host raster with pitch N * nc * 8 — every GPU over its own PCIe link, no funnel through one GPU. */
+NM_API int nm_read_rows_pitched(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst_pitch_bytes);
+
 /* Gather the records of the listed samples (ids r*nc+c; h/d pointers) — what the probe search reads. */
 NM_API int nm_read_pixels(nm_ctx* ctx, const int32_t* pix, int64_t n, nm_escape* dst);
 

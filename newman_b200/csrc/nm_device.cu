@@ -770,6 +770,19 @@ int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst) {
   return NM_OK;
 }
 
+int nm_read_rows_pitched(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst_pitch_bytes) {
+  if (!ctx) return NM_EINVAL;
+  const size_t row_bytes = (size_t)ctx->nc * sizeof(nm_escape);
+  if (r0 < 0 || r1 > ctx->nr || r0 > r1 || !dst || dst_pitch_bytes < row_bytes)
+    return fail(ctx, NM_EINVAL, "nm_read_rows_pitched: bad range or pitch");
+  if (int rc = finish_frame(ctx)) return rc;
+  if (r1 > r0)
+    NM_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch_bytes, ctx->out.as<nm_escape>() + (size_t)r0 * ctx->nc, row_bytes, row_bytes,
+                                   (size_t)(r1 - r0), cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
 int nm_read_pixels(nm_ctx* ctx, const int32_t* pix, int64_t n, nm_escape* dst) {
   if (!ctx) return NM_EINVAL;
   if (n < 0 || (n && (!pix || !dst))) return fail(ctx, NM_EINVAL, "nm_read_pixels: bad arguments");

@@ -123,6 +123,10 @@ class Device:
         self._ck(self.lib.nm_read_rows(self.h, r0, r1, L.ptr(out)))
         return out
 
+    def read_rows_pitched(self, r0, r1, dst_ptr, pitch_bytes):
+        """Rows [r0, r1) to host/device address dst_ptr with a row pitch (interleaved bands of a shared raster)."""
+        self._ck(self.lib.nm_read_rows_pitched(self.h, r0, r1, C.c_void_p(dst_ptr), pitch_bytes))
+
     def read_pixels(self, pix):
         pix = np.ascontiguousarray(pix, dtype=np.int32)
         out = np.zeros(len(pix), dtype=L.ESCAPE_DTYPE)

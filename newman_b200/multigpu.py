@@ -54,3 +54,56 @@ def gather_bands(band, nr, rank, world):
     for r in range(world):
         full[r::world] = bufs[r]
     return full
+
+
+class SharedHostRaster:
+    """The host-facing raster of an N-rank frame as ONE pinned buffer every rank can DMA into: a POSIX
+    shared-memory file mapped by all ranks of the node and page-locked in each (cudaHostRegister), so
+    rank r copies its interleaved rows r, r+N, ... device -> host over its own PCIe link
+    (Device.read_rows_pitched) instead of funnelling the whole frame through rank 0's. Rank 0 reads the
+    assembled raster after the barrier. (The NCCL alternative is gather_bands.)"""
+
+    def __init__(self, nr, nc, rank, world, device, tag="raster"):
+        import mmap
+        import os
+        self.nr, self.nc, self.rank, self.world = nr, nc, rank, world
+        self.nbytes = nr * nc * 8
+        name = [f"/dev/shm/newman_b200_{os.getpid()}_{tag}" if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        self.path = name[0]
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.nbytes)
+        if world > 1:
+            dist.barrier()
+        self._f = open(self.path, "r+b")
+        self._mm = mmap.mmap(self._f.fileno(), self.nbytes)
+        self.array = np.frombuffer(self._mm, dtype=np.int32).reshape(nr, nc, 2)
+        self.ptr = self.array.ctypes.data
+        self._registered = False
+        rt = torch.cuda.cudart()
+        err = rt.cudaHostRegister(self.ptr, self.nbytes, 0)
+        self._registered = int(err) == 0
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(self.path)      # the mappings keep it alive; nothing is left behind in /dev/shm
+            except OSError:
+                pass
+
+    def band_ptr(self):
+        """Address of this rank's first row; rows are self.world * nc * 8 bytes apart."""
+        return self.ptr + self.rank * self.nc * 8, self.world * self.nc * 8
+
+    def close(self):
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            self._registered = False
+        self.array = None
+        try:
+            self._mm.close()
+        except BufferError:
+            pass
+        self._f.close()
