@@ -185,6 +185,29 @@ NM_API int nm_resolve(nm_ctx* ctx, const uint8_t* pal_rgb, int n_pal, int N, int
 NM_API int nm_resolve_grid(nm_ctx* ctx, const nm_escape* grid, int nr, int nc, const uint8_t* pal_rgb,
                     int n_pal, int N, int sc, int smooth, uint8_t* rgb_out);
 
+/* ---- K5: zoom-video in-betweening -------------------------------------------------------------
+ * Replaces the frame loop of VideoZoom::nextFrame (video.cpp:14-34): from the previous and the new key
+ * frame (H x W x 3 bytes each, interleaved; the new one rendered 1.5x deeper) all `rate` in-between
+ * canvases (nr x nc x 3 each, consecutive in frames_out) in one launch: previous enlarged by 1.5^(i/rate),
+ * new one shrunk by (2/3) 1.5^(i/rate) blended over it with weight i/rate, both centred. h/d pointers.
+ * Resampling conventions (libbyteimage is not vendored): see csrc/k5_video.cuh. ms_k4 of nm_frame_stats
+ * holds the kernel time. Encoding the frames (byteimage::VideoWriter) stays with the caller. */
+NM_API int nm_video_inbetween(nm_ctx* ctx, const uint8_t* prev_rgb, const uint8_t* next_rgb, int H, int W, int nr,
+                              int nc, int rate, uint8_t* frames_out);
+
+/* ---- K6: palette table on the device ----------------------------------------------------------
+ * MultiWaveGenerator::cache (multiwave.cpp:75-116) as a kernel: the N-entry RGB table is generated in
+ * HBM from the generator's parameters (hue cycles flattened: cycle k has hue_counts[k] nodes, in degrees,
+ * consecutive in hue_values) and kept in the ctx; rgb_out (h/d pointer, may be NULL) receives a copy.
+ * nm_resolve_device_palette then recolours the resident raster with it: a palette edit costs two small
+ * launches and no table upload (README.md:84-86 "re-index without re-rendering"). Within 1 LSB per channel
+ * of the host builder nmp_cache (device libm). */
+NM_API int nm_palette_cache(nm_ctx* ctx, int n_cycles, const int* hue_counts, const float* hue_values,
+                            const int* hue_periods, int hue_period, int n_sat, const float* sat_values,
+                            int sat_period, int n_lum, const float* lum_amp, const int* lum_period, int N,
+                            uint8_t* rgb_out);
+NM_API int nm_resolve_device_palette(nm_ctx* ctx, int N, int sc, int smooth, uint8_t* rgb_out);
+
 /* ---- measurement helpers --------------------------------------------------------------------
  * FP64-pipe peak probe: runs `iters` dependent-chain DFMA (kind 0), DADD (1), DMUL (2) per thread
  * (kind 3: the K3 iteration body from registers, counted as 10 instructions per pixel-iteration)
@@ -275,6 +298,8 @@ NM_API int nmp_set_hue_period(nmp_palette* p, int period);
 NM_API int nmp_set_sat_cycle(nmp_palette* p, const float* sats, int n, int period);
 NM_API int nmp_add_lum_wave(nmp_palette* p, float amplitude, int period);
 NM_API int nmp_cache(const nmp_palette* p, int N, uint8_t* rgb_out); /* cache(N): 3*N bytes r,g,b */
+/* the same table generated on the GPU of `ctx` (K6, nm_palette_cache) and kept there for nm_resolve_device_palette */
+NM_API int nmp_cache_device(const nmp_palette* p, nm_ctx* ctx, int N, uint8_t* rgb_out);
 
 #ifdef __cplusplus
 }

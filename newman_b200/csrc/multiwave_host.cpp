@@ -194,6 +194,23 @@ int nmp_add_lum_wave(nmp_palette* p, float amplitude, int period) {
   p->mw.lum_waves.push_back(w);
   return NM_OK;
 }
+int nmp_cache_device(const nmp_palette* p, nm_ctx* ctx, int N, uint8_t* rgb_out) {
+  if (!p || !ctx || N < 0) return NM_EINVAL;
+  const MultiWaveGenerator& mw = p->mw;
+  if (mw.hue_cycles.empty() || mw.sat_cycle.values.empty()) return NM_ESTATE;
+  std::vector<int> counts, periods, lper;
+  std::vector<float> hues, lamp;
+  for (const MultiWaveGenerator::FloatCycle& hc : mw.hue_cycles) {
+    counts.push_back((int)hc.values.size());
+    periods.push_back(hc.period);
+    hues.insert(hues.end(), hc.values.begin(), hc.values.end());
+  }
+  for (const MultiWaveGenerator::FloatWave& w : mw.lum_waves) { lamp.push_back(w.amplitude); lper.push_back(w.period); }
+  return nm_palette_cache(ctx, (int)counts.size(), counts.data(), hues.data(), periods.data(), mw.hue_period,
+                          (int)mw.sat_cycle.values.size(), mw.sat_cycle.values.data(), mw.sat_cycle.period, (int)lamp.size(),
+                          lamp.empty() ? nullptr : lamp.data(), lper.empty() ? nullptr : lper.data(), N, rgb_out);
+}
+
 int nmp_cache(const nmp_palette* p, int N, uint8_t* rgb_out) {
   if (!p || N < 0 || (N > 0 && !rgb_out)) return NM_EINVAL;
   if (p->mw.hue_cycles.empty() || p->mw.sat_cycle.values.empty()) return NM_ESTATE;

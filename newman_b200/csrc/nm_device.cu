@@ -25,6 +25,8 @@
 #include "k3_perturb.cuh"
 #include "k3_fast.cuh"
 #include "k4_resolve.cuh"
+#include "k5_video.cuh"
+#include "k6_palette.cuh"
 
 using namespace nm;
 
@@ -62,7 +64,8 @@ struct nm_ctx {
   bool have_list = false;
   bool launched = false, finished = false;
 
-  DevBuf out, cre, cim, ctr, ambig, fix, fixapply;
+  DevBuf out, cre, cim, ctr, ambig, fix, fixapply, palpar, paldev, vprev, vnext, vout;
+  int paldev_n = 0;  // entries of the device-generated palette in paldev (0: none)
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
   DevBuf Z, ghi, gb, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
@@ -547,7 +550,8 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e};
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
+                    &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
@@ -838,6 +842,103 @@ int nm_resolve_grid(nm_ctx* ctx, const nm_escape* grid, int nr, int nc, const ui
   int rc = run_resolve(ctx, ctx->gridtmp.as<nm_escape>(), nr, nc, pal_rgb, n_pal, N, sc, smooth, rgb_out);
   ctx->kind = saved;
   return rc;
+}
+
+int nm_video_inbetween(nm_ctx* ctx, const uint8_t* prev_rgb, const uint8_t* next_rgb, int H, int W, int nr, int nc, int rate,
+                       uint8_t* frames_out) {
+  if (!ctx) return NM_EINVAL;
+  if (!prev_rgb || !next_rgb || !frames_out || H < 1 || W < 1 || nr < 1 || nc < 1 || rate < 1)
+    return fail(ctx, NM_EINVAL, "nm_video_inbetween: bad arguments");
+  if (int rc = set_device(ctx)) return rc;
+  const size_t kb = (size_t)H * W * 3, ob = (size_t)rate * nr * nc * 3;
+  NM_CUDA(ctx, ctx->vprev.ensure(kb));
+  NM_CUDA(ctx, ctx->vnext.ensure(kb));
+  NM_CUDA(ctx, ctx->vout.ensure(ob));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->vprev.p, prev_rgb, kb, cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->vnext.p, next_rgb, kb, cudaMemcpyDefault, ctx->stream));
+  K5Params p;
+  p.prev = ctx->vprev.as<uint8_t>(); p.next = ctx->vnext.as<uint8_t>();
+  p.H = H; p.W = W; p.nr = nr; p.nc = nc; p.rate = rate; p.out = ctx->vout.as<uint8_t>();
+  p.v = (float)pow(1.5, 1.0 / rate);
+  long long total = (long long)rate * nr * nc;
+  long long blocks = (total + 255) / 256;
+  const long long maxb = (long long)ctx->sm_count * 16;
+  if (blocks > maxb) blocks = maxb;
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  k5_inbetween<<<(unsigned)blocks, 256, 0, ctx->stream>>>(p);
+  NM_CUDA(ctx, cudaGetLastError());
+  cudaEvent_t evend;
+  NM_CUDA(ctx, cudaEventCreate(&evend));
+  NM_CUDA(ctx, cudaEventRecord(evend, ctx->stream));
+  ctx->stats.kernel_launches++;
+  NM_CUDA(ctx, cudaMemcpyAsync(frames_out, ctx->vout.p, ob, cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[3], evend);
+  ctx->stats.ms_k4 = ms;
+  cudaEventDestroy(evend);
+  return NM_OK;
+}
+
+int nm_palette_cache(nm_ctx* ctx, int n_cycles, const int* hue_counts, const float* hue_values, const int* hue_periods,
+                     int hue_period, int n_sat, const float* sat_values, int sat_period, int n_lum, const float* lum_amp,
+                     const int* lum_period, int N, uint8_t* rgb_out) {
+  if (!ctx) return NM_EINVAL;
+  if (n_cycles < 1 || !hue_counts || !hue_values || !hue_periods || hue_period < 1 || n_sat < 1 || !sat_values ||
+      sat_period < 1 || n_lum < 0 || (n_lum && (!lum_amp || !lum_period)) || N < 0)
+    return fail(ctx, NM_EINVAL, "nm_palette_cache: bad arguments");
+  if (int rc = set_device(ctx)) return rc;
+  int n_hue = 0;
+  std::vector<int> offs((size_t)n_cycles);
+  for (int k = 0; k < n_cycles; k++) {
+    if (hue_counts[k] < 1 || hue_periods[k] < 1) return fail(ctx, NM_EINVAL, "nm_palette_cache: empty hue cycle");
+    offs[k] = n_hue;
+    n_hue += hue_counts[k];
+  }
+  for (int k = 0; k < n_lum; k++) if (lum_period[k] < 1) return fail(ctx, NM_EINVAL, "nm_palette_cache: bad wave period");
+  // one packed parameter block: [counts | offsets | periods | lum_period] ints, then [hue | sat | lum_amp] floats
+  const size_t n_int = (size_t)3 * n_cycles + n_lum, n_flt = (size_t)n_hue + n_sat + n_lum;
+  std::vector<int32_t> pack(n_int + n_flt);
+  memcpy(&pack[0], hue_counts, sizeof(int) * n_cycles);
+  memcpy(&pack[n_cycles], offs.data(), sizeof(int) * n_cycles);
+  memcpy(&pack[2 * n_cycles], hue_periods, sizeof(int) * n_cycles);
+  if (n_lum) memcpy(&pack[3 * n_cycles], lum_period, sizeof(int) * n_lum);
+  float* pf = reinterpret_cast<float*>(&pack[n_int]);
+  memcpy(pf, hue_values, sizeof(float) * n_hue);
+  memcpy(pf + n_hue, sat_values, sizeof(float) * n_sat);
+  if (n_lum) memcpy(pf + n_hue + n_sat, lum_amp, sizeof(float) * n_lum);
+  NM_CUDA(ctx, ctx->palpar.ensure(pack.size() * 4));
+  NM_CUDA(ctx, ctx->paldev.ensure((size_t)3 * (N > 0 ? N : 1)));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->palpar.p, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `pack` is pageable and dies with this scope
+  K6Params p;
+  const int* di = ctx->palpar.as<int>();
+  const float* df = reinterpret_cast<const float*>(di + n_int);
+  p.n_cycles = n_cycles; p.hue_counts = di; p.hue_offsets = di + n_cycles; p.hue_periods = di + 2 * n_cycles;
+  p.lum_period = di + 3 * n_cycles; p.hue_values = df; p.sat_values = df + n_hue; p.lum_amp = df + n_hue + n_sat;
+  p.hue_period = hue_period; p.n_sat = n_sat; p.sat_period = sat_period; p.n_lum = n_lum; p.N = N;
+  p.rgb = ctx->paldev.as<uint8_t>();
+  if (N > 0) {
+    int blocks = (N + 255) / 256;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k6_palette<<<blocks, 256, 0, ctx->stream>>>(p);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+  }
+  ctx->paldev_n = N;
+  if (rgb_out && N > 0) {
+    NM_CUDA(ctx, cudaMemcpyAsync(rgb_out, ctx->paldev.p, (size_t)3 * N, cudaMemcpyDefault, ctx->stream));
+    NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return NM_OK;
+}
+
+int nm_resolve_device_palette(nm_ctx* ctx, int N, int sc, int smooth, uint8_t* rgb_out) {
+  if (!ctx) return NM_EINVAL;
+  if (ctx->paldev_n < 1) return fail(ctx, NM_ESTATE, "nm_resolve_device_palette: no palette generated (nm_palette_cache)");
+  if (int rc = finish_frame(ctx)) return rc;
+  return run_resolve(ctx, ctx->out.as<nm_escape>(), ctx->nr, ctx->nc, ctx->paldev.as<uint8_t>(), ctx->paldev_n, N, sc, smooth,
+                     rgb_out);
 }
 
 int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms_out) {

@@ -163,6 +163,22 @@ class Device:
         self._ck(self.lib.nm_resolve(self.h, L.ptr(pal_rgb), n_pal, N, sc, int(bool(smooth)), L.ptr(out)))
         return out
 
+    def video_inbetween(self, prev_rgb, next_rgb, nr, nc, rate=45, out=None):
+        """VideoZoom::nextFrame (video.cpp:14-34): the `rate` canvases between two key frames -> (rate, nr, nc, 3) uint8."""
+        H, W = prev_rgb.shape[0], prev_rgb.shape[1]
+        assert tuple(next_rgb.shape) == tuple(prev_rgb.shape)
+        if out is None:
+            out = np.zeros((rate, nr, nc, 3), dtype=np.uint8)
+        self._ck(self.lib.nm_video_inbetween(self.h, L.ptr(prev_rgb), L.ptr(next_rgb), H, W, nr, nc, rate, L.ptr(out)))
+        return out
+
+    def resolve_device_palette(self, N, sc=1, smooth=True, out=None):
+        """Colour resolve of the resident raster with the palette MultiWaveGenerator.cache_device() left on this GPU."""
+        if out is None:
+            out = np.zeros((self.nr // sc, self.nc // sc, 3), dtype=np.uint8)
+        self._ck(self.lib.nm_resolve_device_palette(self.h, N, sc, int(bool(smooth)), L.ptr(out)))
+        return out
+
     def resolve_grid(self, grid, pal_rgb, N, sc=1, smooth=True, out=None):
         nr, nc = grid.shape
         n_pal = len(pal_rgb) // 3 if pal_rgb.ndim == 1 else pal_rgb.shape[0]

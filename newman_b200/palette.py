@@ -16,6 +16,7 @@ PALETTE_API = {
     "nmp_set_sat_cycle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "nmp_add_lum_wave": (C.c_int, [C.c_void_p, C.c_float, C.c_int]),
     "nmp_cache": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nmp_cache_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 }
 _bound = False
 
@@ -70,6 +71,15 @@ class MultiWaveGenerator:
 
     def add_lum_wave(self, amplitude, period):
         self._ck(self.lib.nmp_add_lum_wave(self.h, float(amplitude), int(period)), "add_lum_wave")
+
+    def cache_device(self, dev, N):
+        """cache(N) generated on the GPU of `dev` (K6) and kept there for dev.resolve_device_palette();
+        returns a host copy (N, 3) uint8."""
+        out = np.zeros((N, 3), dtype=np.uint8)
+        rc = self.lib.nmp_cache_device(self.h, dev.h, int(N), L.ptr(out))
+        if rc != L.NM_OK:
+            raise L.NmError(rc, dev.lib.nm_last_error(dev.h).decode() or "palette is empty")
+        return out
 
     def cache(self, N):
         """cache(N) -> (N, 3) uint8 RGB table (multiwave.cpp:75-116)."""

@@ -521,3 +521,46 @@ void oraclep_palette_cache(int n_cycles, const int* hue_counts, const float* hue
     interp3(col[0], col[1], ty, rgb + 3 * i);
   }
 }
+
+/* ---- zoom-video in-betweening (video.cpp:14-34; conventions of newman_b200/csrc/k5_video.cuh) ----- */
+static void vid_sample(const uint8_t* src, int H, int W, int sh, int sw, int r, int c, float* rgb) {
+  float fy = (r + 0.5f) * ((float)H / (float)sh) - 0.5f;
+  float fx = (c + 0.5f) * ((float)W / (float)sw) - 0.5f;
+  fy = fy < 0.0f ? 0.0f : (fy > (float)(H - 1) ? (float)(H - 1) : fy);
+  fx = fx < 0.0f ? 0.0f : (fx > (float)(W - 1) ? (float)(W - 1) : fx);
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + 1 < H ? y0 + 1 : H - 1, x1 = x0 + 1 < W ? x0 + 1 : W - 1;
+  float wy = fy - (float)y0, wx = fx - (float)x0;
+  const uint8_t* p00 = src + 3 * ((size_t)y0 * W + x0);
+  const uint8_t* p01 = src + 3 * ((size_t)y0 * W + x1);
+  const uint8_t* p10 = src + 3 * ((size_t)y1 * W + x0);
+  const uint8_t* p11 = src + 3 * ((size_t)y1 * W + x1);
+  for (int k = 0; k < 3; k++) {
+    float top = (1.0f - wx) * p00[k] + wx * p01[k];
+    float bot = (1.0f - wx) * p10[k] + wx * p11[k];
+    rgb[k] = truncf((1.0f - wy) * top + wy * bot);
+  }
+}
+
+void oraclep_video_inbetween(const uint8_t* prev, const uint8_t* next, int H, int W, int nr, int nc, int rate,
+                             float v, uint8_t* out) {
+  float sm = 2.0f / 3.0f, lg = 1.0f; /* video.cpp:17; v = pow(1.5, 1.0 / rate) is passed in (see header) */
+  for (int i = 0; i < rate; i++) {
+    float t = (float)i / (float)rate;
+    int lh = (int)(H * lg), lw = (int)(W * lg), sh = (int)(H * sm), sw = (int)(W * sm);
+    for (int r = 0; r < nr; r++)
+      for (int c = 0; c < nc; c++) {
+        float o[3] = {0.0f, 0.0f, 0.0f}, s[3];
+        int lr = r - (nr - lh) / 2, lc = c - (nc - lw) / 2;
+        if (lr >= 0 && lr < lh && lc >= 0 && lc < lw) vid_sample(prev, H, W, lh, lw, lr, lc, o);
+        int sr = r - (nr - sh) / 2, sc = c - (nc - sw) / 2;
+        if (sr >= 0 && sr < sh && sc >= 0 && sc < sw) {
+          vid_sample(next, H, W, sh, sw, sr, sc, s);
+          for (int k = 0; k < 3; k++) o[k] = truncf((1.0f - t) * o[k] + t * s[k]);
+        }
+        uint8_t* q = out + 3 * (((size_t)i * nr + r) * nc + c);
+        q[0] = (uint8_t)o[0]; q[1] = (uint8_t)o[1]; q[2] = (uint8_t)o[2];
+      }
+    sm *= v; lg *= v;
+  }
+}

@@ -63,6 +63,11 @@ void oraclep_palette_cache(int n_cycles, const int* hue_counts, const float* hue
                            int hue_period, int n_sat, const float* sat_values, int sat_period, int n_lum,
                            const float* lum_amp, const int* lum_period, int N, uint8_t* rgb);
 
+/* video.cpp:14-34 with this repo's resampling conventions (k5_video.cuh). v = (float)pow(1.5, 1.0 / rate)
+ * (video.cpp:17) is passed in so that the caller's libm decides its last bit, as in the product (host side). */
+void oraclep_video_inbetween(const uint8_t* prev, const uint8_t* next, int H, int W, int nr, int nc, int rate,
+                             float v, uint8_t* out);
+
 float oraclep_smoothing(double r2);
 double oraclep_trunc_add3(double hi, double lo, double d);
 #endif

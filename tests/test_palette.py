@@ -5,6 +5,7 @@ import ctypes as C
 import os
 
 import numpy as np
+import pytest
 
 import newman_b200
 import oracles
@@ -94,3 +95,40 @@ def test_hue_extremes():
         assert False, "empty palette must be refused"
     except newman_b200.NmError:
         pass
+
+
+@pytest.mark.gpu
+def test_device_palette_k6_vs_host_builder(dev):
+    """K6 (MultiWaveGenerator::cache as a kernel, SURVEY 8f-2) against the host builder: <= 1 LSB per
+    channel (north-star tolerance; device libm), nearly always equal; and the recolour of a resident
+    raster from the device table equals the resolve with that table passed from the host."""
+    import newman_b200
+    mw = newman_b200.MultiWaveGenerator(os.path.join(HERE, "golden", "default.pal"))
+    for N in (1, 256, 65536):
+        host = mw.cache(N)
+        gpu = mw.cache_device(dev, N)
+        diff = np.abs(host.astype(np.int16) - gpu.astype(np.int16))
+        assert diff.max() <= 1, (N, int(diff.max()))
+        print("N", N, "entries differing by 1 LSB:", int((diff.max(axis=1) > 0).sum()))
+        assert (diff.max(axis=1) > 0).mean() < 0.01
+    # a second generator with several hue cycles / waves built through the API
+    g = newman_b200.MultiWaveGenerator()
+    g.add_hue_cycle([0.0, 120.0, 240.0], 97)
+    g.add_hue_cycle([30.0, 300.0], 41)
+    g.add_hue_cycle([200.0], 13)
+    g.set_hue_period(1000)
+    g.set_sat_cycle([1.0, 0.2, 0.7], 333)
+    g.add_lum_wave(0.9, 77)
+    g.add_lum_wave(0.4, 11)
+    g.add_lum_wave(1.3, 1000)
+    host, gpu = g.cache(5000), g.cache_device(dev, 5000)
+    assert np.abs(host.astype(np.int16) - gpu.astype(np.int16)).max() <= 1
+    # recolour without re-rendering
+    m = newman_b200.Mandelbrot(48, 64, N=256)
+    grid = m.render()
+    cre, cim = m.host_coords()
+    dev.render_hw(cre, cim, 256)
+    table = mw.cache_device(dev, 256)
+    a = dev.resolve_device_palette(256, sc=2, smooth=True)
+    b = dev.resolve(table, 256, sc=2, smooth=True)
+    assert np.array_equal(a, b)
