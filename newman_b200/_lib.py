@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnewman_b200.so")
+# NEWMAN_B200_LIB: an alternative build of the same library (kernel-variant experiments); default in-tree
+LIB_PATH = os.environ.get("NEWMAN_B200_LIB") or os.path.join(_HERE, "libnewman_b200.so")
 
 ESCAPE_DTYPE = np.dtype([("iterations", "<i4"), ("smoothing", "<f4")])  # grid.h:8-16
 

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -366,6 +367,16 @@ int launch_deep(nm_ctx* ctx) {
   NM_CUDA(ctx, cudaStreamSynchronize(st));
   unsigned long long min_j = ctx->h_ctr[2];
 
+  static const bool debug_levels = getenv("NM_DEBUG_LEVELS") != nullptr;
+  cudaEvent_t dbg_ev = nullptr;
+  unsigned long long dbg_prev = 0;
+  if (debug_levels) {
+    cudaEventCreate(&dbg_ev);
+    cudaMemcpyAsync(&dbg_prev, &ctr[CTR_EXECUTED], 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaEventRecord(dbg_ev, st);
+  }
+
   for (int sweep = 0;; ++sweep) {
     const int par = sweep & 1;
     int kstart = 0;
@@ -415,6 +426,19 @@ int launch_deep(nm_ctx* ctx) {
                                            : launch_level<NM_MODE_REQUEUE, false>(ctx, p, blocks, smem);
       if (e != cudaSuccess) return fail(ctx, NM_ECUDA, "k3 level launch: %s", cudaGetErrorString(e));
       ctx->stats.kernel_launches++;
+      if (debug_levels) {  // NM_DEBUG_LEVELS=1: per-level device time and executed iterations (serialises the frame)
+        cudaEventRecord(ctx->ev[3], st);
+        unsigned long long ex = 0, nx = 0;
+        cudaMemcpyAsync(&ex, &ctr[CTR_EXECUTED], 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&nx, &qcount[k + 1], 8, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, dbg_ev, ctx->ev[3]);
+        fprintf(stderr, "nm level sweep %d k %3d: %8.3f ms  executed +%llu  (%.1f Giter/s)  -> next %llu\n", sweep, k, ms,
+                ex - dbg_prev, ms > 0 ? (double)(ex - dbg_prev) / ms * 1e-6 : 0.0, nx);
+        dbg_prev = ex;
+        cudaEventRecord(dbg_ev, st);
+      }
     }
     if (fast) {  // resolve what the branch-free kernel exported: escapes, glitches, limits, rebases, false alarms
       if (scaled)
@@ -437,6 +461,7 @@ int launch_deep(nm_ctx* ctx) {
     min_j = ctx->h_ctr[2];
     if (ctx->h_ctr[0] == 0 || ctx->h_ctr[1] != 0) break;
   }
+  if (dbg_ev) cudaEventDestroy(dbg_ev);
   NM_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
   return NM_OK;
 }
