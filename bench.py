@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 
 K3_INST_PER_ITER = 10   # 7 DFMA + 2 DADD + 1 DMUL (k3_perturb.cuh)
 K3_FLOPS_PER_ITER = 17
+# DRAM bytes per state and full-level launch of the dominant kernel, from the ncu --set full capture
+# profiles/r01f_k3_fast4_cfg3_metrics.txt (1.065 GB read + 1.018 GB written for 33 177 600 states): the
+# 32-byte state of every sample in and out once = the algorithmic traffic (64 B), nothing re-read.
+K3_DRAM_B_PER_STATE = (1.065023e9 + 1.018445e9) / 33177600
 K2_INST_PER_EVAL = 19   # 12 DMUL + 6 DADD + ... (k2_series.cuh phase-1 body incl. the compare)
 METRIC = "executed pixel-iterations/sec"
 UNIT = "Giter/s"
@@ -554,7 +558,12 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64_pipe", "kernel": k_name, "achieved": achieved, "peak": peak_dadd / 1e9,
-                         "unit": "Ginst/s", "frac": achieved / (peak_dadd / 1e9) if peak_dadd else None, "traffic": None,
+                         "unit": "Ginst/s", "frac": achieved / (peak_dadd / 1e9) if peak_dadd else None,
+                         "bound_note": "neither hbm nor tensor: 10 FP64 instructions per 0.06 B of DRAM traffic, no contraction "
+                                       "(SURVEY.md 8d); achieved = executed iterations x 10 FP64 instructions / K3 device time",
+                         "traffic": None if hw else K3_DRAM_B_PER_STATE * len(rows) * nc,
+                         "traffic_note": None if hw else "bytes per full-level launch of k3_fast for this rank's states, from the "
+                                         "ncu capture profiles/r01f_k3_fast4_cfg3_metrics.txt (62.8 B per state; algorithmic 64 B)",
                          "peak_source": "measured live: nm_fp64_peak DADD issue rate (MEASURED_PEAKS.json has no FP64 entry)",
                          "peak_dfma_ginst": peak_dfma / 1e9,
                          "fp64_tflops": executed / world * K3_FLOPS_PER_ITER / (k3_ms * 1e-3) / 1e12 if (k3_ms > 0 and not hw) else None,

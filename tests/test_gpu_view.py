@@ -185,3 +185,63 @@ def test_probe_search_gpu_assisted_equals_exhaustive(kat):
     assert fast[3] <= max(24, exact[3] // 4)
     h = m.host_tables()
     assert h["probe"] == exact[:2] and h["M"] == min(exact[2], m.N)
+
+
+def _offset_center(center, pitch_exp, rng, span):
+    """centre + a random offset of up to `span` pitches, as exact decimal strings."""
+    from fractions import Fraction
+    out = []
+    for c in center:
+        f = Fraction(c) + Fraction(int(rng.integers(-span, span + 1)), 10 ** pitch_exp)
+        neg, f = f < 0, abs(f)
+        digits = pitch_exp + 6
+        ip = f.numerator // f.denominator
+        frac = f - ip
+        out.append(("-" if neg else "") + f"{ip}." + str((frac.numerator * 10 ** digits) // frac.denominator).rjust(digits, "0"))
+    return tuple(out)
+
+
+@pytest.mark.parametrize("case", range(15))
+def test_random_views_class_equals_oracle_rounds(case):
+    """Seeded random small views on structured locations (the deep zoom path of workloads.py, the
+    Misiurewicz point c = i, the seahorse valley): ragged sizes, depths 1e-17 .. 1e-300, iteration limits
+    that some samples reach, orbits shorter and longer than a chunk, all three floatexp levels. The drop-in
+    class == Oracle-P through the same rounds, bit for bit, including the references used and the executed
+    iterations."""
+    rng = np.random.default_rng(1000 + case)
+    kind = case % 3
+    if kind == 0:      # on the zoom path: long orbits (1e4 .. 2e5), hundreds to thousands of delta updates per sample
+        depth = int(rng.integers(17, 131))
+        nr, nc, N = int(rng.integers(3, 14)), int(rng.integers(3, 20)), 1 << 18
+        base = workloads.CFG4_CENTER
+    elif kind == 1:    # c = i: short orbits (3.3 per decade), any depth
+        depth = int(rng.integers(17, 301))
+        nr, nc, N = int(rng.integers(3, 40)), int(rng.integers(3, 50)), int(rng.choice([300, 1500, 5000]))
+        base = ("0", "1")
+    else:              # seahorse valley, chaotic continuation
+        depth = int(rng.integers(17, 27))
+        nr, nc, N = int(rng.integers(3, 20)), int(rng.integers(3, 24)), 20000
+        base = ("-0.743643887037158704752191506114774", "0.131825904205311970493132056385139")
+    pitch = f"{float(rng.uniform(1, 9)):.6f}e-{depth}"
+    k = dict(nr=nr, nc=nc, N=N, sz=(pitch, pitch), center=_offset_center(base, depth, rng, 40))
+    m = mk(k)
+    got = m.render()
+    info = m.frame_info()
+    assert info["hardware"] != 1
+    fe = {0: 0, 2: 1, 3: 2}[info["hardware"]]
+    ref_m = mk(k)
+    nc_ = ref_m.cols()
+    mkts = lambda d: pipeline.TableSet(d, N, 1e-10, 1e-6, pipeline.floatexp_level(d))
+    primary = mkts(ref_m.host_tables(info["probe_row"], info["probe_col"]))
+    assert primary.fe == fe
+    od = OracleDevice()
+    mode, mask = ref_m.host_cardioid()
+    res = pipeline.render_rounds(od, primary, lambda gp: mkts(ref_m.host_tables(gp // nc_, gp % nc_)), nc_, np.arange(nr),
+                                 cardioid_mode=mode, mask=mask if mode == 2 else None)
+    exp = od.out
+    print(case, "depth", depth, (nr, nc), N, "M", info["orbit_len"], "refs", info["references"], "fe", fe,
+          "it", int(got["iterations"].min()), int(got["iterations"].max()), "executed", info["executed_iters"])
+    assert np.array_equal(got["iterations"], exp["iterations"]), (k, info)
+    assert np.array_equal(bits(got["smoothing"]), bits(exp["smoothing"])), (k, info)
+    assert info["references"] == 1 + len(res["refs"])
+    assert info["executed_iters"] == sum(s["executed_iters"] for s in res["stats"])
