@@ -472,7 +472,8 @@ def run_ours(args):
         lens = [len(pipeline.local_rows(nr, r, world)) for r in range(world)]
         assert len(set(lens)) == 1, "grid rows must divide evenly across ranks"
     if world > 1 and args.gather == "shm":
-        shared = multigpu.SharedHostRaster(nr, nc, rank, world, devt)
+        shared = multigpu.SharedHostRaster.create(dev, nr, nc, rank, world, devt)   # None: /dev/shm too small
+    if shared is not None:
         out_host = torch.from_numpy(shared.array) if rank == 0 else None
     else:
         out_dev = torch.empty((len(rows), nc, 2), dtype=torch.int32, device=devt)

@@ -148,6 +148,12 @@ NM_API int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst);
  * host raster with pitch N * nc * 8 — every GPU over its own PCIe link, no funnel through one GPU. */
 NM_API int nm_read_rows_pitched(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst_pitch_bytes);
 
+/* Page-lock / release a caller-owned host buffer (e.g. a raster in POSIX shared memory that several ranks
+ * write with nm_read_rows_pitched) so that copies to it are DMA transfers. NM_ENOMEM when the OS refuses;
+ * the buffer then still works as pageable memory. */
+NM_API int nm_host_register(nm_ctx* ctx, void* ptr, size_t bytes);
+NM_API int nm_host_unregister(nm_ctx* ctx, void* ptr);
+
 /* Gather the records of the listed samples (ids r*nc+c; h/d pointers) — what the probe search reads. */
 NM_API int nm_read_pixels(nm_ctx* ctx, const int32_t* pix, int64_t n, nm_escape* dst);
 

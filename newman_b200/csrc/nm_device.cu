@@ -812,6 +812,25 @@ int nm_read_rows_pitched(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst
   return NM_OK;
 }
 
+int nm_host_register(nm_ctx* ctx, void* ptr, size_t bytes) {
+  if (!ctx || !ptr || !bytes) return NM_EINVAL;
+  if (int rc = set_device(ctx)) return rc;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // not sticky: clear it so that the caller can fall back to pageable / NCCL paths
+    return fail(ctx, NM_ENOMEM, "cudaHostRegister(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  }
+  return NM_OK;
+}
+
+int nm_host_unregister(nm_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return NM_EINVAL;
+  if (int rc = set_device(ctx)) return rc;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, NM_ECUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+  return NM_OK;
+}
+
 int nm_read_pixels(nm_ctx* ctx, const int32_t* pix, int64_t n, nm_escape* dst) {
   if (!ctx) return NM_EINVAL;
   if (n < 0 || (n && (!pix || !dst))) return fail(ctx, NM_EINVAL, "nm_read_pixels: bad arguments");

@@ -127,6 +127,13 @@ class Device:
         """Rows [r0, r1) to host/device address dst_ptr with a row pitch (interleaved bands of a shared raster)."""
         self._ck(self.lib.nm_read_rows_pitched(self.h, r0, r1, C.c_void_p(dst_ptr), pitch_bytes))
 
+    def host_register(self, ptr, nbytes):
+        """Page-lock a host buffer; False if the OS refuses (the buffer then stays pageable)."""
+        return self.lib.nm_host_register(self.h, C.c_void_p(ptr), nbytes) == L.NM_OK
+
+    def host_unregister(self, ptr):
+        self.lib.nm_host_unregister(self.h, C.c_void_p(ptr))
+
     def read_pixels(self, pix):
         pix = np.ascontiguousarray(pix, dtype=np.int32)
         out = np.zeros(len(pix), dtype=L.ESCAPE_DTYPE)

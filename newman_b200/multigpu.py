@@ -58,40 +58,57 @@ def gather_bands(band, nr, rank, world):
 
 class SharedHostRaster:
     """The host-facing raster of an N-rank frame as ONE pinned buffer every rank can DMA into: a POSIX
-    shared-memory file mapped by all ranks of the node and page-locked in each (cudaHostRegister), so
+    shared-memory file mapped by all ranks of the node and page-locked in each (nm_host_register), so
     rank r copies its interleaved rows r, r+N, ... device -> host over its own PCIe link
     (Device.read_rows_pitched) instead of funnelling the whole frame through rank 0's. Rank 0 reads the
-    assembled raster after the barrier. (The NCCL alternative is gather_bands.)"""
+    assembled raster after the barrier. (The NCCL alternative is gather_bands.)
 
-    def __init__(self, nr, nc, rank, world, device, tag="raster"):
+    create() returns None — on every rank alike — when /dev/shm cannot hold the raster or any rank fails
+    to page-lock it; the caller then uses gather_bands."""
+
+    MAX_BYTES = 4 << 30
+
+    @staticmethod
+    def create(dev, nr, nc, rank, world, device, tag="raster"):
         import mmap
         import os
-        self.nr, self.nc, self.rank, self.world = nr, nc, rank, world
-        self.nbytes = nr * nc * 8
-        name = [f"/dev/shm/newman_b200_{os.getpid()}_{tag}" if rank == 0 else None]
-        if world > 1:
-            dist.broadcast_object_list(name, src=0)
-        self.path = name[0]
+        nbytes = nr * nc * 8
+        ok = [False, None]
         if rank == 0:
-            with open(self.path, "wb") as f:
-                f.truncate(self.nbytes)
+            try:
+                st = os.statvfs("/dev/shm")
+                # (page-locking one 8.5 GB mapping in each of 8 processes was refused by the OS on the B200 box)
+                if st.f_bavail * st.f_frsize > nbytes * 1.25 and nbytes <= SharedHostRaster.MAX_BYTES:
+                    path = f"/dev/shm/newman_b200_{os.getpid()}_{tag}"
+                    with open(path, "wb") as f:
+                        f.truncate(nbytes)
+                    ok = [True, path]
+            except OSError:
+                ok = [False, None]
         if world > 1:
-            dist.barrier()
+            dist.broadcast_object_list(ok, src=0)
+        if not ok[0]:
+            return None
+        self = SharedHostRaster.__new__(SharedHostRaster)
+        self.nr, self.nc, self.rank, self.world, self.dev, self.path = nr, nc, rank, world, dev, ok[1]
+        self.nbytes = nbytes
         self._f = open(self.path, "r+b")
-        self._mm = mmap.mmap(self._f.fileno(), self.nbytes)
+        self._mm = mmap.mmap(self._f.fileno(), nbytes)
         self.array = np.frombuffer(self._mm, dtype=np.int32).reshape(nr, nc, 2)
         self.ptr = self.array.ctypes.data
-        self._registered = False
-        rt = torch.cuda.cudart()
-        err = rt.cudaHostRegister(self.ptr, self.nbytes, 0)
-        self._registered = int(err) == 0
+        self._registered = dev.host_register(self.ptr, nbytes)
+        good = torch.tensor([1 if self._registered else 0], dtype=torch.int32, device=device)
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(good, op=dist.ReduceOp.MIN)
         if rank == 0:
             try:
                 os.unlink(self.path)      # the mappings keep it alive; nothing is left behind in /dev/shm
             except OSError:
                 pass
+        if int(good.item()) == 0:
+            self.close()
+            return None
+        return self
 
     def band_ptr(self):
         """Address of this rank's first row; rows are self.world * nc * 8 bytes apart."""
@@ -99,7 +116,7 @@ class SharedHostRaster:
 
     def close(self):
         if self._registered:
-            torch.cuda.cudart().cudaHostUnregister(self.ptr)
+            self.dev.host_unregister(self.ptr)
             self._registered = False
         self.array = None
         try:
