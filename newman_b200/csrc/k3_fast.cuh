@@ -89,6 +89,9 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
   const int nload2 = (nload + 1) & ~1;  // bulk copies move multiples of 16 bytes
   double2* sZ = (double2*)smem_raw;
   const int32_t* sG = (const int32_t*)(smem_raw + (size_t)(CH + 4) * sizeof(double2));  // gb[] doubles; high word at [2i+1]
+  // 2*Z[j], formed once per CTA: w = 2Z + delta is then a DADD of two table values instead of fma(2, Z, delta)
+  // (bit-identical: 2Z is exact) — DADD issues ~9 % faster than DFMA on this part (profiles/r01_fp64_peak.json)
+  double2* sZ2 = (double2*)(smem_raw + (size_t)(CH + 4) * (sizeof(double2) + sizeof(double)));
   __shared__ __align__(8) uint64_t bar;
 
   const unsigned long long n_cur = p.cur_count ? *p.cur_count : 0ULL;
@@ -134,6 +137,8 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
   }
 
   mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < nload; i += blockDim.x) { const double2 z = sZ[i]; sZ2[i] = make_double2(2.0 * z.x, 2.0 * z.y); }
+  __syncthreads();
 
   for (;;) {
     // ---- re-deal: one group of P same-index pixels per lane (every lane is idle here) ------------
@@ -227,7 +232,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
           double dr0[P], di0[P];
 #pragma unroll
           for (int s = 0; s < P; ++s) { dr0[s] = dr[s]; di0[s] = di[s]; }
-          double2 x = sZ[j - jbase];
+          double2 x2 = sZ2[j - jbase];
           bool bad[P];
           int hi_last[P];
 #pragma unroll
@@ -236,13 +241,13 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
           for (int t = 0; t < 4; ++t) {
             const int jl = j + t + 1 - jbase;
             const double2 y = sZ[jl];
+            const double2 y2 = sZ2[jl];
             const int g = sG[2 * jl + 1];
-            const double x2r = 2.0 * x.x, x2i = 2.0 * x.y;  // SCALED only (dead code otherwise)
 #pragma unroll
             for (int s = 0; s < P; ++s) {
               double wr, wi;
-              if (SCALED) { wr = __fma_rn(S[s], dr[s], x2r); wi = __fma_rn(S[s], di[s], x2i); }
-              else { wr = __fma_rn(2.0, x.x, dr[s]); wi = __fma_rn(2.0, x.y, di[s]); }
+              if (SCALED) { wr = __fma_rn(S[s], dr[s], x2.x); wi = __fma_rn(S[s], di[s], x2.y); }
+              else { wr = x2.x + dr[s]; wi = x2.y + di[s]; }   // == fma(2, Z, delta): 2Z is exact
               double ndr = __fma_rn(-di[s], wi, __fma_rn(dr[s], wr, er[s]));
               double ndi = __fma_rn(di[s], wr, __fma_rn(dr[s], wi, ei[s]));
               dr[s] = ndr; di[s] = ndi;
@@ -254,7 +259,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
               bad[s] = bad[s] || (hi <= g);
               hi_last[s] = hi;
             }
-            x = y;
+            x2 = y2;
           }
           bool any_bad = false;
 #pragma unroll

@@ -353,7 +353,7 @@ int launch_deep(nm_ctx* ctx) {
   p.rq_pix = ctx->rq_pix.as<int32_t>(); p.rq_iter = ctx->rq_iter.as<int32_t>();
   p.log_bailout = ctx->log_bailout;
 
-  const size_t smem = (size_t)(CH + 4) * (sizeof(double2) + sizeof(double));
+  const size_t smem = (size_t)(CH + 4) * (sizeof(double2) + sizeof(double) + (fast ? sizeof(double2) : 0));
   int occ = (scaled ? ctx->occ_k3s : ctx->occ_k3)[ctx->mode == NM_MODE_REBASE ? 1 : 0];
   if (G == 2) occ = (scaled ? ctx->occ_k3fs : ctx->occ_k3f)[0];
   if (G == 4) occ = (scaled ? ctx->occ_k3fs : ctx->occ_k3f)[1];
@@ -555,6 +555,12 @@ int nm_create(int device, nm_ctx** out) {
   NM_K3_SETUP((k3_level<NM_MODE_REBASE, false>), K3_THREADS, ctx->occ_k3[1]);
   NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, true>), K3_THREADS, ctx->occ_k3s[0]);
   NM_K3_SETUP((k3_level<NM_MODE_REBASE, true>), K3_THREADS, ctx->occ_k3s[1]);
+#undef NM_K3_SETUP
+  const size_t smem_f = smem + (size_t)(ctx->CH + 4) * sizeof(double2);   // + the 2Z table of k3_fast
+#define NM_K3_SETUP(fn, threads, occ_out)                                                                       \
+  NM_CREATE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));           \
+  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(occ_out), fn, threads, smem_f));                \
+  if ((occ_out) < 1) (occ_out) = 1;
   NM_K3_SETUP((k3_fast<2, false>), K3F_THREADS, ctx->occ_k3f[0]);
   NM_K3_SETUP((k3_fast<4, false>), K3F_THREADS, ctx->occ_k3f[1]);
   NM_K3_SETUP((k3_fast<2, true>), K3F_THREADS, ctx->occ_k3fs[0]);
