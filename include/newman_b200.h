@@ -216,10 +216,19 @@ NM_API int nm_resolve_device_palette(nm_ctx* ctx, int N, int sc, int smooth, uin
 
 /* ---- measurement helpers --------------------------------------------------------------------
  * FP64-pipe peak probe: runs `iters` dependent-chain DFMA (kind 0), DADD (1), DMUL (2) per thread
- * (kind 3: the K3 iteration body from registers, counted as 10 instructions per pixel-iteration)
+ * (kind 3: the former K3 iteration body from registers, counted as 10 instructions per pixel-iteration;
+ * kinds 4-7: 8 DFMA chains interleaved with 0/8/16/24 integer-pipe operations, 64 warps per SM; kinds 8-11:
+ * the same at 16 warps per SM — only the FP64 instructions are counted)
  * over a full-chip grid and returns instructions/s. Used by bench.py for the roofline denominator
  * (MEASURED_PEAKS.json carries no FP64 entry). */
 NM_API int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms);
+/* Host-side evaluation of the K3 candidate filter (newman_b200/csrc/k3_filter.cuh) — no GPU involved: the
+ * table entry k3_fast would use at an orbit index with Z = (zr, zi) and glitch bound gb
+ * (entry[0..3] = lo_r, w_r, lo_i, w_i; entry[4] = escape high word), and the two tests as the kernel makes
+ * them (scaled != 0: the state is a scaled one). The filters replace the per-iteration |z|^2 tests of the
+ * perturbation loop and must have no false negatives; tests/test_k3_filter.py attacks that claim. */
+NM_API void nm_k3_filter_entry(double zr, double zi, double gb, uint32_t entry[5]);
+NM_API int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int scaled, int* glitch, int* escape);
 NM_API int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes, char* name, int cap);
 
 /* ==== view level: the drop-in class through C ===================================================

@@ -179,6 +179,32 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters,
   if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 
+// Issue-port probe: 8 independent DFMA chains interleaved with NI integer-pipe operations (IADD / LOP on 8
+// independent accumulators) per loop iteration. Reports the DFMA rate: if it stays at the pure-DFMA rate the
+// integer work rides along for free, if it drops the warp instructions share dispatch cycles (the model
+// DESIGN.md uses for k3_fast: a warp-wide FP64 instruction holds the dispatch port for 2 cycles).
+template <int NI>
+__global__ void __launch_bounds__(256) fp64_int_mix_kernel(double* sink, int iters, double b, double c, int m0, int m1) {
+  double a[8];
+  int k[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { a[q] = threadIdx.x * 1e-9 + q; k[q] = threadIdx.x + q; }
+#pragma unroll 2
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      a[q] = __fma_rn(a[q], b, c);
+      if (NI >= 8) k[q] += m0;
+      if (NI >= 16) k[q] ^= m1;
+      if (NI >= 24) k[q] = max(k[q], m0 + q);
+    }
+  }
+  double s = 0.0; int t = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { s += a[q]; t ^= k[q]; }
+  if (s == 123.456 || t == 0x12345678) sink[0] = s + t;
+}
+
 // The K3 iteration body itself (4 pixels per thread, all operands in distinct registers, no memory):
 // what the FP64 pipe sustains for this exact instruction mix (7 DFMA + 2 DADD + 1 DMUL per pixel-
 // iteration with three different 64-bit register operands per DFMA).

@@ -7,18 +7,21 @@
 // k3_fast<P>: every lane carries P pixels that sit at the SAME orbit index j, so one Z[j+1] /
 // glitch-bound load feeds P delta updates (shared-memory wavefronts per pixel-iteration drop ~4P x)
 // and the P independent dependency chains give the FP64 pipe ILP. All states handled here have
-// j == 0 (mod 4) and advance in branch-free blocks of 4 iterations: per iteration and pixel 10 FP64
-// instructions + one integer compare that ORs "high word of |z|^2 <= high word of the glitch bound"
-// into a per-pixel flag; the escape test is made once per block on the last |z|^2 (once |z| > 1024
-// it grows monotonically and cannot overflow within 3 more steps).
+// j == 0 (mod 4) and advance in branch-free blocks of 4 iterations. The kernel runs the delta recurrence
+// ALONE — per iteration and pixel 6 FP64 instructions (2 DADD + 4 DFMA) — and never forms z = Z + delta:
+// whether the exact glitch / escape comparisons could fire is decided on the integer pipe from the high
+// words of delta against a per-index table (k3_filter.cuh: conservative, no false negatives; the glitch
+// filter every iteration, the escape filter once per block on the last delta — once |z| > 1024 it grows
+// monotonically and cannot overflow within 3 more steps). The earlier form computed z and |z|^2 every
+// iteration (10 FP64 instructions) on a kernel that ncu showed bound by the FP64 pipe.
 //
-// Nothing is decided inside this kernel. A pixel whose block was flagged is rolled back to the
-// block's start state and EXPORTED (state, index) while its lane-mates simply keep their end-of-
-// block state; so is a pixel that cannot take another whole block (iteration limit or end of the
+// Nothing is decided inside this kernel. A pixel for which a filter fired is rolled back to the last
+// checkpoint (at most 16 iterations back, see k3_fast_body) and EXPORTED (state, index) while its lane-mates
+// simply keep going; so is a pixel that cannot take another whole block (iteration limit or end of the
 // orbit table less than 4 steps away). Exported pixels are parked on the reference orbit itself
 // (delta = eps = 0, which stays 0 and never flags) until the lane's pass through the chunk ends, and
 // are appended to the event queue with the same warp-aggregated reservation as the survivors that
-// move on to the next chunk. k3_events then replays at most 4 checked steps per exported pixel with
+// move on to the next chunk. k3_events then replays at most 24 checked steps per exported pixel with
 // the exact double comparisons — escape (+ smoothing), glitch (-> re-queue list), iteration limit,
 // rebase at the end of the orbit, or "false alarm" (-> carried into the next sweep, index again a
 // multiple of 4). Every decision is therefore the one k3_perturb.cuh and the oracle take.
@@ -28,11 +31,19 @@
 // ran 5x slower than the simple kernel — profiles/r01b_*.)
 #pragma once
 #include "k3_checked.cuh"
+#include "k3_filter.cuh"
 #include "k3_perturb.cuh"
 
 namespace nm {
 
 constexpr int K3F_THREADS = 256;
+#ifndef K3F_MIN_CTAS
+#define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? 2 : 3)   // register budget: 128 / 80 per thread (measured: DESIGN.md)
+#endif
+// shared-memory bytes of the per-chunk tables (2Z, filter entries, escape words) / of everything k3_fast<P> needs
+__host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
+  return (((size_t)(CH + 4) * (sizeof(double2) + sizeof(int4) + sizeof(int32_t))) + 15) & ~(size_t)15;
+}
 constexpr int K3_EVENT_BUDGET = 252;  // extra checked steps k3_events grants a freshly rebased state (multiple of 4)
 
 template <bool SCALED>
@@ -47,7 +58,10 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
     EpsVal<SCALED> eps;
     eps.load(eps_tab, e.pix);
     int steps = 0;
-    bool cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, 4, &steps);
+    // 24 = a whole segment of k3_fast (the event lies at most 16 steps past the checkpoint) + two blocks: a
+    // candidate of the escape filter whose |z|^2 is still below 2^20 at the segment end escapes within the
+    // next step or two (|z| > 700 squares), so it is finished here and not carried
+    bool cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, 24, &steps);
     // A state that was just rebased onto the start of the orbit (it outlived the reference: |z| is
     // large) nearly always escapes within a few steps: finish it here rather than carrying it through
     // another sweep of (mostly empty) level launches. Same steps, same decisions, same order.
@@ -57,7 +71,7 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
       steps += more;
     }
     if (cont) {
-      // carried into the next sweep (index is a multiple of 4 again: 0 after a rebase, block start + 4 else)
+      // carried into the next sweep (index is a multiple of 4 again: 0 after a rebase, checkpoint + 24 else)
       unsigned long long slot = atomicAdd(carry_count, 1ULL);
       carry.d[slot] = make_double2(e.dr, e.di);
       carry.j[slot] = e.j;
@@ -76,9 +90,66 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
   }
 }
 
+// One branch-free block of 4 iterations for the P slots of a lane, in place. jrel = the block's start index
+// relative to the chunk. bad[s] |= the glitch filter (k3_filter.cuh) fired for slot s in this block.
+template <int P, bool SCALED>
+__device__ __forceinline__ void k3_block(double (&dr)[P], double (&di)[P], const double (&er)[P], const double (&ei)[P],
+                                         const double (&S)[P], const uint32_t (&sm)[P],
+                                         const double2* __restrict__ sZ2, const int4* __restrict__ sF, int jrel,
+                                         bool (&bad)[P]) {
+  double2 x2 = sZ2[jrel];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int jl = jrel + t + 1;   // the new delta pairs with Z[j + t + 1]
+    const int4 f = sF[jl];
+    double2 x2n = x2;
+    if (t < 3) x2n = sZ2[jl];
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      double wr, wi;
+      if (SCALED) { wr = __fma_rn(S[s], dr[s], x2.x); wi = __fma_rn(S[s], di[s], x2.y); }
+      else { wr = x2.x + dr[s]; wi = x2.y + di[s]; }   // == fma(2, Z, delta): 2Z is exact
+      const double ndr = __fma_rn(-di[s], wi, __fma_rn(dr[s], wr, er[s]));
+      const double ndi = __fma_rn(di[s], wr, __fma_rn(dr[s], wi, ei[s]));
+      dr[s] = ndr; di[s] = ndi;
+      uint32_t ca = (uint32_t)__double2hiint(ndr) - (uint32_t)f.x;   // k3_filter_glitch
+      uint32_t cb = (uint32_t)__double2hiint(ndi) - (uint32_t)f.z;
+      if (SCALED) { ca |= sm[s]; cb |= sm[s]; }
+      bad[s] = bad[s] | ((ca <= (uint32_t)f.y) & (cb <= (uint32_t)f.w));
+    }
+    x2 = x2n;
+  }
+}
+
+// Per-thread slot records in shared memory (k3_fast keeps only delta and eps in registers).
+// Layout [field][slot][thread]: conflict-free for the warp-wide accesses.
+template <int P>
+struct K3Slots {
+  double2* ck;     // delta at the last checkpoint = the state an exported slot hands to k3_events
+  int32_t* pix;
+  int32_t* off;
+  int32_t* evj;    // orbit index of the checkpoint an exported slot was rolled back to
+  __device__ __forceinline__ K3Slots(unsigned char* base) {
+    ck = (double2*)base;
+    pix = (int32_t*)(base + (size_t)P * K3F_THREADS * sizeof(double2));
+    off = pix + P * K3F_THREADS;
+    evj = off + P * K3F_THREADS;
+  }
+  static constexpr size_t bytes() { return (size_t)P * K3F_THREADS * (sizeof(double2) + 3 * sizeof(int32_t)); }
+};
+
 // SCALED: states carry a scale exponent (floatexp.cuh). A lane's slots share j, so "re-normalise
-// before the step from j = 0 (mod 64)" is one test per lane and block; the per-slot scale S = 2^e and
+// before the step from j = 0 (mod 64)" is one test per lane and segment; the per-slot scale S = 2^e and
 // eps / 2^e live in registers between re-normalisations.
+//
+// A lane's pass through the chunk runs in SEGMENTS that end at the orbit indices = 0 (mod 16) (at most 4 blocks).
+// At the start of a segment the lane's deltas are checkpointed in shared memory; the filters' verdicts are
+// looked at once per segment (the glitch flags are sticky; the escape filter looks at the segment's last delta:
+// a slot that escaped earlier in the segment has |delta| growing without bound since — inf or NaN at worst,
+// whose high words pass the filter too, and which disturb nobody: slots do not interact). A flagged slot is
+// exported with its checkpoint state, so k3_events replays at most 16 steps to reach the event.
+// Against the one-block-at-a-time form (profiles/r01k_*: 250 instructions per 96 FP64, of which 34 register
+// moves for the roll-back copy and 18 for the per-block escape test) this leaves ~150.
 template <int P, bool SCALED>
 __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -86,12 +157,14 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
   const int jbase = p.k * CH;
   int nload = p.Jmax + 1 - jbase;
   if (nload > CH + 1) nload = CH + 1;
-  const int nload2 = (nload + 1) & ~1;  // bulk copies move multiples of 16 bytes
-  double2* sZ = (double2*)smem_raw;
-  const int32_t* sG = (const int32_t*)(smem_raw + (size_t)(CH + 4) * sizeof(double2));  // gb[] doubles; high word at [2i+1]
-  // 2*Z[j], formed once per CTA: w = 2Z + delta is then a DADD of two table values instead of fma(2, Z, delta)
-  // (bit-identical: 2Z is exact) — DADD issues ~9 % faster than DFMA on this part (profiles/r01_fp64_peak.json)
-  double2* sZ2 = (double2*)(smem_raw + (size_t)(CH + 4) * (sizeof(double2) + sizeof(double)));
+  const int nload4 = (nload + 3) & ~3;  // bulk copies move multiples of 16 bytes
+  // per index of the chunk: 2*Z[j] (w = 2Z + delta is a DADD of a table value: bit-identical to fma(2, Z, delta)
+  // since 2Z is exact, and DADD issues ~9 % faster than DFMA on this part, profiles/r01_fp64_peak.json), the
+  // glitch-filter entry and the escape-filter high word (k3_filter.cuh); built once per table upload
+  double2* sZ2 = (double2*)smem_raw;
+  const int4* sF = (const int4*)(smem_raw + (size_t)(CH + 4) * sizeof(double2));
+  const int32_t* sE = (const int32_t*)(smem_raw + (size_t)(CH + 4) * (sizeof(double2) + sizeof(int4)));
+  K3Slots<P> slots(smem_raw + k3f_table_bytes(CH));
   __shared__ __align__(8) uint64_t bar;
 
   const unsigned long long n_cur = p.cur_count ? *p.cur_count : 0ULL;
@@ -114,35 +187,36 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t bz = (uint32_t)nload * (uint32_t)sizeof(double2);
-    uint32_t bg = (uint32_t)nload2 * (uint32_t)sizeof(double);
-    mbar_expect_tx(&bar, bz + bg);
-    bulk_g2s(sZ, p.Z + jbase, bz, &bar);
-    bulk_g2s((void*)sG, p.gb + jbase, bg, &bar);
+    uint32_t be = (uint32_t)nload4 * (uint32_t)sizeof(int32_t);
+    mbar_expect_tx(&bar, 2 * bz + be);
+    bulk_g2s(sZ2, p.Z2 + jbase, bz, &bar);
+    bulk_g2s((void*)sF, p.filt + jbase, bz, &bar);
+    bulk_g2s((void*)sE, p.esc_hi + jbase, be, &bar);
   }
 
   const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
   const int jend = jbase + CH;
   const int jcap = jend < p.Jmax ? jend : p.Jmax;  // a pass can never step beyond this index
 
-  // slot state: 0 empty/parked, 1 live, 2 exported (ev_* hold the state to hand to k3_events)
-  double dr[P], di[P], er[P], ei[P], ev_dr[P], ev_di[P], S[P];
-  int pix[P], off[P], st[P], ev_j[P], sc[P];
+  // registers: delta, eps (and the scale of a scaled state); bit s of `live` / `expo`: slot s is iterating /
+  // was exported (its record sits in `slots`); neither: empty. Exported and empty slots are parked on the
+  // reference orbit itself (delta = eps = 0 stays 0 and never flags).
+  double dr[P], di[P], er[P], ei[P], S[P];
+  int sc[P];
+  uint32_t sm[P];   // SCALED: all-ones while the slot holds a scaled state (its d is not delta: k3_filter.cuh)
+  unsigned live = 0, expo = 0;
   bool drained = false;
   int j = 0;
   unsigned long long executed = 0;
 #pragma unroll
-  for (int s = 0; s < P; ++s) {
-    dr[s] = di[s] = er[s] = ei[s] = ev_dr[s] = ev_di[s] = 0.0; S[s] = 1.0;
-    pix[s] = -1; off[s] = -1; st[s] = 0; ev_j[s] = 0; sc[s] = 0;
-  }
+  for (int s = 0; s < P; ++s) { dr[s] = di[s] = er[s] = ei[s] = 0.0; S[s] = 1.0; sc[s] = 0; sm[s] = 0u; }
 
   mbar_wait(&bar, 0);
-  for (int i = threadIdx.x; i < nload; i += blockDim.x) { const double2 z = sZ[i]; sZ2[i] = make_double2(2.0 * z.x, 2.0 * z.y); }
-  __syncthreads();
 
   for (;;) {
     // ---- re-deal: one group of P same-index pixels per lane (every lane is idle here) ------------
-    bool lane_active = false;
+    live = 0; expo = 0;
     if (!drained) {
       unsigned long long base = 0;
       if (lane == 0) {
@@ -156,35 +230,37 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
         if (g < g_total) {
 #pragma unroll
           for (int s = 0; s < P; ++s) {
-            dr[s] = di[s] = er[s] = ei[s] = 0.0; pix[s] = -1; off[s] = -1; st[s] = 0; sc[s] = 0; S[s] = 1.0;
+            dr[s] = di[s] = er[s] = ei[s] = 0.0; sc[s] = 0; S[s] = 1.0; sm[s] = 0u;
+            int pix = -1, off = -1;
             if (g < g_cur) {
               unsigned long long idx = g * P + s;
               if (idx < n_cur) {
                 PixState q = p.cur[idx];
-                dr[s] = q.dr; di[s] = q.di; pix[s] = q.pix; off[s] = q.off; j = q.j; sc[s] = SCALED ? q.e : 0;
+                dr[s] = q.dr; di[s] = q.di; pix = q.pix; off = q.off; j = q.j; sc[s] = SCALED ? q.e : 0;
               }
             } else {
               int w = p.fresh_ids[fresh_begin + (unsigned)((g - g_cur) * P + s)];
               if (w >= 0) {
                 double2 d0 = p.fresh.d[w];
-                dr[s] = d0.x; di[s] = d0.y; off[s] = p.fresh.off[w]; j = p.fresh.j[w]; pix[s] = p.fresh.pix[w];
+                dr[s] = d0.x; di[s] = d0.y; off = p.fresh.off[w]; j = p.fresh.j[w]; pix = p.fresh.pix[w];
                 if (SCALED) sc[s] = p.fresh.e[w];
               }
             }
-            if (pix[s] >= 0) {
+            if (pix >= 0) {
               EpsVal<SCALED> eps;
-              eps.load(p.eps, pix[s]);
+              eps.load(p.eps, pix);
               er[s] = eps.re_at(sc[s]);
               ei[s] = eps.im_at(sc[s]);
-              if (SCALED) S[s] = pow2d(sc[s]);
-              st[s] = 1;
-              lane_active = true;
+              if (SCALED) { S[s] = pow2d(sc[s]); sm[s] = sc[s] ? 0xffffffffu : 0u; }
+              slots.pix[s * K3F_THREADS + tid] = pix;
+              slots.off[s * K3F_THREADS + tid] = off;
+              live |= 1u << s;
             }
           }
         }
       }
     }
-    if (!__any_sync(FULL_MASK, lane_active)) break;
+    if (!__any_sync(FULL_MASK, live != 0)) break;
 
     // ---- one warp-synchronous pass through the chunk -----------------------------------------------
     const int j_in = j;  // every slot of this lane's group entered at this index
@@ -193,87 +269,82 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
       // their iteration limit — unless they simply reached the chunk end with room beyond it: those
       // move on to the next level after the loop. nb = whole blocks every remaining live slot can take.
       int nb = 0x7fffffff;
-      bool any_live = false;
+      bool any_room = false;
 #pragma unroll
       for (int s = 0; s < P; ++s)
-        if (st[s] == 1) {
-          const int jN = p.N - 1 - off[s];
+        if (live & (1u << s)) {
+          const int jN = p.N - 1 - slots.off[s * K3F_THREADS + tid];
           const int lim = jcap < jN ? jcap : jN;
           const int room = (lim - j) >> 2;
-          if (room > 0) { any_live = true; if (room < nb) nb = room; }
+          if (room > 0) { any_room = true; if (room < nb) nb = room; }
           else if (!(j == jend && j < p.Jmax && jN > j)) {
-            st[s] = 2; ev_dr[s] = dr[s]; ev_di[s] = di[s]; ev_j[s] = j;
+            live &= ~(1u << s); expo |= 1u << s;
+            slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
+            slots.evj[s * K3F_THREADS + tid] = j;
             executed += (unsigned long long)(j - j_in);
             dr[s] = di[s] = er[s] = ei[s] = 0.0;
           }
         }
-      if (!(lane_active && any_live)) nb = 0;
+      if (!any_room) nb = 0;
       if (!__any_sync(FULL_MASK, nb > 0)) break;
 
-      // nb branch-free blocks; a flagged slot is rolled back, exported and parked on the spot, its
-      // lane-mates keep going (their limits can only be farther away, so nb stays valid)
-      for (int b = 0; __any_sync(FULL_MASK, b < nb); ++b) {
+      // nb blocks in segments (see above); a flagged slot is rolled back to the segment's checkpoint, exported
+      // and parked, its lane-mates keep going (their limits can only be farther away, so nb stays valid)
+      for (int b = 0; __any_sync(FULL_MASK, b < nb);) {
         if (b < nb) {
           if (SCALED && (j & RENORM_MASK) == 0) {
 #pragma unroll
             for (int s = 0; s < P; ++s)
-              if (st[s] == 1) {
+              if (live & (1u << s)) {
                 pstate ps; ps.dr = dr[s]; ps.di = di[s]; ps.e = sc[s];
                 state_renorm(ps);
                 if (ps.e != sc[s]) {
                   EpsVal<SCALED> eps;
-                  eps.load(p.eps, pix[s]);
+                  eps.load(p.eps, slots.pix[s * K3F_THREADS + tid]);
                   er[s] = eps.re_at(ps.e); ei[s] = eps.im_at(ps.e);
                   S[s] = pow2d(ps.e);
                 }
-                dr[s] = ps.dr; di[s] = ps.di; sc[s] = ps.e;
+                dr[s] = ps.dr; di[s] = ps.di; sc[s] = ps.e; sm[s] = ps.e ? 0xffffffffu : 0u;
               }
           }
-          double dr0[P], di0[P];
+          int n4 = 4 - ((j >> 2) & 3);   // blocks up to the next index = 0 (mod 16)
+          if (n4 > nb - b) n4 = nb - b;
+          const int j_ck = j;
 #pragma unroll
-          for (int s = 0; s < P; ++s) { dr0[s] = dr[s]; di0[s] = di[s]; }
-          double2 x2 = sZ2[j - jbase];
+          for (int s = 0; s < P; ++s)
+            if (live & (1u << s)) slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
           bool bad[P];
-          int hi_last[P];
 #pragma unroll
           for (int s = 0; s < P; ++s) bad[s] = false;
+          if (n4 == 4) {   // the common case, straight-line: the sticky flags stay in predicate registers
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int jl = j + t + 1 - jbase;
-            const double2 y = sZ[jl];
-            const double2 y2 = sZ2[jl];
-            const int g = sG[2 * jl + 1];
-#pragma unroll
-            for (int s = 0; s < P; ++s) {
-              double wr, wi;
-              if (SCALED) { wr = __fma_rn(S[s], dr[s], x2.x); wi = __fma_rn(S[s], di[s], x2.y); }
-              else { wr = x2.x + dr[s]; wi = x2.y + di[s]; }   // == fma(2, Z, delta): 2Z is exact
-              double ndr = __fma_rn(-di[s], wi, __fma_rn(dr[s], wr, er[s]));
-              double ndi = __fma_rn(di[s], wr, __fma_rn(dr[s], wi, ei[s]));
-              dr[s] = ndr; di[s] = ndi;
-              double zr, zi;
-              if (SCALED) { zr = __fma_rn(S[s], ndr, y.x); zi = __fma_rn(S[s], ndi, y.y); }
-              else { zr = y.x + ndr; zi = y.y + ndi; }
-              double zmag = __fma_rn(zi, zi, zr * zr);
-              int hi = __double2hiint(zmag);
-              bad[s] = bad[s] || (hi <= g);
-              hi_last[s] = hi;
+            for (int q = 0; q < 4; ++q) k3_block<P, SCALED>(dr, di, er, ei, S, sm, sZ2, sF, j - jbase + 4 * q, bad);
+            j += 16;
+          } else {
+            for (int q = 0; q < n4; ++q) {
+              k3_block<P, SCALED>(dr, di, er, ei, S, sm, sZ2, sF, j - jbase, bad);
+              j += 4;
             }
-            x2 = y2;
           }
+          b += n4;
+          const int esc_hi = sE[j - jbase];   // k3_filter_escape on the segment's last delta
           bool any_bad = false;
 #pragma unroll
-          for (int s = 0; s < P; ++s) { bad[s] = bad[s] || (hi_last[s] >= ESC_HI); any_bad = any_bad || bad[s]; }
+          for (int s = 0; s < P; ++s) {
+            const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
+            bad[s] = bad[s] | ((__double2hiint(dr[s]) & keep) >= esc_hi) | ((__double2hiint(di[s]) & keep) >= esc_hi);
+            any_bad = any_bad | bad[s];
+          }
           if (any_bad) {
 #pragma unroll
             for (int s = 0; s < P; ++s)
-              if (st[s] == 1 && bad[s]) {
-                st[s] = 2; ev_dr[s] = dr0[s]; ev_di[s] = di0[s]; ev_j[s] = j;
-                executed += (unsigned long long)(j - j_in);
+              if ((live & (1u << s)) && bad[s]) {
+                live &= ~(1u << s); expo |= 1u << s;   // slots.ck already holds the state to hand over
+                slots.evj[s * K3F_THREADS + tid] = j_ck;
+                executed += (unsigned long long)(j_ck - j_in);
                 dr[s] = di[s] = er[s] = ei[s] = 0.0;
               }
           }
-          j += 4;
         }
       }
     }
@@ -281,20 +352,22 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
     // ---- hand over (converged; warp-aggregated appends) --------------------------------------------
 #pragma unroll
     for (int s = 0; s < P; ++s) {
-      const bool toNext = lane_active && st[s] == 1;   // reached the chunk end alive
-      const bool toEvents = lane_active && st[s] == 2;
+      const bool toNext = (live >> s) & 1u;     // reached the chunk end alive
+      const bool toEvents = (expo >> s) & 1u;
       if (toNext) executed += (unsigned long long)(j - j_in);
       unsigned long long slot = warp_reserve(p.next_count, toNext);
       if (toNext) {
-        PixState q; q.dr = dr[s]; q.di = di[s]; q.pix = pix[s]; q.j = j; q.off = off[s]; q.e = SCALED ? sc[s] : 0;
+        PixState q; q.dr = dr[s]; q.di = di[s]; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = j;
+        q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;
         p.next[slot] = q;
       }
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
-        PixState q; q.dr = ev_dr[s]; q.di = ev_di[s]; q.pix = pix[s]; q.j = ev_j[s]; q.off = off[s]; q.e = SCALED ? sc[s] : 0;  // an exported slot is parked: its exponent is never re-normalised
+        const double2 d = slots.ck[s * K3F_THREADS + tid];
+        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = slots.evj[s * K3F_THREADS + tid];
+        q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;  // an exported slot is parked: its exponent is never re-normalised
         events[slot] = q;
       }
-      st[s] = 0; pix[s] = -1;
     }
   }
 
@@ -309,7 +382,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
 constexpr unsigned long long K3F_SPARSE_MAX = 148ULL * 2 * K3F_THREADS;
 
 template <int P, bool SCALED>
-__global__ void __launch_bounds__(K3F_THREADS, (P == 4 ? 2 : (SCALED ? 2 : 3)))
+__global__ void __launch_bounds__(K3F_THREADS, K3F_MIN_CTAS(P, SCALED))
 k3_fast(K3Params p, PixState* events) {
   const int jbase = p.k * p.CH;
   int l1 = jbase + p.CH;

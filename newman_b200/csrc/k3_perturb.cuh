@@ -44,6 +44,9 @@ struct K3Params {
   const double2* Z;      // [Jmax+1 (+pad)]
   const int32_t* ghi;    // high words of gb[j] = glitch_tol*|Z[j]|^2
   const double* gb;      // full doubles (slow-path exact check)
+  const double2* Z2;     // k3_fast: 2*Z[j] (exact)
+  const int4* filt;      // k3_fast: glitch-filter entries (k3_filter.cuh: K3Filt)
+  const int32_t* esc_hi; // k3_fast: escape-filter high words
   int Jmax;              // last valid table index
   int N, CH, k;
   EpsTab eps;

@@ -69,7 +69,7 @@ struct nm_ctx {
   int paldev_n = 0;  // entries of the device-generated palette in paldev (0: none)
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
-  DevBuf Z, ghi, gb, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
+  DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
       rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
@@ -106,17 +106,22 @@ int fail(nm_ctx* ctx, int code, const char* fmt, ...) {
                   cudaGetErrorString(e__));                                                    \
   } while (0)
 
-__global__ void k_glitch_bounds(const double2* Z, double* gb, int32_t* ghi, int n, int pad_n, double gtol,
-                                int zero_last) {
+// Per-index tables derived from the orbit: the glitch bound (and its high word for k3_level), and for
+// k3_fast 2*Z[j] and the candidate-filter entries of k3_filter.cuh.
+__global__ void k_glitch_bounds(const double2* Z, double* gb, int32_t* ghi, double2* Z2, K3Filt* filt, int32_t* esc_hi,
+                                int n, int pad_n, double gtol, int zero_last) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= pad_n) return;
   double v = 0.0;
-  if (j > 0 && j < n && !(zero_last && j == n - 1)) {
-    double2 z = Z[j];
-    v = (z.x * z.x + z.y * z.y) * gtol;
-  }
+  const double2 z = Z[j];   // zero beyond the table
+  if (j > 0 && j < n && !(zero_last && j == n - 1)) v = (z.x * z.x + z.y * z.y) * gtol;
   gb[j] = v;
   ghi[j] = __double2hiint(v);
+  Z2[j] = make_double2(2.0 * z.x, 2.0 * z.y);
+  K3Filt f; int32_t e;
+  k3_filter_entry(z.x, z.y, v, &f, &e);
+  filt[j] = f;
+  esc_hi[j] = e;
 }
 
 __global__ void k_apply_fixups(nm_escape* out, const int32_t* pix, const float* val, int n) {
@@ -344,6 +349,7 @@ int launch_deep(nm_ctx* ctx) {
   // ---- K3 ---------------------------------------------------------------------------------------
   K3Params p;
   p.Z = ctx->Z.as<double2>(); p.ghi = ctx->ghi.as<int32_t>(); p.gb = ctx->gb.as<double>();
+  p.Z2 = ctx->Z2.as<double2>(); p.filt = ctx->k3filt.as<int4>(); p.esc_hi = ctx->esc_hi.as<int32_t>();
   p.Jmax = ctx->Jmax; p.N = ctx->N; p.CH = CH;
   p.eps = eps; p.nc = ctx->nc;
   p.fresh_ids = ctx->fresh.as<int32_t>();
@@ -353,7 +359,9 @@ int launch_deep(nm_ctx* ctx) {
   p.rq_pix = ctx->rq_pix.as<int32_t>(); p.rq_iter = ctx->rq_iter.as<int32_t>();
   p.log_bailout = ctx->log_bailout;
 
-  const size_t smem = (size_t)(CH + 4) * (sizeof(double2) + sizeof(double) + (fast ? sizeof(double2) : 0));
+  // k3_level: Z + glitch-bound words; k3_fast: 2Z + filter entries + escape words + the slot records (k3_fast.cuh)
+  const size_t smem = fast ? k3f_table_bytes(CH) + (G == 4 ? K3Slots<4>::bytes() : K3Slots<2>::bytes())
+                           : (size_t)(CH + 4) * (sizeof(double2) + sizeof(double));
   int occ = (scaled ? ctx->occ_k3s : ctx->occ_k3)[ctx->mode == NM_MODE_REBASE ? 1 : 0];
   if (G == 2) occ = (scaled ? ctx->occ_k3fs : ctx->occ_k3f)[0];
   if (G == 4) occ = (scaled ? ctx->occ_k3fs : ctx->occ_k3f)[1];
@@ -556,15 +564,17 @@ int nm_create(int device, nm_ctx** out) {
   NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, true>), K3_THREADS, ctx->occ_k3s[0]);
   NM_K3_SETUP((k3_level<NM_MODE_REBASE, true>), K3_THREADS, ctx->occ_k3s[1]);
 #undef NM_K3_SETUP
-  const size_t smem_f = smem + (size_t)(ctx->CH + 4) * sizeof(double2);   // + the 2Z table of k3_fast
-#define NM_K3_SETUP(fn, threads, occ_out)                                                                       \
-  NM_CREATE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));           \
-  NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(occ_out), fn, threads, smem_f));                \
-  if ((occ_out) < 1) (occ_out) = 1;
-  NM_K3_SETUP((k3_fast<2, false>), K3F_THREADS, ctx->occ_k3f[0]);
-  NM_K3_SETUP((k3_fast<4, false>), K3F_THREADS, ctx->occ_k3f[1]);
-  NM_K3_SETUP((k3_fast<2, true>), K3F_THREADS, ctx->occ_k3fs[0]);
-  NM_K3_SETUP((k3_fast<4, true>), K3F_THREADS, ctx->occ_k3fs[1]);
+#define NM_K3_SETUP(fn, P, occ_out)                                                                             \
+  {                                                                                                             \
+    const size_t smem_f = k3f_table_bytes(ctx->CH) + K3Slots<P>::bytes();   /* k3_fast.cuh */                   \
+    NM_CREATE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));         \
+    NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(occ_out), fn, K3F_THREADS, smem_f));         \
+    if ((occ_out) < 1) (occ_out) = 1;                                                                           \
+  }
+  NM_K3_SETUP((k3_fast<2, false>), 2, ctx->occ_k3f[0]);
+  NM_K3_SETUP((k3_fast<4, false>), 4, ctx->occ_k3f[1]);
+  NM_K3_SETUP((k3_fast<2, true>), 2, ctx->occ_k3fs[0]);
+  NM_K3_SETUP((k3_fast<4, true>), 4, ctx->occ_k3fs[1]);
 #undef NM_K3_SETUP
   NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k1, k1_escape, K1_THREADS, 0));
 #undef NM_CREATE_CUDA
@@ -578,7 +588,7 @@ void nm_destroy(nm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->own);
-  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi,
+  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
                     &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
@@ -689,6 +699,9 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->Z.ensure((size_t)(J1 + 8) * sizeof(double2)));
   NM_CUDA(ctx, ctx->gb.ensure((size_t)(J1 + 8) * sizeof(double)));
   NM_CUDA(ctx, ctx->ghi.ensure((size_t)(J1 + 8) * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->Z2.ensure((size_t)(J1 + 8) * sizeof(double2)));
+  NM_CUDA(ctx, ctx->k3filt.ensure((size_t)(J1 + 8) * sizeof(K3Filt)));
+  NM_CUDA(ctx, ctx->esc_hi.ensure((size_t)(J1 + 8) * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->xlo.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->a.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->b.ensure((size_t)M * sizeof(double2)));
@@ -744,7 +757,8 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   }
   {
     int pad_n = J1 + 8;
-    k_glitch_bounds<<<(pad_n + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->ghi.as<int32_t>(), J1,
+    k_glitch_bounds<<<(pad_n + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->ghi.as<int32_t>(),
+                                                        ctx->Z2.as<double2>(), ctx->k3filt.as<K3Filt>(), ctx->esc_hi.as<int32_t>(), J1,
                                                         pad_n, ctx->gtol, ctx->has_escape);
     NM_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
@@ -991,11 +1005,28 @@ int nm_resolve_device_palette(nm_ctx* ctx, int N, int sc, int smooth, uint8_t* r
                      rgb_out);
 }
 
+void nm_k3_filter_entry(double zr, double zi, double gb, uint32_t entry[5]) {
+  K3Filt f; int32_t e;
+  k3_filter_entry(zr, zi, gb, &f, &e);
+  entry[0] = f.lo_r; entry[1] = f.w_r; entry[2] = f.lo_i; entry[3] = f.w_i; entry[4] = (uint32_t)e;
+}
+
+int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int scaled, int* glitch, int* escape) {
+  K3Filt f; f.lo_r = entry[0]; f.w_r = entry[1]; f.lo_i = entry[2]; f.w_i = entry[3];
+  const uint32_t m = scaled ? 0xffffffffu : 0u;
+  const bool g = k3_filter_glitch(f, dr, di, m), e = k3_filter_escape((int32_t)entry[4], dr, di, m);
+  if (glitch) *glitch = g;
+  if (escape) *escape = e;
+  return (g || e) ? 1 : 0;
+}
+
 int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms_out) {
-  if (!ctx || kind < 0 || kind > 3 || iters < 1) return NM_EINVAL;
+  if (!ctx || kind < 0 || kind > 11 || iters < 1) return NM_EINVAL;
   if (int rc = set_device(ctx)) return rc;
   NM_CUDA(ctx, ctx->fixapply.ensure(64));
-  const unsigned blocks = (unsigned)ctx->sm_count * 8;
+  // kinds 4-7: DFMA + 0/8/16/24 integer operations per 8 DFMA at full occupancy (64 warps/SM); 8-11: the
+  // same at 16 warps/SM (k3_fast's occupancy). The rate returned counts the FP64 instructions only.
+  const unsigned blocks = (unsigned)ctx->sm_count * (kind >= 8 ? 2 : 8);
   cudaEvent_t a, b;
   NM_CUDA(ctx, cudaEventCreate(&a));
   NM_CUDA(ctx, cudaEventCreate(&b));
@@ -1006,7 +1037,11 @@ int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* m
     if (kind == 0) fp64_peak_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
     else if (kind == 1) fp64_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
     else if (kind == 2) fp64_peak_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else fp64_k3mix_kernel<<<blocks, 256, 0, ctx->stream>>>(sink, iters / 4 + 1, 0.3, -0.2, 0.31, -0.19);
+    else if (kind == 3) fp64_k3mix_kernel<<<blocks, 256, 0, ctx->stream>>>(sink, iters / 4 + 1, 0.3, -0.2, 0.31, -0.19);
+    else if ((kind & 3) == 0) fp64_int_mix_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
+    else if ((kind & 3) == 1) fp64_int_mix_kernel<8><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
+    else if ((kind & 3) == 2) fp64_int_mix_kernel<16><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
+    else fp64_int_mix_kernel<24><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
     NM_CUDA(ctx, cudaGetLastError());
     NM_CUDA(ctx, cudaEventRecord(b, ctx->stream));
     NM_CUDA(ctx, cudaEventSynchronize(b));
