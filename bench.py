@@ -31,13 +31,33 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K3_INST_PER_ITER = 10   # 7 DFMA + 2 DADD + 1 DMUL (k3_perturb.cuh)
-K3_FLOPS_PER_ITER = 17
+# k3_fast runs the delta recurrence alone: 2 DADD + 4 DFMA = 6 FP64 instructions, 10 flops per iteration; the
+# glitch / escape decisions ride on the integer pipe (k3_filter.cuh). (The simple kernel k3_level, --k3-group 0,
+# forms z and |z|^2 as well: 10 instructions, 17 flops.)
+K3_INST_PER_ITER = 6
+K3_FLOPS_PER_ITER = 10
+K3_INST_PER_ITER_SIMPLE = 10
+K3_FLOPS_PER_ITER_SIMPLE = 17
 # DRAM bytes per state and full-level launch of the dominant kernel, from the ncu --set full capture
-# profiles/r01f_k3_fast4_cfg3_metrics.txt (1.065 GB read + 1.018 GB written for 33 177 600 states): the
+# profiles/r01l_k3_fast_cfg3_metrics.txt (1.072 GB read + 1.018 GB written for 33 177 600 states): the
 # 32-byte state of every sample in and out once = the algorithmic traffic (64 B), nothing re-read.
-K3_DRAM_B_PER_STATE = (1.065023e9 + 1.018445e9) / 33177600
+K3_DRAM_B_PER_STATE = (1.072093e9 + 1.018343e9) / 33177600
 K2_INST_PER_EVAL = 19   # 12 DMUL + 6 DADD + ... (k2_series.cuh phase-1 body incl. the compare)
+
+
+def mix_ceiling(hw, simple, executed, k_ms, peak_dadd, peak_dfma3):
+    """What the measured instruction rates allow for k3_fast's instruction mix: per iteration 2 DADD at the DADD
+    rate + 4 DFMA whose three 64-bit operands are all different registers — such a DFMA issues at 2/3 of the
+    pipe rate (register read port; tools/issue_probe.py, nm_fp64_peak kind 12). Iterations/s as a fraction of
+    that ceiling says how close the kernel is to what the SM can deliver for THIS arithmetic; `frac` (against
+    the plain DADD rate) is the stricter, instruction-mix-agnostic number."""
+    if hw or simple or not (k_ms > 0 and peak_dadd and peak_dfma3):
+        return {}
+    ceiling = 1.0 / (2.0 / peak_dadd + 4.0 / peak_dfma3)       # iterations/s
+    return {"mix_ceiling_giter_s": ceiling / 1e9, "frac_of_mix_ceiling": executed / (k_ms * 1e-3) / ceiling,
+            "peak_dfma_3_distinct_operands_ginst": peak_dfma3 / 1e9}
+
+
 METRIC = "executed pixel-iterations/sec"
 UNIT = "Giter/s"
 
@@ -449,6 +469,7 @@ def run_ours(args):
     # FP64 issue peak measured live on this box (MEASURED_PEAKS.json has no FP64 entry)
     peak_dfma, _ = dev.fp64_peak(0, 1 << 15)
     peak_dadd, _ = dev.fp64_peak(1, 1 << 15)
+    peak_dfma3, _ = dev.fp64_peak(12, 1 << 15)   # DFMA reading 3 registers no neighbour shares (operand-port bound)
     dev.sync()
 
     # ---- timed: device-resident ---------------------------------------------------------------------
@@ -537,7 +558,10 @@ def run_ours(args):
         h2d = (8 * (nc + len(rows))) * world if hw else per_step_tables * world
         d2h = nr * nc * 8
         # roofline of the dominant kernel, FP64 pipe (no tensor cores, not HBM bound)
-        k_inst = executed / world * (K3_INST_PER_ITER if not hw else 8)
+        simple = args.k3_group == 0
+        k3_inst_iter = K3_INST_PER_ITER_SIMPLE if simple else K3_INST_PER_ITER
+        k3_flops_iter = K3_FLOPS_PER_ITER_SIMPLE if simple else K3_FLOPS_PER_ITER
+        k_inst = executed / world * (k3_inst_iter if not hw else 8)
         k_name = "k3_level (FP64 perturbation)" if not hw else "k1_escape (plain double)"
         k_ms = k3_ms
         if k2_ms > k3_ms:
@@ -560,14 +584,17 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "fp64_pipe", "kernel": k_name, "achieved": achieved, "peak": peak_dadd / 1e9,
                          "unit": "Ginst/s", "frac": achieved / (peak_dadd / 1e9) if peak_dadd else None,
-                         "bound_note": "neither hbm nor tensor: 10 FP64 instructions per 0.06 B of DRAM traffic, no contraction "
-                                       "(SURVEY.md 8d); achieved = executed iterations x 10 FP64 instructions / K3 device time",
+                         "bound_note": "neither hbm nor tensor: FP64 instructions per 0.06 B of DRAM traffic, no contraction "
+                                       "(SURVEY.md 8d); achieved = executed iterations x FP64 instructions per iteration "
+                                       "(inst_per_iter) / K3 device time of whole frames (all levels, sparse ones included)",
+                         "inst_per_iter": (k3_inst_iter if not hw else 8),
+                         **mix_ceiling(hw, simple, executed / world, k_ms, peak_dadd, peak_dfma3),
                          "traffic": None if hw else K3_DRAM_B_PER_STATE * len(rows) * nc,
                          "traffic_note": None if hw else "bytes per full-level launch of k3_fast for this rank's states, from the "
-                                         "ncu capture profiles/r01f_k3_fast4_cfg3_metrics.txt (62.8 B per state; algorithmic 64 B)",
+                                         "ncu capture profiles/r01l_k3_fast_cfg3_metrics.txt (63.0 B per state; algorithmic 64 B)",
                          "peak_source": "measured live: nm_fp64_peak DADD issue rate (MEASURED_PEAKS.json has no FP64 entry)",
                          "peak_dfma_ginst": peak_dfma / 1e9,
-                         "fp64_tflops": executed / world * K3_FLOPS_PER_ITER / (k3_ms * 1e-3) / 1e12 if (k3_ms > 0 and not hw) else None,
+                         "fp64_tflops": executed / world * k3_flops_iter / (k3_ms * 1e-3) / 1e12 if (k3_ms > 0 and not hw) else None,
                          "fp64_tflops_peak_dfma": 2 * peak_dfma / 1e12,
                          "kernel_ms_per_step": k_ms / args.steps, "k2_ms_per_step": k2_ms / args.steps,
                          "k3_ms_per_step": k3_ms / args.steps},
@@ -716,6 +743,7 @@ def run_video(args):
             render(job, True, False)
     peak_dfma, _ = dev.fp64_peak(0, 1 << 15)
     peak_dadd, _ = dev.fp64_peak(1, 1 << 15)
+    peak_dfma3, _ = dev.fp64_peak(12, 1 << 15)   # DFMA reading 3 registers no neighbour shares (operand-port bound)
     dev.sync()
 
     tot.clear()
@@ -765,7 +793,7 @@ def run_video(args):
     d2h = allred(sum(j["cfg"]["nr"] * j["cfg"]["nc"] * 8 for j in jobs))
     n_hw = allred(sum(1 for j in jobs if j["hw"]))
     if rank == 0:
-        # mixed frames: plain-double frames execute 8, perturbation frames 10 FP64 instructions per iteration
+        # mixed frames: plain-double frames execute 8, perturbation frames 6 FP64 instructions per iteration
         inst = executed / world * K3_INST_PER_ITER
         achieved = inst / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         cfg0 = workloads.video_frame(0, scale=args.scale)
@@ -783,6 +811,8 @@ def run_video(args):
             "roofline": {"bound": "fp64_pipe", "kernel": "k3_fast/k3_level (FP64 perturbation) + k1_escape on the shallow frames",
                          "achieved": achieved, "peak": peak_dadd / 1e9, "unit": "Ginst/s",
                          "frac": achieved / (peak_dadd / 1e9) if peak_dadd else None, "traffic": None,
+                         "inst_per_iter": K3_INST_PER_ITER,
+                         **mix_ceiling(False, False, executed / world, k_ms, peak_dadd, peak_dfma3),
                          "peak_source": "measured live: nm_fp64_peak DADD issue rate", "peak_dfma_ginst": peak_dfma / 1e9,
                          "kernel_ms_per_step": k_ms / args.steps, "k2_ms_per_step": k2_ms / args.steps},
             "executed_iters_per_step": executed / args.steps, "frames_per_step": len(sel),

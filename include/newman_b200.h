@@ -64,6 +64,11 @@ NM_API int nm_sync(nm_ctx* ctx);
 /*   NM_OPT_K3_GROUP (4)    pixels per lane in the fast perturbation kernel (k3_fast.cuh): 4 or 2;
  *                          0/1 selects the simple one-pixel-per-lane kernel (k3_perturb.cuh). Same results. */
 #define NM_OPT_K3_GROUP 2
+/*   NM_OPT_K3_FINISH_MAX (65536; environment NM_K3_FINISH_MAX overrides the default at nm_create)
+ *                          a frame — or what is left of one after a sweep — with at most this many states is run
+ *                          to completion by ONE launch (k3_finish.cuh: one thread per state, no level launches);
+ *                          0: always the level kernels. Same results; the tests run both. */
+#define NM_OPT_K3_FINISH_MAX 3
 NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
 /* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
 NM_API int nm_cancel(nm_ctx* ctx);
@@ -218,7 +223,9 @@ NM_API int nm_resolve_device_palette(nm_ctx* ctx, int N, int sc, int smooth, uin
  * FP64-pipe peak probe: runs `iters` dependent-chain DFMA (kind 0), DADD (1), DMUL (2) per thread
  * (kind 3: the former K3 iteration body from registers, counted as 10 instructions per pixel-iteration;
  * kinds 4-7: 8 DFMA chains interleaved with 0/8/16/24 integer-pipe operations, 64 warps per SM; kinds 8-11:
- * the same at 16 warps per SM — only the FP64 instructions are counted)
+ * the same at 16 warps per SM — only the FP64 instructions are counted; kinds 12-15: DFMA whose instructions
+ * read 3 / 2 / 1 distinct 64-bit registers that no neighbour shares, and DADD with 2: the register-operand
+ * bandwidth behind the FP64 pipe)
  * over a full-chip grid and returns instructions/s. Used by bench.py for the roofline denominator
  * (MEASURED_PEAKS.json carries no FP64 entry). */
 NM_API int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms);

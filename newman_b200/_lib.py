@@ -20,6 +20,7 @@ CARDIOID_NONE, CARDIOID_ALL, CARDIOID_MASK = 0, 1, 2
 MODE_REQUEUE, MODE_REBASE = 0, 1
 OPT_K2_LITERAL = 1
 OPT_K3_GROUP = 2
+OPT_K3_FINISH_MAX = 3
 
 
 class NmError(RuntimeError):

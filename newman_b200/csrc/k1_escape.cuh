@@ -205,6 +205,31 @@ __global__ void __launch_bounds__(256) fp64_int_mix_kernel(double* sink, int ite
   if (s == 123.456 || t == 0x12345678) sink[0] = s + t;
 }
 
+// Register-operand probe: 8 DFMA (or DADD) chains whose instructions read 3 (2, 1) DISTINCT 64-bit register
+// operands that no neighbouring instruction shares, so the operand-reuse caches cannot help — unlike
+// fp64_peak_kernel, whose b and c are the same registers in every instruction. OPS: 3 = fma(a[q], b[q], c[q]),
+// 2 = fma(a[q], b, c[q]), 1 = fma(a[q], b, c) (== kind 0), 0 = a[q] + c[q] (DADD, 2 distinct).
+template <int OPS>
+__global__ void __launch_bounds__(256) fp64_operand_kernel(double* sink, int iters, double b0, double c0) {
+  double a[8], b[8], c[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { a[q] = threadIdx.x * 1e-9 + q; b[q] = b0 + 1e-12 * (q + threadIdx.x); c[q] = c0 * (q + 1); }
+#pragma unroll 2
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (OPS == 3) a[q] = __fma_rn(a[q], b[q], c[q]);
+      else if (OPS == 2) a[q] = __fma_rn(a[q], b[0], c[q]);
+      else if (OPS == 1) a[q] = __fma_rn(a[q], b[0], c[0]);
+      else a[q] = __dadd_rn(a[q], c[q]);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += a[q] + b[q] + c[q];
+  if (s == 123.456) sink[0] = s;
+}
+
 // The K3 iteration body itself (4 pixels per thread, all operands in distinct registers, no memory):
 // what the FP64 pipe sustains for this exact instruction mix (7 DFMA + 2 DADD + 1 DMUL per pixel-
 // iteration with three different 64-bit register operands per DFMA).

@@ -39,10 +39,11 @@ template <> struct EpsVal<true> {
   __device__ __forceinline__ double im_at(int e) const { return eps_scaled(i, i0, e); }
 };
 
-// Exact single step + decisions, shared by K2's alignment steps and k3_events. Returns:
-//   0 continue, 1 escaped (r2 set), 2 glitched. State (dr, di, j) is advanced in place; (zr, zi) = z.
+// Exact single step + decisions, shared by K2's alignment steps, k3_events and k3_finish. Returns:
+//   0 continue, 1 escaped (r2 set), 2 glitched (MODE_REQUEUE), 3 |z|^2 < |delta|^2: rebase (MODE_REBASE).
+// State (dr, di, j) is advanced in place; (zr, zi) = z.
 // S = 2^e and (er, ei) = eps / 2^e of the state (1 and eps for a plain state).
-template <bool SCALED>
+template <bool SCALED, int MODE = NM_MODE_REQUEUE>
 __device__ __forceinline__ int checked_step(const double2* __restrict__ Z, const double* __restrict__ gb, int Jmax,
                                             double er, double ei, double S, double& dr, double& di, int& j, double& r2,
                                             double& zr, double& zi) {
@@ -59,7 +60,14 @@ __device__ __forceinline__ int checked_step(const double2* __restrict__ Z, const
   else { zr = y.x + dr; zi = y.y + di; }
   double zmag = __fma_rn(zi, zi, zr * zr);
   if (zmag > BAILOUT2) { r2 = zr * zr + zi * zi; return 1; }  // sqMag as the reference forms it (complex.h:23)
-  if (j != Jmax && zmag < gb[j]) return 2;
+  if (MODE == NM_MODE_REQUEUE) {
+    if (j != Jmax && zmag < gb[j]) return 2;
+  } else {
+    double dmag;   // |delta|^2 of the value itself (k3_perturb.cuh: exact when S == 1)
+    if (SCALED) { const double tr = S * dr, ti = S * di; dmag = __fma_rn(ti, ti, tr * tr); }
+    else dmag = __fma_rn(di, di, dr * dr);
+    if (zmag < dmag) return 3;
+  }
   return 0;
 }
 

@@ -25,6 +25,7 @@
 #include "k2_series.cuh"
 #include "k3_perturb.cuh"
 #include "k3_fast.cuh"
+#include "k3_finish.cuh"
 #include "k4_resolve.cuh"
 #include "k5_video.cuh"
 #include "k6_palette.cuh"
@@ -74,6 +75,7 @@ struct nm_ctx {
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
+  long long opt_k3_finish_max = K3_FINISH_MAX_STATES;  // frames / remainders up to this many states: k3_finish
   int occ_k3f[2] = {0, 0}, occ_k3fs[2] = {0, 0};
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
   double tol = 0, gtol = 0;
@@ -387,6 +389,27 @@ int launch_deep(nm_ctx* ctx) {
 
   for (int sweep = 0;; ++sweep) {
     const int par = sweep & 1;
+    // Few states (left): run them to completion in one launch instead of sweeping every level (k3_finish.cuh).
+    // Sweep 0: K2's hand-over (W entries, finished ones marked); later sweeps of the fast path: the carried states.
+    const unsigned long long n_states = sweep == 0 ? (unsigned long long)ctx->W : ctx->h_ctr[0];
+    if ((sweep == 0 || fast) && n_states <= (unsigned long long)ctx->opt_k3_finish_max) {
+      unsigned fb = (unsigned)((n_states + K3_FINISH_THREADS - 1) / K3_FINISH_THREADS);
+      if (fb < 1) fb = 1;
+      const unsigned long long* cnt = sweep == 0 ? nullptr : &ccount[par];
+      const FreshArrays fa = fresh_set(ctx, par);
+      const long long nmax = (long long)ctx->W;
+      if (ctx->mode == NM_MODE_REBASE) {
+        if (scaled) k3_finish<NM_MODE_REBASE, true><<<fb, K3_FINISH_THREADS, 0, st>>>(ck, eps, fa, cnt, nmax);
+        else k3_finish<NM_MODE_REBASE, false><<<fb, K3_FINISH_THREADS, 0, st>>>(ck, eps, fa, cnt, nmax);
+      } else {
+        if (scaled) k3_finish<NM_MODE_REQUEUE, true><<<fb, K3_FINISH_THREADS, 0, st>>>(ck, eps, fa, cnt, nmax);
+        else k3_finish<NM_MODE_REQUEUE, false><<<fb, K3_FINISH_THREADS, 0, st>>>(ck, eps, fa, cnt, nmax);
+      }
+      NM_CUDA(ctx, cudaGetLastError());
+      ctx->stats.kernel_launches++;
+      ctx->stats.sweeps++;
+      break;
+    }
     int kstart = 0;
     if (fast || sweep == 0) kstart = min_j >= (unsigned long long)(K * CH) ? K : (int)(min_j / (unsigned long long)CH);
     // chunk-sorted "fresh" list of this sweep: K2's hand-over (sweep 0) or the carried states
@@ -579,6 +602,7 @@ int nm_create(int device, nm_ctx** out) {
   NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k1, k1_escape, K1_THREADS, 0));
 #undef NM_CREATE_CUDA
   if (ctx->occ_k1 < 1) ctx->occ_k1 = 1;
+  if (const char* fm = getenv("NM_K3_FINISH_MAX")) { const long long v = atoll(fm); if (v >= 0) ctx->opt_k3_finish_max = v; }
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
   return NM_OK;
@@ -615,6 +639,10 @@ int nm_set_option(nm_ctx* ctx, int key, int value) {
     case NM_OPT_K3_GROUP:
       if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, NM_EINVAL, "NM_OPT_K3_GROUP must be 0, 1, 2 or 4");
       ctx->opt_k3_group = value;
+      return NM_OK;
+    case NM_OPT_K3_FINISH_MAX:
+      if (value < 0) return fail(ctx, NM_EINVAL, "NM_OPT_K3_FINISH_MAX must be >= 0");
+      ctx->opt_k3_finish_max = value;
       return NM_OK;
     default: return fail(ctx, NM_EINVAL, "nm_set_option: unknown key %d", key);
   }
@@ -1021,12 +1049,13 @@ int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int scaled
 }
 
 int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* ms_out) {
-  if (!ctx || kind < 0 || kind > 11 || iters < 1) return NM_EINVAL;
+  if (!ctx || kind < 0 || kind > 15 || iters < 1) return NM_EINVAL;
   if (int rc = set_device(ctx)) return rc;
   NM_CUDA(ctx, ctx->fixapply.ensure(64));
   // kinds 4-7: DFMA + 0/8/16/24 integer operations per 8 DFMA at full occupancy (64 warps/SM); 8-11: the
   // same at 16 warps/SM (k3_fast's occupancy). The rate returned counts the FP64 instructions only.
-  const unsigned blocks = (unsigned)ctx->sm_count * (kind >= 8 ? 2 : 8);
+  // kinds 12-15: DFMA with 3 / 2 / 1 distinct register operands per instruction, DADD with 2 (64 warps/SM).
+  const unsigned blocks = (unsigned)ctx->sm_count * ((kind >= 8 && kind < 12) ? 2 : 8);
   cudaEvent_t a, b;
   NM_CUDA(ctx, cudaEventCreate(&a));
   NM_CUDA(ctx, cudaEventCreate(&b));
@@ -1038,6 +1067,10 @@ int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* m
     else if (kind == 1) fp64_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
     else if (kind == 2) fp64_peak_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
     else if (kind == 3) fp64_k3mix_kernel<<<blocks, 256, 0, ctx->stream>>>(sink, iters / 4 + 1, 0.3, -0.2, 0.31, -0.19);
+    else if (kind == 12) fp64_operand_kernel<3><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
+    else if (kind == 13) fp64_operand_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
+    else if (kind == 14) fp64_operand_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
+    else if (kind == 15) fp64_operand_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
     else if ((kind & 3) == 0) fp64_int_mix_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
     else if ((kind & 3) == 1) fp64_int_mix_kernel<8><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
     else if ((kind & 3) == 2) fp64_int_mix_kernel<16><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);

@@ -24,5 +24,8 @@ def oracles_built():
 def dev():
     import newman_b200
     d = newman_b200.Device(0)
+    # device-level tests exercise the level kernels (k3_fast / k3_level) on their small fixtures; the
+    # run-to-completion kernel that production uses for such small frames has its own module (test_gpu_finish.py)
+    d.set_option(newman_b200._lib.OPT_K3_FINISH_MAX, 0)
     yield d
     d.close()
