@@ -69,6 +69,11 @@ NM_API int nm_sync(nm_ctx* ctx);
  *                          to completion by ONE launch (k3_finish.cuh: one thread per state, no level launches);
  *                          0: always the level kernels. Same results; the tests run both. */
 #define NM_OPT_K3_FINISH_MAX 3
+/*   NM_OPT_K3_SPLIT (1)    k3_fast: an orbit chunk that follows a chunk in which more than 1/32 of the states
+ *                          escaped is run as 4 quarter-chunk launches with a global compaction after each
+ *                          (decided on the device from the queue counters) if it holds at least 303 104 states;
+ *                          0: always whole chunks; n > 1: that minimum instead (tests). Same results. */
+#define NM_OPT_K3_SPLIT 4
 NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
 /* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
 NM_API int nm_cancel(nm_ctx* ctx);

@@ -21,6 +21,7 @@ MODE_REQUEUE, MODE_REBASE = 0, 1
 OPT_K2_LITERAL = 1
 OPT_K3_GROUP = 2
 OPT_K3_FINISH_MAX = 3
+OPT_K3_SPLIT = 4
 
 
 class NmError(RuntimeError):

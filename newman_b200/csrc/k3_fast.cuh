@@ -44,6 +44,7 @@ constexpr int K3F_THREADS = 256;
 __host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
   return (((size_t)(CH + 4) * (sizeof(double2) + sizeof(int4) + sizeof(int32_t))) + 15) & ~(size_t)15;
 }
+constexpr unsigned long long K3F_SPLIT_MIN = 4ULL * 148 * 2 * 256;   // levels with fewer states are not split (4 x K3F_SPARSE_MAX)
 constexpr int K3_EVENT_BUDGET = 252;  // extra checked steps k3_events grants a freshly rebased state (multiple of 4)
 
 template <bool SCALED>
@@ -121,6 +122,60 @@ __device__ __forceinline__ void k3_block(double (&dr)[P], double (&di)[P], const
   }
 }
 
+// What one launch of k3_fast works on. A level (orbit chunk k) is launched K3F_SUBS times (sub = 0..3). If few
+// states escaped in the level before, launch 0 takes the whole chunk and the others return at once. Otherwise
+// ("split": the level before lost more than 1/32 of its states) launch s takes the quarter-chunk
+// [jbase + s*CH/4, jbase + (s+1)*CH/4) and hands its survivors to launch s+1 through two scratch queues, so the
+// states are compacted globally every CH/4 instead of every CH iterations: where samples escape, a lane's
+// slots die at different times and a dead slot costs the same issue cycles as a live one until the lane's
+// pass ends (profiles/r01h_cfg2_levels.txt: such levels ran at 45-65 % of the rate of full ones). Decided on
+// the device from the queue counters — every CTA of every launch of the level reads the same values — so the
+// host enqueues blindly and nothing is read back.
+constexpr int K3F_SUBS = 4;
+struct K3Work {
+  int jlo, jhi;                      // orbit indices this launch covers; passes end at jhi
+  const PixState* cur; unsigned long long n_cur;
+  PixState* next; unsigned long long* next_count;
+  unsigned long long* head;
+  unsigned fresh_begin; unsigned long long n_fresh;
+  bool run;
+};
+
+__device__ __forceinline__ K3Work k3f_work(const K3Params& p) {
+  K3Work w;
+  const int CH = p.CH, k = p.k, jbase = k * CH;
+  int l1 = jbase + CH;
+  if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
+  const unsigned long long n_in = (p.cur_count ? *p.cur_count : 0ULL) + (p.fresh_off[l1] - p.fresh_off[jbase]);
+  bool split = false;
+  if (p.sub_count && k > 0 && n_in >= p.split_min) {
+    const unsigned long long prev_in = p.qcount[k - 1] + (p.fresh_off[jbase] - p.fresh_off[jbase - CH]);
+    const unsigned long long prev_out = p.qcount[k];
+    split = prev_in > prev_out && (prev_in - prev_out) * 32ULL > prev_in;
+  }
+  w.run = split || p.sub == 0;
+  if (!split) {
+    w.jlo = jbase; w.jhi = jbase + CH;
+    w.cur = p.cur; w.n_cur = p.cur_count ? *p.cur_count : 0ULL;
+    w.next = p.next; w.next_count = p.next_count;
+  } else {
+    const int q = CH / K3F_SUBS;
+    w.jlo = jbase + p.sub * q; w.jhi = w.jlo + q;
+    w.cur = p.sub == 0 ? p.cur : p.tmp[(p.sub - 1) & 1];
+    w.n_cur = p.sub == 0 ? (p.cur_count ? *p.cur_count : 0ULL) : p.sub_count[p.sub - 1];
+    w.next = p.sub == K3F_SUBS - 1 ? p.next : p.tmp[p.sub & 1];
+    w.next_count = p.sub == K3F_SUBS - 1 ? p.next_count : &p.sub_count[p.sub];
+  }
+  w.head = p.head + p.sub;
+  int f1 = w.jhi;
+  if (f1 > p.Jmax + 1) f1 = p.Jmax + 1;
+  int f0 = w.jlo;
+  if (f0 > f1) f0 = f1;
+  w.fresh_begin = p.fresh_off[f0];
+  w.n_fresh = p.fresh_off[f1] - w.fresh_begin;  // multiple of the group size by construction
+  return w;
+}
+
 // Per-thread slot records in shared memory (k3_fast keeps only delta and eps in registers).
 // Layout [field][slot][thread]: conflict-free for the warp-wide accesses.
 template <int P>
@@ -150,53 +205,35 @@ struct K3Slots {
 // exported with its checkpoint state, so k3_events replays at most 16 steps to reach the event.
 // Against the one-block-at-a-time form (profiles/r01k_*: 250 instructions per 96 FP64, of which 34 register
 // moves for the roll-back copy and 18 for the per-block escape test) this leaves ~150.
-template <int P, bool SCALED>
-__device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events) {
+//
+// Units: the launch's states in dealing order — the input queue padded to a multiple of G (the launch's group
+// size: G consecutive units sit at the same orbit index), then the chunk-sorted fresh list (runs padded to G).
+// A body<P> call deals the units [u0, u1) (u0 a multiple of P, P | G), P consecutive ones per lane.
+// GL = the launch's group size: the slot records keep ITS layout in both calls (warps of one CTA may be in
+// different calls at the same time).
+template <int P, int GL, bool SCALED>
+__device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk, PixState* events,
+                                             unsigned long long u0, unsigned long long u1, unsigned long long u_cur,
+                                             unsigned long long* head) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
   const int jbase = p.k * CH;
-  int nload = p.Jmax + 1 - jbase;
-  if (nload > CH + 1) nload = CH + 1;
-  const int nload4 = (nload + 3) & ~3;  // bulk copies move multiples of 16 bytes
   // per index of the chunk: 2*Z[j] (w = 2Z + delta is a DADD of a table value: bit-identical to fma(2, Z, delta)
   // since 2Z is exact, and DADD issues ~9 % faster than DFMA on this part, profiles/r01_fp64_peak.json), the
   // glitch-filter entry and the escape-filter high word (k3_filter.cuh); built once per table upload
-  double2* sZ2 = (double2*)smem_raw;
+  const double2* sZ2 = (const double2*)smem_raw;
   const int4* sF = (const int4*)(smem_raw + (size_t)(CH + 4) * sizeof(double2));
   const int32_t* sE = (const int32_t*)(smem_raw + (size_t)(CH + 4) * (sizeof(double2) + sizeof(int4)));
-  K3Slots<P> slots(smem_raw + k3f_table_bytes(CH));
-  __shared__ __align__(8) uint64_t bar;
+  K3Slots<GL> slots(smem_raw + k3f_table_bytes(CH));
 
-  const unsigned long long n_cur = p.cur_count ? *p.cur_count : 0ULL;
-  unsigned long long n_fresh = 0;
-  unsigned fresh_begin = 0;
-  {
-    int l1 = jbase + CH;
-    if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
-    fresh_begin = p.fresh_off[jbase];
-    n_fresh = p.fresh_off[l1] - fresh_begin;  // multiple of the group size by construction
-  }
-  const unsigned long long g_cur = (n_cur + P - 1) / P;
-  const unsigned long long g_total = g_cur + n_fresh / P;
+  const unsigned long long n_cur = wk.n_cur;
+  const unsigned fresh_begin = wk.fresh_begin;
+  const unsigned long long g_total = (u1 - u0) / P;   // deals of this call
   if (g_total == 0) return;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t bz = (uint32_t)nload * (uint32_t)sizeof(double2);
-    uint32_t be = (uint32_t)nload4 * (uint32_t)sizeof(int32_t);
-    mbar_expect_tx(&bar, 2 * bz + be);
-    bulk_g2s(sZ2, p.Z2 + jbase, bz, &bar);
-    bulk_g2s((void*)sF, p.filt + jbase, bz, &bar);
-    bulk_g2s((void*)sE, p.esc_hi + jbase, be, &bar);
-  }
 
   const int lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
-  const int jend = jbase + CH;
+  const int jend = wk.jhi;   // passes end here (the chunk end, or the end of this launch's quarter)
   const int jcap = jend < p.Jmax ? jend : p.Jmax;  // a pass can never step beyond this index
 
   // registers: delta, eps (and the scale of a scaled state); bit s of `live` / `expo`: slot s is iterating /
@@ -212,8 +249,6 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
 #pragma unroll
   for (int s = 0; s < P; ++s) { dr[s] = di[s] = er[s] = ei[s] = 0.0; S[s] = 1.0; sc[s] = 0; sm[s] = 0u; }
 
-  mbar_wait(&bar, 0);
-
   for (;;) {
     // ---- re-deal: one group of P same-index pixels per lane (every lane is idle here) ------------
     live = 0; expo = 0;
@@ -221,7 +256,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
       unsigned long long base = 0;
       if (lane == 0) {
         if (((volatile unsigned long long*)p.ctr)[CTR_CANCEL]) base = g_total;
-        else base = atomicAdd(p.head, 32ULL);
+        else base = atomicAdd(head, 32ULL);
       }
       base = __shfl_sync(FULL_MASK, base, 0);
       if (base >= g_total) drained = true;
@@ -232,14 +267,14 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
           for (int s = 0; s < P; ++s) {
             dr[s] = di[s] = er[s] = ei[s] = 0.0; sc[s] = 0; S[s] = 1.0; sm[s] = 0u;
             int pix = -1, off = -1;
-            if (g < g_cur) {
-              unsigned long long idx = g * P + s;
-              if (idx < n_cur) {
-                PixState q = p.cur[idx];
+            const unsigned long long u = u0 + g * P + s;
+            if (u < u_cur) {
+              if (u < n_cur) {
+                PixState q = wk.cur[u];
                 dr[s] = q.dr; di[s] = q.di; pix = q.pix; off = q.off; j = q.j; sc[s] = SCALED ? q.e : 0;
               }
             } else {
-              int w = p.fresh_ids[fresh_begin + (unsigned)((g - g_cur) * P + s)];
+              int w = p.fresh_ids[fresh_begin + (unsigned)(u - u_cur)];
               if (w >= 0) {
                 double2 d0 = p.fresh.d[w];
                 dr[s] = d0.x; di[s] = d0.y; off = p.fresh.off[w]; j = p.fresh.j[w]; pix = p.fresh.pix[w];
@@ -355,11 +390,11 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
       const bool toNext = (live >> s) & 1u;     // reached the chunk end alive
       const bool toEvents = (expo >> s) & 1u;
       if (toNext) executed += (unsigned long long)(j - j_in);
-      unsigned long long slot = warp_reserve(p.next_count, toNext);
+      unsigned long long slot = warp_reserve(wk.next_count, toNext);
       if (toNext) {
         PixState q; q.dr = dr[s]; q.di = di[s]; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = j;
         q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;
-        p.next[slot] = q;
+        wk.next[slot] = q;
       }
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
@@ -375,21 +410,56 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, PixState* events
   if (lane == 0 && executed) atomicAdd(&p.ctr[CTR_EXECUTED], executed);
 }
 
-// A level with so few states that every one can have a lane of its own is latency bound: a lane's
-// pass takes 1024 x (P x 10 FP64 instructions issued from ONE warp, ~7 cycles apart) — 146 ns per
-// iteration with P = 4 on the tail levels of cfg2 against 31 ns with one pixel per lane. Such levels
-// (uniformly for the whole grid: the counts are launch-wide) run the same body with P = 1.
-constexpr unsigned long long K3F_SPARSE_MAX = 148ULL * 2 * K3F_THREADS;
-
 template <int P, bool SCALED>
 __global__ void __launch_bounds__(K3F_THREADS, K3F_MIN_CTAS(P, SCALED))
 k3_fast(K3Params p, PixState* events) {
-  const int jbase = p.k * p.CH;
-  int l1 = jbase + p.CH;
-  if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
-  const unsigned long long n_states = (p.cur_count ? *p.cur_count : 0ULL) + (p.fresh_off[l1] - p.fresh_off[jbase]);
-  if (P > 1 && n_states <= K3F_SPARSE_MAX) k3_fast_body<1, SCALED>(p, events);
-  else k3_fast_body<P, SCALED>(p, events);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const K3Work wk = k3f_work(p);
+  if (!wk.run) return;
+  const unsigned long long u_cur = (wk.n_cur + P - 1) / P * P;   // the input queue, padded to whole groups
+  const unsigned long long u_total = u_cur + wk.n_fresh;
+  if (u_total == 0) return;
+
+  // this launch's slice of the chunk tables: one bulk-async copy (TMA) per table and CTA
+  {
+    const int CH = p.CH, jbase = p.k * CH;
+    const int first = wk.jlo - jbase;          // entries [first, first + nload) of the chunk's tables are needed
+    int nload = p.Jmax + 1 - wk.jlo;
+    if (nload > wk.jhi - wk.jlo + 1) nload = wk.jhi - wk.jlo + 1;
+    const int nload4 = (nload + 3) & ~3;  // bulk copies move multiples of 16 bytes
+    double2* sZ2 = (double2*)smem_raw;
+    int4* sF = (int4*)(smem_raw + (size_t)(CH + 4) * sizeof(double2));
+    int32_t* sE = (int32_t*)(smem_raw + (size_t)(CH + 4) * (sizeof(double2) + sizeof(int4)));
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t bz = (uint32_t)nload * (uint32_t)sizeof(double2);
+      uint32_t be = (uint32_t)nload4 * (uint32_t)sizeof(int32_t);
+      mbar_expect_tx(&bar, 2 * bz + be);
+      bulk_g2s(sZ2 + first, p.Z2 + wk.jlo, bz, &bar);
+      bulk_g2s((void*)(sF + first), p.filt + wk.jlo, bz, &bar);
+      bulk_g2s((void*)(sE + first), p.esc_hi + wk.jlo, be, &bar);
+    }
+    mbar_wait(&bar, 0);
+  }
+
+  // Whole waves of lane groups (grid x 256 lanes x P states) run with P states per lane. What is left over
+  // would cost a whole pass of its own however few lanes it fills; if it is at most 3/4 of a wave it is dealt
+  // one state per lane instead: such a pass issues a quarter of the instructions and is latency bound at about
+  // a quarter of the time (profiles/r01h_cfg2_levels.txt: 31 against 146 ns per iteration), and at most three
+  // of them are needed. (Levels with less than 3/4 of a wave altogether run entirely that way.)
+  unsigned long long u_a = u_total;
+  if (P > 1) {
+    const unsigned long long wave = (unsigned long long)gridDim.x * K3F_THREADS * P;
+    const unsigned long long rem = u_total % wave;
+    if (rem * 4 <= wave * 3) u_a = u_total - rem;
+  }
+  if (u_a > 0) k3_fast_body<P, P, SCALED>(p, wk, events, 0, u_a, u_cur, wk.head);
+  if (P > 1 && u_a < u_total) k3_fast_body<1, P, SCALED>(p, wk, events, u_a, u_total, u_cur, wk.head + K3F_SUBS);
 }
 
 }  // namespace nm

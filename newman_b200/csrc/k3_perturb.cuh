@@ -58,6 +58,13 @@ struct K3Params {
   FreshArrays fresh;           // hand-over records the fresh_ids index
   PixState* next;
   unsigned long long* next_count;
+  // k3_fast only (k3_fast.cuh: K3Work): which of the level's K3F_SUBS launches this is, the queue counters of
+  // all levels (qcount[k] = survivors handed to level k), two scratch queues and their counters for a split level
+  int sub;
+  const unsigned long long* qcount;
+  PixState* tmp[2];
+  unsigned long long* sub_count;
+  unsigned long long split_min;   // levels with fewer states are never split
   PixState* restart;
   unsigned long long* restart_count;
   unsigned long long* head;

@@ -75,6 +75,7 @@ struct nm_ctx {
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
+  int opt_k3_split = 1;  // k3_fast: levels that follow an escape-heavy level run as 4 quarter-chunk launches
   long long opt_k3_finish_max = K3_FINISH_MAX_STATES;  // frames / remainders up to this many states: k3_finish
   int occ_k3f[2] = {0, 0}, occ_k3fs[2] = {0, 0};
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
@@ -266,10 +267,13 @@ int launch_deep(nm_ctx* ctx) {
   const int K = ctx->K;
   cudaStream_t st = ctx->stream;
   unsigned long long* qctr = ctx->qctr.as<unsigned long long>();
-  // qctr layout: qcount[K+2] | head[K+2] | rcount[2] | carry_count[2]
+  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | rcount[2] | carry_count[2]
+  // (head: per level, per quarter-chunk launch, one deal cursor for the 4-states-per-lane waves and one for the
+  //  one-state-per-lane remainder: k3_fast.cuh)
   unsigned long long* qcount = qctr;
   unsigned long long* head = qctr + (K + 2);
-  unsigned long long* rcount = qctr + 2 * (K + 2);
+  unsigned long long* subcount = qctr + 9 * (K + 2);
+  unsigned long long* rcount = qctr + 13 * (K + 2);
   unsigned long long* ccount = rcount + 2;
   unsigned long long* ctr = ctx->ctr.as<unsigned long long>();
 
@@ -424,7 +428,7 @@ int launch_deep(nm_ctx* ctx) {
       ctx->stats.kernel_launches += 2;
       NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(nbins + 2) * sizeof(unsigned), st));
     }
-    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 2 * (K + 2) * sizeof(unsigned long long), st));
+    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 13 * (K + 2) * sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&rcount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ccount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_EVENTS], 0, sizeof(unsigned long long), st));
@@ -443,14 +447,27 @@ int launch_deep(nm_ctx* ctx) {
       p.next_count = &qcount[k + 1];
       p.restart = ctx->rq[par ^ 1].as<PixState>();
       p.restart_count = &rcount[par ^ 1];
-      p.head = &head[k];
+      p.head = &head[2 * K3F_SUBS * k];
       p.fresh_off = have_fresh ? ctx->offs.as<unsigned>() : nullptr;
-      cudaError_t e;
+      p.qcount = qcount;
+      p.tmp[0] = ctx->rq[0].as<PixState>(); p.tmp[1] = ctx->rq[1].as<PixState>();   // idle in the fast path
+      p.split_min = ctx->opt_k3_split > 1 ? (unsigned long long)ctx->opt_k3_split : K3F_SPLIT_MIN;
+      p.sub_count = (ctx->opt_k3_split && (unsigned long long)ctx->W >= p.split_min) ? &subcount[K3F_SUBS * k] : nullptr;
+      cudaError_t e = cudaSuccess;
       PixState* evq = ctx->events.as<PixState>();
-      if (G == 4 && scaled) { k3_fast<4, true><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
-      else if (G == 4) { k3_fast<4, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
-      else if (G == 2 && scaled) { k3_fast<2, true><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
-      else if (G == 2) { k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq); e = cudaGetLastError(); }
+      if (fast) {   // K3F_SUBS launches per level; all but the first return at once unless the level is split (K3Work)
+        // (a frame that cannot reach the split minimum is spared the three empty launches per level)
+        const int subs = (ctx->opt_k3_split && (unsigned long long)ctx->W >= p.split_min) ? K3F_SUBS : 1;
+        for (int sub = 0; sub < subs && e == cudaSuccess; ++sub) {
+          p.sub = sub;
+          if (G == 4 && scaled) k3_fast<4, true><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
+          else if (G == 4) k3_fast<4, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
+          else if (scaled) k3_fast<2, true><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
+          else k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
+          e = cudaGetLastError();
+          if (sub) ctx->stats.kernel_launches++;
+        }
+      }
       else if (scaled) e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, true>(ctx, p, blocks, smem)
                                                        : launch_level<NM_MODE_REQUEUE, true>(ctx, p, blocks, smem);
       else e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, false>(ctx, p, blocks, smem)
@@ -640,6 +657,10 @@ int nm_set_option(nm_ctx* ctx, int key, int value) {
       if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, NM_EINVAL, "NM_OPT_K3_GROUP must be 0, 1, 2 or 4");
       ctx->opt_k3_group = value;
       return NM_OK;
+    case NM_OPT_K3_SPLIT:
+      if (value < 0) return fail(ctx, NM_EINVAL, "NM_OPT_K3_SPLIT must be >= 0");
+      ctx->opt_k3_split = value;
+      return NM_OK;
     case NM_OPT_K3_FINISH_MAX:
       if (value < 0) return fail(ctx, NM_EINVAL, "NM_OPT_K3_FINISH_MAX must be >= 0");
       ctx->opt_k3_finish_max = value;
@@ -747,7 +768,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     NM_CUDA(ctx, ctx->q[i].ensure(Wn * sizeof(PixState)));
     NM_CUDA(ctx, ctx->rq[i].ensure(Wn * sizeof(PixState)));
   }
-  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(2 * (K + 2) + 4) * sizeof(unsigned long long)));
+  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(13 * (K + 2) + 4) * sizeof(unsigned long long)));
   NM_CUDA(ctx, ctx->rq_pix.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->rq_iter.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->events.ensure(Wn * sizeof(PixState)));

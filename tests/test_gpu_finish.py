@@ -100,3 +100,30 @@ def test_finish_option_validation():
         dev.set_option(L.OPT_K3_FINISH_MAX, 1 << 20)
     finally:
         dev.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("group", [4, 2])
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D90", "KAT-S"])
+def test_split_levels_vs_oraclep(kat, group):
+    """NM_OPT_K3_SPLIT: chunks that follow an escape-heavy chunk run as four quarter-chunk launches with a global
+    compaction after each (k3_fast.cuh: K3Work). With the state-count minimum lowered to 2 the small fixtures
+    take that path wherever samples escape; rasters, glitch lists and counts must not change — plain, floatexp
+    series and scaled forms."""
+    t, er, ei = kat_inputs(kat)
+    dev = newman_b200.Device(0)
+    try:
+        dev.set_option(L.OPT_K3_FINISH_MAX, 0)
+        dev.set_option(L.OPT_K3_GROUP, group)
+        base = p_render_deep(t, er, ei, mode=0)
+        launches = []
+        for split in (0, 2):
+            dev.set_option(L.OPT_K3_SPLIT, split)
+            gs = check(dev, t, er, ei, 0, base)
+            launches.append(gs["kernel_launches"])
+            ts, mr, mi = t.floatexp(er, ei)
+            check(dev, t.floatexp(), er, ei, 0, base)
+            check(dev, ts, mr, mi, 0, base)
+        assert launches[1] > launches[0]
+    finally:
+        dev.close()
