@@ -16,12 +16,13 @@
 namespace nm {
 
 constexpr int K3_FINISH_THREADS = 128;
-constexpr int K3_FINISH_BURST = 16;
+constexpr int K3_FINISH_BURST = 8;
 constexpr long long K3_FINISH_MAX_STATES = 65536;   // above this the level kernels win (measured: DESIGN.md)
 
 template <int MODE, bool SCALED>
 __global__ void __launch_bounds__(K3_FINISH_THREADS) k3_finish(CheckedParams p, EpsTab eps_tab, FreshArrays f,
                                                               const unsigned long long* count, long long n_max) {
+  __shared__ double2 park[K3_FINISH_BURST][K3_FINISH_THREADS];   // the burst's deltas, one column per thread
   const unsigned long long n = count ? *count : (unsigned long long)n_max;
   unsigned long long executed = 0, rebased = 0;
   for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < n;
@@ -43,13 +44,16 @@ __global__ void __launch_bounds__(K3_FINISH_THREADS) k3_finish(CheckedParams p, 
       ++rebased; off = j + off; j = 0; dr = zr; di = zi;
       if (SCALED) { e = 0; S = 1.0; er = eps.r0; ei = eps.i0; }
     }
-    // Bursts of up to 16 steps in which nothing is decided: the delta recurrence (3 dependent FP64 operations
-    // per step — at one warp per scheduler the ~40-cycle FP64 latency is all there is, profiles/r01m_*) runs
-    // ahead while z, |z|^2 and the comparisons trail off the critical path into one sticky flag. A flagged
-    // burst is rolled back and replayed step by step with the decisions taken in order, so the results are
-    // those of the step-by-step loop (the first version of this kernel: 4x slower).
+    // Bursts of up to K3_FINISH_BURST steps in which nothing is decided: the delta recurrence (3 dependent FP64
+    // operations per step — at one warp per scheduler the ~40-cycle FP64 latency is all there is,
+    // profiles/r01m_*) runs ahead while z, |z|^2 and the comparisons trail off the critical path into one bit
+    // per step, and every step's delta is parked in shared memory. The first set bit is the step at which the
+    // step-by-step loop would have stopped (all steps before it took no decision, so its operands are the same
+    // bits): its delta is fetched back and the decision taken there, in the loop's order. Nothing is replayed.
+    // (v1 of this kernel decided every step: 4x slower; v2 replayed flagged bursts: 1.6x slower, because in
+    // MODE_REBASE a sample whose delta has grown to the size of z rebases every few steps.)
     for (unsigned burst = 0;; ++burst) {
-      if ((burst & 63u) == 63u && ((volatile unsigned long long*)p.ctr)[CTR_CANCEL]) break;   // ~ every 1000 steps
+      if ((burst & 63u) == 63u && ((volatile unsigned long long*)p.ctr)[CTR_CANCEL]) break;   // ~ every 500 steps
       int nb = p.Jmax - j;
       const int nN = p.N - 1 - off - j;   // steps until it = j + off reaches N - 1
       if (nN < nb) nb = nN;
@@ -61,13 +65,13 @@ __global__ void __launch_bounds__(K3_FINISH_THREADS) k3_finish(CheckedParams p, 
         dr = ps.dr; di = ps.di; e = ps.e;
         S = pow2d(e); er = eps.re_at(e); ei = eps.im_at(e);
       }
-      const double dr0 = dr, di0 = di;
       const int j0 = j;
       double zr = 0.0, zi = 0.0;
-      bool flag = false;
+      unsigned mask = 0;
       {
         double2 x = p.Z[j];
-        for (int t = 0; t < nb; ++t) {
+        // one undecided step; t = its position in the burst
+        auto step = [&](int t) {
           const double2 y = p.Z[j + 1];
           double wr, wi;
           if (SCALED) { wr = __fma_rn(S, dr, 2.0 * x.x); wi = __fma_rn(S, di, 2.0 * x.y); }
@@ -75,6 +79,7 @@ __global__ void __launch_bounds__(K3_FINISH_THREADS) k3_finish(CheckedParams p, 
           const double ndr = __fma_rn(-di, wi, __fma_rn(dr, wr, er));
           const double ndi = __fma_rn(di, wr, __fma_rn(dr, wi, ei));
           dr = ndr; di = ndi;
+          park[t][threadIdx.x] = make_double2(dr, di);
           x = y;
           ++j;
           if (SCALED) { zr = __fma_rn(S, dr, y.x); zi = __fma_rn(S, di, y.y); }
@@ -88,50 +93,64 @@ __global__ void __launch_bounds__(K3_FINISH_THREADS) k3_finish(CheckedParams p, 
             else dmag = __fma_rn(di, di, dr * dr);
             c = c | (zmag < dmag);
           }
-          flag = flag | c;
+          mask |= (c ? 1u : 0u) << t;
+        };
+        if (nb == K3_FINISH_BURST) {
+          // straight-line: a warp issues in order, so the trailing test of one step only gets out of the next
+          // step's way if the scheduler can interleave them in the instruction stream (a rolled loop ran at
+          // ~400 cycles per step: delta chain + test chain back to back; profiles/r01n_*)
+#pragma unroll
+          for (int t = 0; t < K3_FINISH_BURST; ++t) step(t);
+        } else {
+          for (int t = 0; t < nb; ++t) step(t);
         }
       }
-      bool done = false;
-      if (flag) {   // replay: at most nb checked steps, decisions in order
-        dr = dr0; di = di0; j = j0;
-        for (int t = 0; t < nb && !done; ++t) {
-          double r2;
-          const int ev = checked_step<SCALED, MODE>(p.Z, p.gb, p.Jmax, er, ei, S, dr, di, j, r2, zr, zi);
-          ++executed;
-          if (ev == 1) {
-            bool unc;
-            const float sm = smoothing_f32(r2, p.log_bailout, &unc);
-            nm_escape v; v.iterations = j + off; v.smoothing = sm;
-            p.out[pix] = v;
-            if (unc) push_fixup(p.ctr, p.fix, p.fix_cap, pix, r2);
-            done = true;
-          } else if (ev == 2) {   // MODE_REQUEUE only
-            const unsigned long long slot = atomicAdd(&p.ctr[CTR_REQUEUE], 1ULL);
-            p.rq_pix[slot] = pix;
-            p.rq_iter[slot] = j + off;
-            nm_escape v; v.iterations = -1; v.smoothing = 0.0f;
-            p.out[pix] = v;
-            done = true;
-          } else if (ev == 3) {   // MODE_REBASE: |z| < |delta| — unless this step was the last one allowed
-            if (j + off + 1 >= p.N) break;
-            ++rebased;
-            off = j + off; j = 0;
-            dr = zr; di = zi;
-            if (SCALED) { e = 0; S = 1.0; er = eps.r0; ei = eps.i0; }
-            break;   // new index: start a fresh burst
-          }
+      int ev = 0;
+      double r2 = 0.0;
+      if (mask) {   // back to the first step that decides something
+        const int t = __ffs(mask) - 1;
+        const double2 d = park[t][threadIdx.x];
+        dr = d.x; di = d.y;
+        j = j0 + t + 1;
+        executed += (unsigned long long)(t + 1);
+        const double2 y = p.Z[j];
+        if (SCALED) { zr = __fma_rn(S, dr, y.x); zi = __fma_rn(S, di, y.y); }
+        else { zr = y.x + dr; zi = y.y + di; }
+        const double zmag = __fma_rn(zi, zi, zr * zr);
+        if (zmag > BAILOUT2) { ev = 1; r2 = zr * zr + zi * zi; }   // sqMag as the reference forms it (complex.h:23)
+        else if (MODE == NM_MODE_REQUEUE) { if (j != p.Jmax && zmag < p.gb[j]) ev = 2; }
+        else {
+          double dmag;
+          if (SCALED) { const double tr = S * dr, ti = S * di; dmag = __fma_rn(ti, ti, tr * tr); }
+          else dmag = __fma_rn(di, di, dr * dr);
+          if (zmag < dmag) ev = 3;
         }
-        if (done) break;
       } else {
         executed += (unsigned long long)nb;
+      }
+      if (ev == 1) {
+        bool unc;
+        const float sm = smoothing_f32(r2, p.log_bailout, &unc);
+        nm_escape v; v.iterations = j + off; v.smoothing = sm;
+        p.out[pix] = v;
+        if (unc) push_fixup(p.ctr, p.fix, p.fix_cap, pix, r2);
+        break;
+      }
+      if (ev == 2) {   // MODE_REQUEUE only
+        const unsigned long long slot = atomicAdd(&p.ctr[CTR_REQUEUE], 1ULL);
+        p.rq_pix[slot] = pix;
+        p.rq_iter[slot] = j + off;
+        nm_escape v; v.iterations = -1; v.smoothing = 0.0f;
+        p.out[pix] = v;
+        break;
       }
       if (j + off + 1 >= p.N) {   // iteration limit (mandelbrot.cpp:226-228)
         nm_escape v; v.iterations = p.N; v.smoothing = 0.0f;
         p.out[pix] = v;
         break;
       }
-      if (j == p.Jmax) {   // the sample outlived the orbit: continue from Z[0] = 0 with delta = z
-        ++rebased;
+      if (ev == 3 || j == p.Jmax) {   // |z| < |delta| (MODE_REBASE), or the sample outlived the orbit:
+        ++rebased;                    // continue from Z[0] = 0 with delta = z
         off = j + off; j = 0;
         dr = zr; di = zi;
         if (SCALED) { e = 0; S = 1.0; er = eps.r0; ei = eps.i0; }
