@@ -1,8 +1,8 @@
 #!/bin/bash
 # ncu --set full capture of the dominant kernel (k3_fast) on a FULL 1024-iteration level. Run under gpurun:
 #   tools/prof_k3.sh <tag> [bench.py options...]        e.g.  tools/prof_k3.sh r01k --workload cfg3 --scale 2
-# Pass 1 lists every k3_fast launch of the command with its duration (cheap), pass 2 captures the two longest
-# consecutive ones of that list with the full metric set. Summaries for profiles/:
+# Pass 1 lists every k3_fast launch of the command with its duration (cheap), pass 2 captures the longest one of
+# that list (a full, unsplit level) and its successor with the full metric set. Summaries for profiles/:
 #   python tools/ncu_summary.py metrics gpurun_out/<tag>_k3fast.ncu-rep > profiles/<tag>_k3_fast_metrics.txt
 tag=$1; shift
 cmd="python bench.py --steps 1 --warmup 3 --no-cpu-baseline $*"
@@ -17,7 +17,7 @@ for r in rows[hi + 1:]:
     if len(r) > vi:
         v = float(r[vi].replace(",", "")); u = r[ui]
         d.append(v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u, 1.0))
-best = max(range(len(d) - 1), key=lambda i: min(d[i], d[i + 1]))
+best = max(range(len(d) - 1), key=lambda i: d[i])
 print(best)
 PY
 )
