@@ -37,9 +37,13 @@
 namespace nm {
 
 constexpr int K3F_THREADS = 256;
-#ifndef K3F_MIN_CTAS
-#define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? 2 : 3)   // register budget: 128 / 80 per thread (measured: DESIGN.md)
+#ifndef K3F_CTAS_PLAIN
+#define K3F_CTAS_PLAIN 2    // CTAs per SM the plain / the scaled kernel is compiled for: 2 = up to 128 registers per
+#endif                      // thread, 3 = 80 (measured both ways for both kernels: 3 is 1.7 % slower)
+#ifndef K3F_CTAS_SCALED
+#define K3F_CTAS_SCALED 2
 #endif
+#define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? K3F_CTAS_SCALED : K3F_CTAS_PLAIN)
 // shared-memory bytes of the per-chunk tables (2Z, filter entries, escape words) / of everything k3_fast<P> needs
 __host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
   return (((size_t)(CH + 4) * (sizeof(double2) + sizeof(int4) + sizeof(int32_t))) + 15) & ~(size_t)15;
