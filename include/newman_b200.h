@@ -241,6 +241,11 @@ NM_API int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, do
  * perturbation loop and must have no false negatives; tests/test_k3_filter.py attacks that claim. */
 NM_API void nm_k3_filter_entry(double zr, double zi, double gb, uint32_t entry[5]);
 NM_API int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int scaled, int* glitch, int* escape);
+/* Host-side evaluation of k3_fast's quiet bound for the segment of 16 iterations that starts at orbit index j0
+ * (k3_filter.cuh: k3_seg_bound): z = the table Z[0..jmax] as interleaved (re, im) doubles, gb[0..jmax] the glitch
+ * bounds, e_max >= |eps| of every sample. Returns the high word T: a state with hi(|dr|) < T and hi(|di|) < T at j0
+ * cannot satisfy the glitch test at any of the indices j0+1 .. j0+16 (0 = no state is exempt). */
+NM_API int32_t nm_k3_seg_bound(const double* z, const double* gb, int j0, int jmax, double e_max);
 NM_API int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes, char* name, int cap);
 
 /* ==== view level: the drop-in class through C ===================================================

@@ -43,6 +43,9 @@ constexpr int K3F_THREADS = 256;
 #ifndef K3F_CTAS_SCALED
 #define K3F_CTAS_SCALED 2
 #endif
+#ifndef K3F_QUIET
+#define K3F_QUIET 1         // quiet segments (k3_filter.cuh: k3_seg_bound) run without the per-iteration glitch filter
+#endif
 #define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? K3F_CTAS_SCALED : K3F_CTAS_PLAIN)
 // shared-memory bytes of the per-chunk tables (2Z, filter entries, escape words) / of everything k3_fast<P> needs
 __host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
@@ -123,6 +126,26 @@ __device__ __forceinline__ void k3_block(double (&dr)[P], double (&di)[P], const
       bad[s] = bad[s] | ((ca <= (uint32_t)f.y) & (cb <= (uint32_t)f.w));
     }
     x2 = x2n;
+  }
+}
+
+// The same block for a QUIET segment (k3_filter.cuh: no slot of the warp can glitch before the segment ends): the
+// recurrence alone.
+template <int P, bool SCALED>
+__device__ __forceinline__ void k3_block_quiet(double (&dr)[P], double (&di)[P], const double (&er)[P], const double (&ei)[P],
+                                               const double (&S)[P], const double2* __restrict__ sZ2, int jrel) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const double2 x2 = sZ2[jrel + t];
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      double wr, wi;
+      if (SCALED) { wr = __fma_rn(S[s], dr[s], x2.x); wi = __fma_rn(S[s], di[s], x2.y); }
+      else { wr = x2.x + dr[s]; wi = x2.y + di[s]; }
+      const double ndr = __fma_rn(-di[s], wi, __fma_rn(dr[s], wr, er[s]));
+      const double ndi = __fma_rn(di[s], wr, __fma_rn(dr[s], wi, ei[s]));
+      dr[s] = ndr; di[s] = ndi;
+    }
   }
 }
 
@@ -330,7 +353,13 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
       // nb blocks in segments (see above); a flagged slot is rolled back to the segment's checkpoint, exported
       // and parked, its lane-mates keep going (their limits can only be farther away, so nb stays valid)
       for (int b = 0; __any_sync(FULL_MASK, b < nb);) {
-        if (b < nb) {
+        const bool act = b < nb;
+        int n4 = 0;
+        // quiet: no slot of this lane can glitch anywhere in the coming (whole) segment, decided from the size of
+        // its deltas against the per-segment bound of k3_filter.cuh (k3_seg_bound). Lanes that sit this round out
+        // do not object. If the whole warp is quiet the segment runs without the per-iteration filter.
+        bool quiet = true;
+        if (act) {
           if (SCALED && (j & RENORM_MASK) == 0) {
 #pragma unroll
             for (int s = 0; s < P; ++s)
@@ -346,8 +375,19 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
                 dr[s] = ps.dr; di[s] = ps.di; sc[s] = ps.e; sm[s] = ps.e ? 0xffffffffu : 0u;
               }
           }
-          int n4 = 4 - ((j >> 2) & 3);   // blocks up to the next index = 0 (mod 16)
+          n4 = 4 - ((j >> 2) & 3);   // blocks up to the next index = 0 (mod 16)
           if (n4 > nb - b) n4 = nb - b;
+          if (K3F_QUIET && n4 == 4) {
+            const int thi = __ldg(&p.seg_hi[j >> 4]);
+#pragma unroll
+            for (int s = 0; s < P; ++s) {
+              const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
+              quiet = quiet & ((__double2hiint(dr[s]) & keep) < thi) & ((__double2hiint(di[s]) & keep) < thi);
+            }
+          } else quiet = false;
+        }
+        const bool warp_quiet = K3F_QUIET && __all_sync(FULL_MASK, quiet);
+        if (act) {
           const int j_ck = j;
 #pragma unroll
           for (int s = 0; s < P; ++s)
@@ -355,7 +395,11 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
           bool bad[P];
 #pragma unroll
           for (int s = 0; s < P; ++s) bad[s] = false;
-          if (n4 == 4) {   // the common case, straight-line: the sticky flags stay in predicate registers
+          if (warp_quiet) {   // n4 == 4 in every active lane
+#pragma unroll
+            for (int q = 0; q < 4; ++q) k3_block_quiet<P, SCALED>(dr, di, er, ei, S, sZ2, j - jbase + 4 * q);
+            j += 16;
+          } else if (n4 == 4) {   // straight-line: the sticky flags stay in predicate registers
 #pragma unroll
             for (int q = 0; q < 4; ++q) k3_block<P, SCALED>(dr, di, er, ei, S, sm, sZ2, sF, j - jbase + 4 * q, bad);
             j += 16;

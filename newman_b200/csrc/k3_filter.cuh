@@ -74,6 +74,66 @@ __host__ __device__ __forceinline__ void k3_filter_entry(double zr, double zi, d
   k3f_component(zi, g, &f->lo_i, &f->w_i);
 }
 
+// Quiet segments. k3_fast advances in segments of 16 iterations from indices j0 = 0 (mod 16). Whether the glitch
+// test can fire ANYWHERE in a segment is decided once, at its start, from the size of delta alone:
+//   the kernel's step  w = fl(2Z_j + delta), delta' = (fma(-di, wi, fma(dr, wr, er)), fma(di, wr, fma(dr, wi, ei)))
+//   is the complex delta*w + eps with |w| <= (2|Z_j| + |delta|)(1 + u) and a componentwise error of at most
+//   u|result| + u(1 + u)(|delta||w| + |eps|)  (u = 2^-53), so in 2-norms
+//       |delta'| <= (|delta| (2|Z_j| + |delta|) + |eps|)(1 + 2^-40)  (+ 1e-290 for results that underflow).
+//   A glitch at index k implies |Z_c + delta_c| < g_k = sqrt(gb_k)(1 + 2^-30) in both components (above), hence
+//   |delta_k| > |Z_k| - sqrt(2) g_k =: L_k. So with D_0 >= |delta_j0| and D_{i+1} = the bound above, no glitch is
+//   possible in the segment if D_i <= L_{j0+i} for i = 1..16. The bound is monotone in D_0; k3_seg_bound searches the
+//   largest high word T such that every state with hi(|dr|) < T and hi(|di|) < T (=> |delta| < sqrt(2) double(T, 0))
+//   and every |eps| <= e_max (the frame's largest pixel offset) passes. The kernel then runs such a segment without the
+//   per-iteration filter (6 FP64 instructions per iteration and nothing else). |delta w| = |delta||w| is exact for
+//   complex numbers, so the bound loses only the sqrt(2) of the component test: a segment is "loud" for a state only
+//   where its |delta| really comes within a small factor of some |Z_k| (an approach of the reference to 0, or the
+//   state's last iterations before it escapes).
+//   T = 0 (never quiet): a segment that reaches beyond the table, contains an entry the filter treats as "always a
+//   candidate" (gb < 2^-900 or max|Z_c| < 2^-100), or has L_k < 2^-160 somewhere. Scaled states (|delta| < 2^-170,
+//   see above) are therefore quiet exactly where T > 0; the kernel masks their high words to 0.
+//   gb_k == 0 (never a glitch) puts no constraint on D_k.
+__host__ __device__ __forceinline__ double k3f_from_hi(uint32_t hi) {
+  const uint64_t u = (uint64_t)hi << 32;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+
+// Z[j] = (zr[j], zi[j]) and gb[j] for j <= jmax (the last valid table index); e_max >= |eps| of every sample.
+__host__ __device__ inline int32_t k3_seg_bound(const double* zr, const double* zi, const double* gb, int zstride, int j0, int jmax,
+                                                double e_max) {
+  if (j0 + 16 > jmax || !(e_max >= 0.0)) return 0;
+  const double up = 1.0 + 9.094947017729282e-13;   // 2^-40
+  double g2[16], L[16];                              // 2|Z_{j0+i}| (rounded up), L_{j0+i+1}
+  for (int i = 0; i < 16; ++i) {
+    const double ar = zr[(size_t)(j0 + i) * zstride], ai = zi[(size_t)(j0 + i) * zstride];
+    g2[i] = 2.0 * sqrt(ar * ar + ai * ai) * up;
+    if (!(g2[i] < 1e300)) return 0;
+    const int k = j0 + i + 1;
+    const double kr = zr[(size_t)k * zstride], ki = zi[(size_t)k * zstride], b = gb[k];
+    if (!(b > 0.0)) { L[i] = 1e308; continue; }     // never a glitch at k
+    if (b < 1.1832913578315177e-271 || !(fmax(fabs(kr), fabs(ki)) >= 7.888609052210118e-31)) return 0;
+    const double l = sqrt(kr * kr + ki * ki) * (1.0 - 9.094947017729282e-13) - 1.4142135623730951 * sqrt(b) * (1.0 + 1.862645149230957e-09);
+    if (!(l >= 6.842277657836021e-49 /* 2^-160 */)) return 0;
+    L[i] = l;
+  }
+  uint32_t lo = 0u, hi = 0x7fe00001u;               // lo passes (or is the sentinel 0), hi fails
+  while (hi - lo > 1u) {
+    const uint32_t mid = lo + (hi - lo) / 2u;
+    double D = 1.4142135623730951 * k3f_from_hi(mid) * up;
+    bool ok = true;
+    for (int i = 0; i < 16 && ok; ++i) {
+      D = (D * (g2[i] + D) + e_max) * up + 1e-290;
+      ok = D <= L[i];                                // false for NaN / inf as well
+    }
+    if (ok) lo = mid; else hi = mid;
+  }
+  return (int32_t)lo;
+}
+
 // The tests as k3_fast evaluates them (scaled_mask: 0 for a plain state, 0xffffffff for a scaled one).
 __host__ __device__ __forceinline__ bool k3_filter_glitch(const K3Filt& f, double dr, double di, uint32_t scaled_mask) {
   const uint32_t a = (k3f_hi32(dr) - f.lo_r) | scaled_mask;

@@ -47,6 +47,7 @@ struct K3Params {
   const double2* Z2;     // k3_fast: 2*Z[j] (exact)
   const int4* filt;      // k3_fast: glitch-filter entries (k3_filter.cuh: K3Filt)
   const int32_t* esc_hi; // k3_fast: escape-filter high words
+  const int32_t* seg_hi; // k3_fast: per 16-iteration segment, the quiet bound on delta's high words (k3_seg_bound)
   int Jmax;              // last valid table index
   int N, CH, k;
   EpsTab eps;

@@ -70,7 +70,7 @@ struct nm_ctx {
   int paldev_n = 0;  // entries of the device-generated palette in paldev (0: none)
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
-  DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
+  DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
       rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
@@ -125,6 +125,45 @@ __global__ void k_glitch_bounds(const double2* Z, double* gb, int32_t* ghi, doub
   k3_filter_entry(z.x, z.y, v, &f, &e);
   filt[j] = f;
   esc_hi[j] = e;
+}
+
+// Largest pixel offset of the frame: |eps| <= sqrt(max|eps_re|^2 + max|eps_im|^2), rounded up (one CTA).
+__global__ void k_eps_max(EpsTab t, int nr, double* out) {
+  __shared__ double sh[2][32];
+  double mr = 0.0, mi = 0.0;
+  for (int i = threadIdx.x; i < t.nc; i += blockDim.x) {
+    double v = fabs(t.re[i]);
+    if (t.re_e) v = scalbn(v, t.re_e[i]);
+    mr = v > mr || v != v ? v : mr;
+  }
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+    double v = fabs(t.im[i]);
+    if (t.im_e) v = scalbn(v, t.im_e[i]);
+    mi = v > mi || v != v ? v : mi;
+  }
+  for (int o = 16; o; o >>= 1) {
+    const double a = __shfl_xor_sync(FULL_MASK, mr, o), b = __shfl_xor_sync(FULL_MASK, mi, o);
+    mr = a > mr || a != a ? a : mr;
+    mi = b > mi || b != b ? b : mi;
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = mr; sh[1][threadIdx.x >> 5] = mi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      const double a = sh[0][w], b = sh[1][w];
+      mr = a > mr || a != a ? a : mr;
+      mi = b > mi || b != b ? b : mi;
+    }
+    *out = sqrt(mr * mr + mi * mi) * (1.0 + 9.094947017729282e-13);   // NaN / inf => no segment is quiet
+  }
+}
+
+// k3_fast's per-segment quiet bounds (k3_filter.cuh: k3_seg_bound), one thread per segment of 16 orbit indices.
+__global__ void k_seg_bounds(const double2* Z, const double* gb, int jmax, const double* e_max, int32_t* seg_hi, int n_seg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const double* z = (const double*)Z;
+  seg_hi[s] = k3_seg_bound(z, z + 1, gb, 2, 16 * s, jmax, *e_max);
 }
 
 __global__ void k_apply_fixups(nm_escape* out, const int32_t* pix, const float* val, int n) {
@@ -356,6 +395,7 @@ int launch_deep(nm_ctx* ctx) {
   K3Params p;
   p.Z = ctx->Z.as<double2>(); p.ghi = ctx->ghi.as<int32_t>(); p.gb = ctx->gb.as<double>();
   p.Z2 = ctx->Z2.as<double2>(); p.filt = ctx->k3filt.as<int4>(); p.esc_hi = ctx->esc_hi.as<int32_t>();
+  p.seg_hi = ctx->seg_hi.as<int32_t>();
   p.Jmax = ctx->Jmax; p.N = ctx->N; p.CH = CH;
   p.eps = eps; p.nc = ctx->nc;
   p.fresh_ids = ctx->fresh.as<int32_t>();
@@ -629,7 +669,7 @@ void nm_destroy(nm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->own);
-  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi,
+  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->eps_max,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
                     &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
@@ -751,6 +791,8 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->Z2.ensure((size_t)(J1 + 8) * sizeof(double2)));
   NM_CUDA(ctx, ctx->k3filt.ensure((size_t)(J1 + 8) * sizeof(K3Filt)));
   NM_CUDA(ctx, ctx->esc_hi.ensure((size_t)(J1 + 8) * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->seg_hi.ensure((size_t)(J1 / 16 + 8) * sizeof(int32_t)));
+  NM_CUDA(ctx, ctx->eps_max.ensure(sizeof(double)));
   NM_CUDA(ctx, ctx->xlo.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->a.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->b.ensure((size_t)M * sizeof(double2)));
@@ -811,6 +853,18 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
                                                         pad_n, ctx->gtol, ctx->has_escape);
     NM_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches++;
+    // quiet bounds of k3_fast's segments: they depend on the orbit AND on the frame's largest pixel offset
+    EpsTab et;
+    et.re = ctx->cre.as<double>(); et.im = ctx->cim.as<double>(); et.nc = nc;
+    et.re_e = ctx->use_fe == 2 ? ctx->cre_e.as<int32_t>() : nullptr;
+    et.im_e = ctx->use_fe == 2 ? ctx->cim_e.as<int32_t>() : nullptr;
+    const int n_seg = J1 / 16 + 2;
+    k_eps_max<<<1, 1024, 0, s>>>(et, nr, ctx->eps_max.as<double>());
+    NM_CUDA(ctx, cudaGetLastError());
+    k_seg_bounds<<<(n_seg + 127) / 128, 128, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->Jmax, ctx->eps_max.as<double>(),
+                                                     ctx->seg_hi.as<int32_t>(), n_seg);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches += 2;
   }
   return NM_OK;
 }
@@ -1058,6 +1112,11 @@ void nm_k3_filter_entry(double zr, double zi, double gb, uint32_t entry[5]) {
   K3Filt f; int32_t e;
   k3_filter_entry(zr, zi, gb, &f, &e);
   entry[0] = f.lo_r; entry[1] = f.w_r; entry[2] = f.lo_i; entry[3] = f.w_i; entry[4] = (uint32_t)e;
+}
+
+int32_t nm_k3_seg_bound(const double* z, const double* gb, int j0, int jmax, double e_max) {
+  if (!z || !gb || j0 < 0) return 0;
+  return k3_seg_bound(z, z + 1, gb, 2, j0, jmax, e_max);
 }
 
 int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int scaled, int* glitch, int* escape) {

@@ -174,3 +174,141 @@ def test_scaled_step_uses_the_same_bounds():
     a = exact_tests(zr, zi, dr, di, gb)
     r, i = fl(Fr(1) * Fr(dr) + Fr(zr)), fl(Fr(1) * Fr(di) + Fr(zi))
     assert (r, i) == (zr + dr, zi + di) and a[0]
+
+
+# ---- quiet segments (k3_filter.cuh: k3_seg_bound) -------------------------------------------------------------------
+def hi_word(x):
+    return int(np.float64(abs(x)).view(np.uint64) >> np.uint64(32))
+
+
+def seg_bound(lib, z, gb, e_max, j0=0):
+    z = np.ascontiguousarray(z, np.float64)
+    gb = np.ascontiguousarray(gb, np.float64)
+    return lib.nm_k3_seg_bound(z.ctypes.data_as(C.POINTER(C.c_double)), gb.ctypes.data_as(C.POINTER(C.c_double)), j0,
+                               len(gb) - 1, e_max)
+
+
+def admissible(T, dr, di):
+    """The kernel's test at the start of a segment (plain state)."""
+    return hi_word(dr) < T and hi_word(di) < T
+
+
+def fast_step(zr, zi, dr, di, er, ei):
+    """One iteration exactly as k3_fast's quiet block computes it (k3_fast.cuh: k3_block_quiet, plain state)."""
+    wr, wi = 2.0 * zr + dr, 2.0 * zi + di               # DADD against the exact 2Z table
+    t = fl(Fr(dr) * Fr(wr) + Fr(er))
+    ndr = fl(Fr(-di) * Fr(wi) + Fr(t))
+    t = fl(Fr(dr) * Fr(wi) + Fr(ei))
+    ndi = fl(Fr(di) * Fr(wr) + Fr(t))
+    return ndr, ndi
+
+
+def random_orbit_piece(rng, n=18):
+    """n table entries of arbitrary size (the bound may not rely on Z being a Mandelbrot orbit)."""
+    style = rng.integers(0, 4)
+    if style == 0:
+        mag = 10.0 ** rng.uniform(-0.6, 0.3, n)
+    elif style == 1:
+        mag = 10.0 ** rng.uniform(-6, 0.3, n)
+    else:
+        mag = 10.0 ** rng.uniform(-0.5, 0.3, n)
+        mag[rng.integers(1, n)] = 10.0 ** rng.uniform(-14, -1)   # an approach to zero
+    th = rng.uniform(0, 2 * math.pi, n)
+    return np.stack([mag * np.cos(th), mag * np.sin(th)], 1)
+
+
+def test_quiet_bound_never_admits_a_glitching_state():
+    """Build a trajectory that DOES glitch at index k of the segment (Z_k is placed on -delta_k afterwards): the
+    bound computed from that table must reject the trajectory's start state."""
+    lib = newman_b200.load()
+    rng = np.random.default_rng(20261018)
+    hits = 0
+    for trial in range(6000):
+        z = random_orbit_piece(rng)
+        tol = float(rng.choice([1e-6, 1e-6, 1e-6, 1e-3, 1e-9, 0.01]))
+        k = int(rng.integers(1, 17))
+        e_max = 10.0 ** rng.uniform(-60, -3)
+        ea = rng.uniform(0, 2 * math.pi)
+        er, ei = e_max * math.cos(ea) * 0.999, e_max * math.sin(ea) * 0.999
+        # the start state: anything from far below eps to the size of Z
+        d0 = 10.0 ** rng.uniform(math.log10(e_max) - 3, 0.0)
+        da = rng.uniform(0, 2 * math.pi) if trial % 3 else rng.choice([0, 0.25, 0.5, 0.75, 1.0, 1.5]) * math.pi
+        dr0, di0 = d0 * math.cos(da), d0 * math.sin(da)
+        dr, di = dr0, di0
+        ok = True
+        for i in range(k):
+            dr, di = fast_step(z[i, 0], z[i, 1], dr, di, er, ei)
+            if not (math.isfinite(dr) and math.isfinite(di)) or max(abs(dr), abs(di)) > 1e3:
+                ok = False
+                break
+        if not ok or max(abs(dr), abs(di)) < 1e-90:
+            continue
+        # put Z_k inside the glitch disc around -delta_k: |Z_k + delta_k| = rad * sqrt(tol) * |Z_k|
+        rad = float(rng.choice([0.0, 0.3, 0.9, 0.999, 0.999999]))
+        ph = rng.uniform(0, 2 * math.pi)
+        m = math.hypot(dr, di)
+        z[k, 0] = -dr + rad * math.sqrt(tol) * m * math.cos(ph)
+        z[k, 1] = -di + rad * math.sqrt(tol) * m * math.sin(ph)
+        gb = np.array([glitch_bound(a, b, tol) for a, b in z])
+        gb[0] = 0.0
+        gl, _ = exact_tests(z[k, 0], z[k, 1], dr, di, gb[k])
+        if not gl:
+            continue
+        hits += 1
+        T = seg_bound(lib, z, gb, e_max)
+        assert not admissible(T, dr0, di0), ("glitch inside a quiet segment", trial, k, T, dr0, di0, z.tolist(), tol, e_max)
+    assert hits > 3000
+
+
+def test_quiet_bound_largest_admissible_states_do_not_glitch():
+    """The other direction: the largest states the bound admits (high words T - 1, all-ones low words, every sign
+    pattern, eps of full size in the worst directions) are iterated through the segment with the kernel's arithmetic;
+    the exact glitch test may fire nowhere."""
+    lib = newman_b200.load()
+    rng = np.random.default_rng(5)
+    checked = 0
+    for trial in range(1500):
+        z = random_orbit_piece(rng)
+        tol = float(rng.choice([1e-6, 1e-6, 1e-3, 1e-9]))
+        gb = np.array([glitch_bound(a, b, tol) for a, b in z])
+        gb[0] = 0.0
+        e_max = 10.0 ** rng.uniform(-60, -2)
+        T = seg_bound(lib, z, gb, e_max)
+        if T <= 0:
+            continue
+        top = float(np.uint64((T - 1) << 32 | 0xffffffff).view(np.float64))
+        for sr, si in ((1, 1), (1, -1), (-1, 1), (-1, -1), (1, 0), (0, -1)):
+            dr, di = sr * top, si * top
+            ea = rng.uniform(0, 2 * math.pi)
+            er, ei = e_max * math.cos(ea) * 0.9999, e_max * math.sin(ea) * 0.9999
+            for i in range(16):
+                dr, di = fast_step(z[i, 0], z[i, 1], dr, di, er, ei)
+                gl, _ = exact_tests(z[i + 1, 0], z[i + 1, 1], dr, di, gb[i + 1])
+                assert not gl, ("admitted state glitches", trial, i, T, z.tolist(), tol, e_max)
+            checked += 1
+    assert checked > 3000
+
+
+def test_quiet_bound_is_useful_and_degenerates_safely():
+    lib = newman_b200.load()
+    # an ordinary stretch of orbit (|Z| around 1, growth ~2 per step) admits deltas up to ~1e-6
+    n = 40
+    z = np.stack([np.full(n, 0.7), np.full(n, -0.6)], 1)
+    gb = np.array([glitch_bound(a, b, 1e-6) for a, b in z]); gb[0] = 0.0
+    T = seg_bound(lib, z, gb, 1e-52, j0=16)
+    lim = float(np.uint64(T << 32).view(np.float64))
+    assert 1e-7 < lim < 1e-3, lim
+    # pixel offsets of the size of Z: nothing is quiet
+    assert seg_bound(lib, z, gb, 1.0, j0=16) == 0
+    # a segment that reaches beyond the table
+    assert seg_bound(lib, z, gb, 1e-52, j0=32) == 0 and seg_bound(lib, z[:33], gb[:33], 1e-52, j0=16) > 0
+    # an "always a candidate" entry (tiny reference iterate) inside the segment
+    z2 = z.copy(); z2[20] = (1e-120, 1e-121)
+    gb2 = np.array([glitch_bound(a, b, 1e-6) for a, b in z2]); gb2[0] = 0.0
+    assert seg_bound(lib, z2, gb2, 1e-52, j0=16) == 0 and seg_bound(lib, z2, gb2, 1e-52, j0=0) > 0
+    # gb == 0 entries (index 0, the escaped iterate) constrain nothing
+    z3 = z.copy(); z3[32] = (1500.0, 200.0)
+    gb3 = gb.copy(); gb3[32] = 0.0
+    assert seg_bound(lib, z3, gb3, 1e-52, j0=16) >= T   # (the last index was the binding one: the bound relaxes)
+    # NaN / inf offsets
+    assert seg_bound(lib, z, gb, math.nan, j0=16) == 0 and seg_bound(lib, z, gb, math.inf, j0=16) == 0
