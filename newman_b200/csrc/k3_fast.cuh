@@ -326,6 +326,36 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
 
     // ---- one warp-synchronous pass through the chunk -----------------------------------------------
     const int j_in = j;  // every slot of this lane's group entered at this index
+    // The largest high word (sign and, for a scaled slot, everything masked off) among the lane's deltas: what both
+    // per-segment decisions look at — "could a slot have escaped" (>= the escape word of the index reached) and "is
+    // the lane quiet in the coming segment" (< the segment's bound). Exact when computed (here, after a
+    // re-normalisation, at every segment end); in between it can only be too high (exported slots are zeroed),
+    // which errs on the loud side.
+    auto hi_max = [&]() {
+      int m = 0;
+#pragma unroll
+      for (int s = 0; s < P; ++s) {
+        const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
+        m = max(m, max(__double2hiint(dr[s]) & keep, __double2hiint(di[s]) & keep));
+      }
+      return m;
+    };
+    // Segment end: export (checkpoint state, index j_ck) every live slot whose sticky glitch flag is set or whose
+    // last delta passes the escape filter. slots.ck already holds the state to hand over.
+    auto export_flagged = [&](const bool (&bad)[P], int esc_hi, int j_ck) {
+#pragma unroll
+      for (int s = 0; s < P; ++s) {
+        const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
+        const bool flagged = bad[s] | ((__double2hiint(dr[s]) & keep) >= esc_hi) | ((__double2hiint(di[s]) & keep) >= esc_hi);
+        if ((live & (1u << s)) && flagged) {
+          live &= ~(1u << s); expo |= 1u << s;
+          slots.evj[s * K3F_THREADS + tid] = j_ck;
+          executed += (unsigned long long)(j_ck - j_in);
+          dr[s] = di[s] = er[s] = ei[s] = 0.0;
+        }
+      }
+    };
+    int m_hi = hi_max();
     for (;;) {
       // Export the live slots that cannot take another whole block before the chunk end / table end /
       // their iteration limit — unless they simply reached the chunk end with room beyond it: those
@@ -374,17 +404,11 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
                 }
                 dr[s] = ps.dr; di[s] = ps.di; sc[s] = ps.e; sm[s] = ps.e ? 0xffffffffu : 0u;
               }
+            m_hi = hi_max();
           }
           n4 = 4 - ((j >> 2) & 3);   // blocks up to the next index = 0 (mod 16)
           if (n4 > nb - b) n4 = nb - b;
-          if (K3F_QUIET && n4 == 4) {
-            const int thi = __ldg(&p.seg_hi[j >> 4]);
-#pragma unroll
-            for (int s = 0; s < P; ++s) {
-              const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
-              quiet = quiet & ((__double2hiint(dr[s]) & keep) < thi) & ((__double2hiint(di[s]) & keep) < thi);
-            }
-          } else quiet = false;
+          quiet = K3F_QUIET && n4 == 4 && m_hi < __ldg(&p.seg_hi[j >> 4]);
         }
         const bool warp_quiet = K3F_QUIET && __all_sync(FULL_MASK, quiet);
         if (act) {
@@ -392,41 +416,40 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
 #pragma unroll
           for (int s = 0; s < P; ++s)
             if (live & (1u << s)) slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
-          bool bad[P];
-#pragma unroll
-          for (int s = 0; s < P; ++s) bad[s] = false;
-          if (warp_quiet) {   // n4 == 4 in every active lane
+          if (warp_quiet) {   // n4 == 4 in every active lane; no glitch flag can be set
 #pragma unroll
             for (int q = 0; q < 4; ++q) k3_block_quiet<P, SCALED>(dr, di, er, ei, S, sZ2, j - jbase + 4 * q);
             j += 16;
-          } else if (n4 == 4) {   // straight-line: the sticky flags stay in predicate registers
+            b += 4;
+            m_hi = hi_max();
+            const int esc_hi = sE[j - jbase];   // k3_filter_escape on the segment's last delta
+            if (m_hi >= esc_hi) {
+              bool none[P];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) k3_block<P, SCALED>(dr, di, er, ei, S, sm, sZ2, sF, j - jbase + 4 * q, bad);
-            j += 16;
-          } else {
-            for (int q = 0; q < n4; ++q) {
-              k3_block<P, SCALED>(dr, di, er, ei, S, sm, sZ2, sF, j - jbase, bad);
-              j += 4;
+              for (int s = 0; s < P; ++s) none[s] = false;
+              export_flagged(none, esc_hi, j_ck);
             }
-          }
-          b += n4;
-          const int esc_hi = sE[j - jbase];   // k3_filter_escape on the segment's last delta
-          bool any_bad = false;
+          } else {
+            bool bad[P];
 #pragma unroll
-          for (int s = 0; s < P; ++s) {
-            const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
-            bad[s] = bad[s] | ((__double2hiint(dr[s]) & keep) >= esc_hi) | ((__double2hiint(di[s]) & keep) >= esc_hi);
-            any_bad = any_bad | bad[s];
-          }
-          if (any_bad) {
+            for (int s = 0; s < P; ++s) bad[s] = false;
+            if (n4 == 4) {   // straight-line: the sticky flags stay in predicate registers
 #pragma unroll
-            for (int s = 0; s < P; ++s)
-              if ((live & (1u << s)) && bad[s]) {
-                live &= ~(1u << s); expo |= 1u << s;   // slots.ck already holds the state to hand over
-                slots.evj[s * K3F_THREADS + tid] = j_ck;
-                executed += (unsigned long long)(j_ck - j_in);
-                dr[s] = di[s] = er[s] = ei[s] = 0.0;
+              for (int q = 0; q < 4; ++q) k3_block<P, SCALED>(dr, di, er, ei, S, sm, sZ2, sF, j - jbase + 4 * q, bad);
+              j += 16;
+            } else {
+              for (int q = 0; q < n4; ++q) {
+                k3_block<P, SCALED>(dr, di, er, ei, S, sm, sZ2, sF, j - jbase, bad);
+                j += 4;
               }
+            }
+            b += n4;
+            m_hi = hi_max();
+            const int esc_hi = sE[j - jbase];
+            bool any_bad = m_hi >= esc_hi;
+#pragma unroll
+            for (int s = 0; s < P; ++s) any_bad = any_bad | bad[s];
+            if (any_bad) export_flagged(bad, esc_hi, j_ck);
           }
         }
       }
