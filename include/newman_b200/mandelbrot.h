@@ -23,6 +23,12 @@
 #include <memory>
 #include <vector>
 
+// The classes below are implemented in libnewman_b200.so, which is otherwise built with hidden visibility: a C++
+// caller (the reference's viewer.o, video.o) links against the library and finds exactly these.
+#ifndef NEWMAN_B200_CXX_API
+#define NEWMAN_B200_CXX_API __attribute__((visibility("default")))
+#endif
+
 // ---- value types (complex.h) ------------------------------------------------------------------
 struct LPComplex {
   double re, im;
@@ -73,7 +79,7 @@ struct FrameInfo {
 };
 }  // namespace newman_b200
 
-class Mandelbrot {
+class NEWMAN_B200_CXX_API Mandelbrot {
 protected:
   RenderGrid grid;
   std::shared_ptr<newman_b200::Engine> engine_;

@@ -12,6 +12,10 @@
 
 #include <vector>
 
+#ifndef NEWMAN_B200_CXX_API
+#define NEWMAN_B200_CXX_API __attribute__((visibility("default")))   // exported from libnewman_b200.so (see mandelbrot.h)
+#endif
+
 #ifdef NEWMAN_B200_HAVE_BYTEIMAGE
 #include <byteimage/palette.h>
 using byteimage::CachedPalette;
@@ -33,20 +37,20 @@ public:
   const Color& operator[](int i) const { return c_[i]; }
   const unsigned char* bytes() const { return c_.empty() ? nullptr : &c_[0].r; }  // 3*size(), r g b r g b ...
 };
-void hsl2rgb(float h_deg, float s, float l, unsigned char& r, unsigned char& g, unsigned char& b);
-Color interp(const Color& a, const Color& b, float t);
+NEWMAN_B200_CXX_API void hsl2rgb(float h_deg, float s, float l, unsigned char& r, unsigned char& g, unsigned char& b);
+NEWMAN_B200_CXX_API Color interp(const Color& a, const Color& b, float t);
 }  // namespace byteimage
 using byteimage::CachedPalette;
 #endif
 
-class MultiWaveGenerator {
+class NEWMAN_B200_CXX_API MultiWaveGenerator {
 public:
-  struct FloatCycle {  // piecewise-linear cyclic table (multiwave.cpp:5-12)
+  struct NEWMAN_B200_CXX_API FloatCycle {  // piecewise-linear cyclic table (multiwave.cpp:5-12)
     std::vector<float> values;
     int period = 1;
     float value(int step) const;
   };
-  struct FloatWave {   // amplitude * sin(step * tau / period) (multiwave.cpp:14-17)
+  struct NEWMAN_B200_CXX_API FloatWave {   // amplitude * sin(step * tau / period) (multiwave.cpp:14-17)
     float amplitude = 1.0f;
     int period = 1;
     float value(int step) const;
