@@ -2,7 +2,10 @@
 #include "hp_host.h"
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 #include "../../include/newman_b200.h"
@@ -237,13 +240,12 @@ void find_probe(const ViewHP& v, int threads, int& row, int& col, int& length) {
   length = len[best];
 }
 
-void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out) {
+// Orbit and series one after the other on the calling thread (host_threads == 1, and the cross-check of the
+// pipelined form below). Leaves X[0] in x0re / x0im.
+static void tables_serial(const ViewHP& v, mpf_srcptr x0re_in, mpf_srcptr x0im_in, DeepTablesHost& out) {
   const mp_bitcnt_t P = v.prec;
-  out.probe_row = row;
-  out.probe_col = col;
-  Mp tmp(P), x0re(P), x0im(P);
-  pixel_re(v, col, tmp.v, x0re.v);
-  pixel_im(v, row, tmp.v, x0im.v);
+  Mp x0re(P), x0im(P);
+  mpf_set(x0re.v, x0re_in); mpf_set(x0im.v, x0im_in);
 
   // ---- computeOrbit (mandelbrot.cpp:97-110), keeping the escaped iterate the reference drops ----
   struct Pair { mpf_t re, im; };
@@ -342,6 +344,220 @@ void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out) {
       store(i);
     }
   }
+  for (auto& x : X) { mpf_clear(x.re); mpf_clear(x.im); }
+}
+
+// The same tables from a 4-stage pipeline: the orbit X and the three coefficient recurrences each on their own thread.
+// A[i] needs X[i-1] and A[i-1]; B[i] needs X[i-1], B[i-1] and the NEW A[i]; C[i] needs X[i-1], C[i-1] and the new
+// A[i], B[i] (mandelbrot.cpp:118-128) — so stage S at index i only waits for stage S-1 at index i. Every stage issues
+// exactly the mpf operations of tables_serial, in the same order, on private temporaries: the tables are bit-identical
+// (tests/test_host_tables.py compares the two forms and both with the compiled reference). Per index the stages cost
+// 3 / 6 / 9 / 10 multiplications, so the pipeline runs at the pace of C: ~2.8x faster than the serial form, which is what
+// a frame at 1e-400 (M = 5e5 at 1344 bits: 5 s per reference) spends most of its host time in.
+namespace {
+
+struct HpPair { mpf_t re, im; };
+
+// Values a stage publishes for the next ones. Blocks of 4096 entries hang off a pointer table of fixed size, so a
+// reader never sees storage move; `ready` = entries published (release / acquire).
+struct HpStream {
+  static const int kBlock = 4096;
+  static const long kBatch = 32;        // entries per publication: the counter's cache line changes hands rarely
+  std::vector<HpPair*> blocks;
+  std::vector<mp_limb_t*> limbs;        // one limb pool per block (an mpf_init2 per entry would be a malloc per entry)
+  int prec_limbs;                        // _mp_prec of an mpf at the stream's precision
+  alignas(64) std::atomic<long> ready;
+  std::atomic<bool> finished;
+  alignas(64) long allocated;           // producer's side
+  alignas(64) long seen;                // consumer-side copies of `ready` live in the consumers
+  HpStream(long max_entries, mp_bitcnt_t p)
+      : blocks((size_t)(max_entries / kBlock + 2), nullptr), limbs((size_t)(max_entries / kBlock + 2), nullptr), ready(0),
+        finished(false), allocated(0), seen(0) {
+    mpf_t t;
+    mpf_init2(t, p);
+    prec_limbs = t->_mp_prec;            // what mpf_init2 derives from the bit count
+    mpf_clear(t);
+  }
+  ~HpStream() {
+    for (HpPair* b : blocks) delete[] b;
+    for (mp_limb_t* l : limbs) delete[] l;
+  }
+  HpPair& at(long i) { return blocks[(size_t)(i / kBlock)][i % kBlock]; }
+  // producer only: a fresh entry (value 0) laid out like mpf_init2 does it — prec + 1 limbs — inside the block's pool;
+  // such an entry is assigned with mpf_set and never passed to mpf_clear / mpf_set_prec
+  HpPair& append() {
+    const long i = allocated++;
+    const size_t bi = (size_t)(i / kBlock);
+    const size_t per = (size_t)prec_limbs + 1;
+    if (i % kBlock == 0) {
+      blocks[bi] = new HpPair[kBlock];
+      limbs[bi] = new mp_limb_t[2 * per * kBlock];
+    }
+    HpPair& q = at(i);
+    mp_limb_t* base = limbs[bi] + 2 * per * (size_t)(i % kBlock);
+    q.re->_mp_prec = prec_limbs; q.re->_mp_size = 0; q.re->_mp_exp = 0; q.re->_mp_d = base;
+    q.im->_mp_prec = prec_limbs; q.im->_mp_size = 0; q.im->_mp_exp = 0; q.im->_mp_d = base + per;
+    return q;
+  }
+  void publish(bool force = false) {
+    if (force || allocated - ready.load(std::memory_order_relaxed) >= kBatch) ready.store(allocated, std::memory_order_release);
+  }
+  void finish() {
+    ready.store(allocated, std::memory_order_release);
+    finished.store(true, std::memory_order_release);
+  }
+  // true once entry i is there; false if the producer finished without it. `have` is the caller's cached copy of
+  // `ready`: the shared counter is only read when the consumer has caught up with what it last saw.
+  bool wait_for(long i, long& have) {
+    if (i < have) return true;
+    for (int spin = 0;; ++spin) {
+      have = ready.load(std::memory_order_acquire);
+      if (have > i) return true;
+      if (finished.load(std::memory_order_acquire)) {
+        have = ready.load(std::memory_order_acquire);
+        return have > i;
+      }
+      if (spin > 256) std::this_thread::yield();
+    }
+  }
+};
+
+struct CoefOut {  // one coefficient's descended tables
+  std::vector<double>* d; std::vector<double>* m; std::vector<int32_t>* e;
+  void push(mpf_srcptr re, mpf_srcptr im) {
+    long ex = 0;
+    d->push_back(mpf_get_d(re)); d->push_back(mpf_get_d(im));
+    m->push_back(mpf_get_d_2exp(&ex, re)); e->push_back((int32_t)ex);
+    m->push_back(mpf_get_d_2exp(&ex, im)); e->push_back((int32_t)ex);
+  }
+};
+
+}  // namespace
+
+static void tables_pipelined(const ViewHP& v, mpf_srcptr x0re, mpf_srcptr x0im, DeepTablesHost& out) {
+  const mp_bitcnt_t P = v.prec;
+  // X holds the non-escaped iterates only (what the series reads); A and B hold the new coefficients of index i at
+  // entry i - 1 (index 0 is the constant start value)
+  HpStream X(v.N, P), A(v.N, P), B(v.N, P);
+  out.a.clear(); out.b.clear(); out.c.clear(); out.a_m.clear(); out.b_m.clear(); out.c_m.clear();
+  out.a_e.clear(); out.b_e.clear(); out.c_e.clear(); out.x_hi.clear(); out.x_lo.clear();
+  out.has_escape = false;
+
+  std::thread tA([&]() {
+    Mp ar(P), ai(P), nar(P), nai(P), p1(P), p2(P), s(P), u(P), two(64), one(64);
+    mpf_set_d(two.v, 2.0); mpf_set_d(one.v, 1.0); mpf_set_d(ar.v, 1.0);
+    CoefOut o = {&out.a, &out.a_m, &out.a_e};
+    long have_x = 0;
+    if (X.wait_for(0, have_x)) o.push(ar.v, ai.v);
+    for (long i = 1; X.wait_for(i, have_x); i++) {   // index i exists iff X[i] is a non-escaped iterate
+      mpf_srcptr xr = X.at(i - 1).re, xi = X.at(i - 1).im;
+      mpf_mul(p1.v, xr, ar.v); mpf_mul(p2.v, xi, ai.v); mpf_sub(s.v, p1.v, p2.v);
+      mpf_mul(u.v, two.v, s.v); mpf_add(nar.v, u.v, one.v);
+      mpf_mul(p1.v, xr, ai.v); mpf_mul(p2.v, xi, ar.v); mpf_add(s.v, p1.v, p2.v);
+      mpf_mul(nai.v, two.v, s.v);
+      mpf_swap(ar.v, nar.v); mpf_swap(ai.v, nai.v);
+      HpPair& q = A.append();
+      mpf_set(q.re, ar.v); mpf_set(q.im, ai.v);
+      A.publish();
+      o.push(ar.v, ai.v);
+    }
+    A.finish();
+  });
+  std::thread tB([&]() {
+    Mp br(P), bi(P), nbr(P), nbi(P), p1(P), p2(P), s(P), u(P), two(64);
+    mpf_set_d(two.v, 2.0);
+    CoefOut o = {&out.b, &out.b_m, &out.b_e};
+    long have_x = 0, have_a = 0;
+    if (X.wait_for(0, have_x)) o.push(br.v, bi.v);
+    for (long i = 1; A.wait_for(i - 1, have_a); i++) {
+      mpf_srcptr xr = X.at(i - 1).re, xi = X.at(i - 1).im, nar = A.at(i - 1).re, nai = A.at(i - 1).im;
+      mpf_mul(p1.v, xr, br.v); mpf_mul(p2.v, xi, bi.v); mpf_sub(s.v, p1.v, p2.v);
+      mpf_mul(u.v, two.v, s.v);
+      mpf_mul(p1.v, nar, nar); mpf_add(s.v, u.v, p1.v);
+      mpf_mul(p2.v, nai, nai); mpf_sub(nbr.v, s.v, p2.v);
+      mpf_mul(p1.v, xr, bi.v); mpf_mul(p2.v, xi, br.v); mpf_add(s.v, p1.v, p2.v);
+      mpf_mul(p1.v, nar, nai); mpf_add(u.v, s.v, p1.v);
+      mpf_mul(nbi.v, two.v, u.v);
+      mpf_swap(br.v, nbr.v); mpf_swap(bi.v, nbi.v);
+      HpPair& q = B.append();
+      mpf_set(q.re, br.v); mpf_set(q.im, bi.v);
+      B.publish();
+      o.push(br.v, bi.v);
+    }
+    B.finish();
+  });
+  std::thread tC([&]() {
+    Mp cr(P), ci(P), ncr(P), nci(P), p1(P), p2(P), s(P), u(P), two(64);
+    mpf_set_d(two.v, 2.0);
+    CoefOut o = {&out.c, &out.c_m, &out.c_e};
+    long have_x = 0, have_b = 0;
+    if (X.wait_for(0, have_x)) o.push(cr.v, ci.v);
+    for (long i = 1; B.wait_for(i - 1, have_b); i++) {
+      mpf_srcptr xr = X.at(i - 1).re, xi = X.at(i - 1).im, nar = A.at(i - 1).re, nai = A.at(i - 1).im;
+      mpf_srcptr nbr = B.at(i - 1).re, nbi = B.at(i - 1).im;
+      mpf_mul(p1.v, xr, cr.v); mpf_mul(p2.v, xi, ci.v); mpf_sub(s.v, p1.v, p2.v);
+      mpf_mul(p1.v, nar, nbr); mpf_add(u.v, s.v, p1.v);
+      mpf_mul(p2.v, nai, nbi); mpf_sub(s.v, u.v, p2.v);
+      mpf_mul(ncr.v, two.v, s.v);
+      mpf_mul(p1.v, xr, ci.v); mpf_mul(p2.v, xi, cr.v); mpf_add(s.v, p1.v, p2.v);
+      mpf_mul(p1.v, nar, nbi); mpf_add(u.v, s.v, p1.v);
+      mpf_mul(p2.v, nai, nbr); mpf_add(s.v, u.v, p2.v);
+      mpf_mul(nci.v, two.v, s.v);
+      mpf_swap(cr.v, ncr.v); mpf_swap(ci.v, nci.v);
+      o.push(cr.v, ci.v);
+    }
+  });
+
+  // ---- stage X on the calling thread: computeOrbit + the descended hi / lo parts as it goes -------
+  {
+    OrbitStep step(P);
+    Mp nre(P), nim(P), d64(64), rem(P);
+    auto descend_pair = [&](mpf_srcptr re, mpf_srcptr im, bool with_lo) {
+      const double hr = mpf_get_d(re), hi = mpf_get_d(im);
+      out.x_hi.push_back(hr); out.x_hi.push_back(hi);
+      if (with_lo) {
+        mpf_set_d(d64.v, hr); mpf_sub(rem.v, re, d64.v); out.x_lo.push_back(mpf_get_d(rem.v));
+        mpf_set_d(d64.v, hi); mpf_sub(rem.v, im, d64.v); out.x_lo.push_back(mpf_get_d(rem.v));
+      }
+    };
+    HpPair& q0 = X.append();
+    mpf_set(q0.re, x0re); mpf_set(q0.im, x0im);
+    descend_pair(q0.re, q0.im, true);
+    X.publish(true);
+    for (int i = 1; i < v.N; i++) {
+      HpPair& prev = X.at(i - 1);
+      step(nre.v, nim.v, prev.re, prev.im, x0re, x0im);
+      if (bailed(nre.v, nim.v)) {   // the escaped iterate: kept in x_hi only (the reference drops it)
+        out.has_escape = true;
+        descend_pair(nre.v, nim.v, false);
+        break;
+      }
+      HpPair& q = X.append();
+      mpf_set(q.re, nre.v); mpf_set(q.im, nim.v);
+      descend_pair(q.re, q.im, true);
+      X.publish();
+    }
+    X.finish();
+  }
+  tA.join(); tB.join(); tC.join();
+  out.M = (int)X.allocated;
+}
+
+void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out, int threads) {
+  const mp_bitcnt_t P = v.prec;
+  out.probe_row = row;
+  out.probe_col = col;
+  Mp tmp(P), x0re(P), x0im(P);
+  pixel_re(v, col, tmp.v, x0re.v);
+  pixel_im(v, row, tmp.v, x0im.v);
+  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+  static const bool debug = getenv("NM_DEBUG_TABLES") != nullptr;   // NM_DEBUG_TABLES=1: time of orbit + series per call
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  if (threads >= 4) tables_pipelined(v, x0re.v, x0im.v, out);
+  else tables_serial(v, x0re.v, x0im.v, out);
+  if (debug)
+    fprintf(stderr, "nm build_tables: M %d, %d bits, %s: %.3f s\n", out.M, (int)P, threads >= 4 ? "pipelined" : "serial",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   out.finite = true;
   for (size_t i = 0; i < out.a.size() && out.finite; i++)
     if (!std::isfinite(out.a[i]) || !std::isfinite(out.b[i]) || !std::isfinite(out.c[i])) out.finite = false;
@@ -354,20 +570,19 @@ void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out) {
     long ex = 0;
     for (int c = 0; c < v.nc; c++) {
       pixel_re(v, c, tmp.v, p.v);
-      mpf_sub(y.v, p.v, X[0].re);
+      mpf_sub(y.v, p.v, x0re.v);
       out.eps_re[c] = mpf_get_d(y.v);
       out.eps_re_m[c] = mpf_get_d_2exp(&ex, y.v); out.eps_re_e[c] = (int32_t)ex;
     }
     for (int r = 0; r < v.nr; r++) {
       pixel_im(v, r, tmp.v, p.v);
-      mpf_sub(y.v, p.v, X[0].im);
+      mpf_sub(y.v, p.v, x0im.v);
       out.eps_im[r] = mpf_get_d(y.v);
       out.eps_im_m[r] = mpf_get_d_2exp(&ex, y.v); out.eps_im_e[r] = (int32_t)ex;
     }
     mpf_get_d_2exp(&ex, v.sz_re);
     out.pitch_exp = (int)ex;
   }
-  for (auto& x : X) { mpf_clear(x.re); mpf_clear(x.im); }
 }
 
 }  // namespace newman_b200

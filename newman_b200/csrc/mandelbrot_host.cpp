@@ -60,6 +60,7 @@ mp_bitcnt_t max_prec(const HPComplex& a, const HPComplex& b) {
 struct RoundParams {
   int N, max_secondary, force_floatexp;
   double tol, gtol;
+  int host_threads;   // build_tables: 4 or more (0 = all cores) pipelines orbit and series
 };
 
 // One reference after another until no sample is left glitched: the frame (or the listed samples)
@@ -113,7 +114,7 @@ void run_rounds(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp
     for (size_t i = 1; i < rq_pix.size(); i++)
       if (rq_iter[i] < rq_iter[best] || (rq_iter[i] == rq_iter[best] && rq_pix[i] < rq_pix[best])) best = i;
     const double t_hp = now_s();
-    newman_b200::build_tables(v, rq_pix[best] / v.nc, rq_pix[best] % v.nc, T);
+    newman_b200::build_tables(v, rq_pix[best] / v.nc, rq_pix[best] % v.nc, T, rp.host_threads);
     info.host_precompute_s += now_s() - t_hp;
     cmode = NM_CARDIOID_NONE;  // listed samples already passed the cardioid test
     round++;
@@ -143,7 +144,7 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
 
   DeepTablesHost T;
-  newman_b200::build_tables(v, v.nr / 2, v.nc / 2, T);
+  newman_b200::build_tables(v, v.nr / 2, v.nc / 2, T, threads);
   newman_b200::FrameInfo scratch;
   // orbit lengths are wanted, not the user's speed/accuracy trade-off: never a looser series tolerance
   // than the reference's default (mandelbrot.cpp:9)
@@ -327,18 +328,18 @@ void Mandelbrot::renderFrame() {
       // every sample returns (N, 0) at mandelbrot.cpp:149-153: no probe search, a one-entry orbit
       ViewHP v1 = v;
       v1.N = 1;
-      newman_b200::build_tables(v1, v.nr / 2, v.nc / 2, T);
+      newman_b200::build_tables(v1, v.nr / 2, v.nc / 2, T, 1);
     } else {
       int prow, pcol, plen;
-      RoundParams rp0 = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance};
+      RoundParams rp0 = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance, host_threads};
       if (probe_search == 0) newman_b200::find_probe(v, host_threads, prow, pcol, plen);
       else find_probe_assisted(eng, v, rp0, host_threads, cmode, mask, prow, pcol, plen, nullptr, info_);
-      newman_b200::build_tables(v, prow, pcol, T);
+      newman_b200::build_tables(v, prow, pcol, T, host_threads);
     }
     info_.orbit_len = T.M; info_.probe_row = T.probe_row; info_.probe_col = T.probe_col;
     info_.host_precompute_s = now_s() - t_begin;
     info_.references = 0;
-    RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance};
+    RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance, host_threads};
     run_rounds(eng, v, rp, T, cmode, mask, nullptr, info_);
     eng.check(nm_read_rows(ctx, 0, v.nr, out), "nm_read_rows");
   }
@@ -366,7 +367,7 @@ void Mandelbrot::findProbe(int& row, int& col, int& length, int* n_exact) {
   if (!engine_ || engine_->device != device) engine_ = std::make_shared<newman_b200::Engine>(device);
   std::vector<uint8_t> mask;
   int cmode = newman_b200::classify_cardioid(v, host_threads, mask);
-  RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance};
+  RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance, host_threads};
   newman_b200::FrameInfo scratch;
   find_probe_assisted(*engine_, v, rp, host_threads, cmode, mask, row, col, length, n_exact, scratch);
   rendered_.reset();  // the device raster now holds the candidates, not a frame

@@ -220,7 +220,7 @@ int nmv_host_tables(nmv_view* v, int row, int col, int* has_escape, int* probe_r
       int len;
       newman_b200::find_probe(h, v->m.host_threads, row, col, len);
     }
-    newman_b200::build_tables(h, row, col, v->tabs);
+    newman_b200::build_tables(h, row, col, v->tabs, v->m.host_threads);
     if (has_escape) *has_escape = v->tabs.has_escape ? 1 : 0;
     if (probe_row) *probe_row = row;
     if (probe_col) *probe_col = col;

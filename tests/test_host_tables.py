@@ -162,3 +162,44 @@ def test_view_transforms_match_reference(tmp_path):
     m6.zoom(1e30)  # enough precision to parse the file (the reference's loader has the same caveat)
     m6.loadLegacy(fn2)
     assert m6.view_strings() == m5.view_strings()
+
+
+ALL_TABLES = ("x_hi", "x_lo", "a", "b", "c", "a_m", "a_e", "b_m", "b_e", "c_m", "c_e", "eps_re", "eps_im", "eps_re_m",
+              "eps_re_e", "eps_im_m", "eps_im_e")
+
+
+def same_tables(h1, h4):
+    assert (h1["M"], h1["has_escape"], h1["finite"]) == (h4["M"], h4["has_escape"], h4["finite"])
+    for n in ALL_TABLES:
+        a, b = np.ascontiguousarray(h1[n]), np.ascontiguousarray(h4[n])
+        assert a.shape == b.shape and a.tobytes() == b.tobytes(), n
+
+
+@pytest.mark.parametrize("name,scale", [("cfg2", 40), ("cfg3", 80)])
+def test_pipelined_tables_equal_serial_tables(name, scale):
+    """build_tables with 4+ host threads runs orbit, A, B, C as a pipeline (hp_host.cpp: tables_pipelined); it must
+    deliver what the one-thread form does, bit for bit — the long orbits of the bench views, double and
+    mantissa/exponent forms."""
+    from newman_b200 import workloads
+    cfg = workloads.config(name, scale=scale)
+    hs = []
+    for threads in (1, 4):
+        v = newman_b200.Mandelbrot(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"],
+                                   host_threads=threads)
+        hs.append(v.host_tables(cfg["nr"] // 2, cfg["nc"] // 2))
+    assert hs[0]["M"] > 50000
+    same_tables(*hs)
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 33, 4097, 9000])
+def test_pipelined_tables_edge_lengths(N):
+    """Orbits that never escape (M == N: a reference inside the main cardioid, lengths around the pipeline's block
+    and batch sizes) and ones that escape at once."""
+    for center in (("-0.1", "0.05"), ("0.4", "0.3"), ("2.5", "0.0")):
+        hs = []
+        for threads in (1, 4):
+            v = newman_b200.Mandelbrot(12, 16, N=N, sz=("1e-30", "1e-30"), center=center, host_threads=threads)
+            hs.append(v.host_tables(6, 8))
+        same_tables(*hs)
+        if center[0] == "-0.1":
+            assert hs[0]["M"] == N and not hs[0]["has_escape"]
