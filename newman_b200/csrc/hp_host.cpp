@@ -368,11 +368,10 @@ struct HpStream {
   int prec_limbs;                        // _mp_prec of an mpf at the stream's precision
   alignas(64) std::atomic<long> ready;
   std::atomic<bool> finished;
-  alignas(64) long allocated;           // producer's side
-  alignas(64) long seen;                // consumer-side copies of `ready` live in the consumers
+  alignas(64) long allocated;           // producer's side (the consumers keep their own copies of `ready`)
   HpStream(long max_entries, mp_bitcnt_t p)
       : blocks((size_t)(max_entries / kBlock + 2), nullptr), limbs((size_t)(max_entries / kBlock + 2), nullptr), ready(0),
-        finished(false), allocated(0), seen(0) {
+        finished(false), allocated(0) {
     mpf_t t;
     mpf_init2(t, p);
     prec_limbs = t->_mp_prec;            // what mpf_init2 derives from the bit count
