@@ -416,7 +416,8 @@ struct HpStream {
         have = ready.load(std::memory_order_acquire);
         return have > i;
       }
-      if (spin > 256) std::this_thread::yield();
+      if (spin > 20000) std::this_thread::sleep_for(std::chrono::microseconds(50));   // oversubscribed host: stop burning a core
+      else if (spin > 256) std::this_thread::yield();
     }
   }
 };
