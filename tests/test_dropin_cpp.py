@@ -23,18 +23,27 @@ def fnv(data, h=0xcbf29ce484222325):
     return h
 
 
-@pytest.fixture(scope="module")
-def viewer(tmp_path_factory):
-    exe = str(tmp_path_factory.mktemp("dropin") / "headless_viewer")
+def build_caller(tmp_path_factory, name):
+    exe = str(tmp_path_factory.mktemp("dropin") / name)
     cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-Werror",
-           "-I" + os.path.join(ROOT, "include", "newman_b200"),       # "mandelbrot.h" resolves to the drop-in
+           "-I" + os.path.join(ROOT, "include", "newman_b200"),       # "mandelbrot.h" / "video.h" resolve to the drop-in
            "-I" + os.path.join(PKG, "csrc", "compat"),               # <gmpxx.h> stand-in: this image has no GMP headers
-           os.path.join(ROOT, "tests", "dropin", "headless_viewer.cpp"), "-o", exe,
+           os.path.join(ROOT, "tests", "dropin", name + ".cpp"), "-o", exe,
            "-L" + os.path.dirname(L.LIB_PATH), "-l:" + os.path.basename(L.LIB_PATH),
            "-Wl,-rpath," + os.path.dirname(L.LIB_PATH), "-l:libgmp.so.10"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
+
+
+@pytest.fixture(scope="module")
+def viewer(tmp_path_factory):
+    return build_caller(tmp_path_factory, "headless_viewer")
+
+
+@pytest.fixture(scope="module")
+def video(tmp_path_factory):
+    return build_caller(tmp_path_factory, "headless_video")
 
 
 def run(exe, *args):
@@ -82,7 +91,8 @@ def test_library_exports_the_dropin_classes():
                 "Mandelbrot::pointAt(int, int, int) const", "Mandelbrot::translate(int, int, int)", "Mandelbrot::zoom(float)",
                 "Mandelbrot::zoomAt(float, int, int, int)", "Mandelbrot::scaleUp(int)", "Mandelbrot::scaleDown(int)",
                 "Mandelbrot::loadLegacy(char const*)", "MultiWaveGenerator::cache(int) const",
-                "MultiWaveGenerator::load_filename(char const*)", "MultiWaveGenerator::save_filename(char const*) const"):
+                "MultiWaveGenerator::load_filename(char const*)", "MultiWaveGenerator::save_filename(char const*) const",
+                "VideoZoom::VideoZoom()", "VideoZoom::nextFrame(byteimage::ByteImage const&)"):
         assert sym in out, f"{sym} is not exported: a C++ caller of the reference could not link"
 
 
@@ -116,3 +126,35 @@ def test_cpp_caller_renders_the_same_frames_as_the_capi(viewer, tmp_path):
     assert got["k4"] == {"equal": "1"} and got["copy"] == {"at": "1"}
     assert got["rerender"]["over"] == "0" and int(got["rerender"]["N"]) == m.frame_N() // 2
     assert (g1["iterations"] < m.frame_N()).any() and (g1["iterations"] > 256).any()   # the deep frame is not trivial
+
+
+def key_frame(k, H, W):
+    r, c, ch = np.meshgrid(np.arange(H), np.arange(W), np.arange(3), indexing="ij")
+    return ((7 * r + 13 * c + 29 * ch + 101 * k + r * c * k) & 255).astype(np.uint8)
+
+
+def test_cpp_video_caller_links_and_needs_a_gpu_only_for_frames(video, tmp_path):
+    """VideoZoom (reference video.h:13-26) from the library: the first key frame is only stored (video.cpp:15, 33); the
+    in-between frames of a pair come from K5, so without a device the second nextFrame fails loudly."""
+    out = str(tmp_path / "one.raw")
+    r = subprocess.run([video, out, "40", "64", "5", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok" and os.path.getsize(out) == 0
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([video, out, "40", "64", "5", "2"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 2 and "runtime_error" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_video_caller_writes_the_frames_of_k5(video, tmp_path, dev):
+    nr, nc, rate, keys = 40, 64, 5, 3
+    out = str(tmp_path / "zoom.raw")
+    r = subprocess.run([video, out, str(nr), str(nc), str(rate), str(keys)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(out, dtype=np.uint8)
+    assert got.size == (keys - 1) * rate * nr * nc * 3
+    got = got.reshape(keys - 1, rate, nr, nc, 3)
+    H, W = nr * 3 // 2, nc * 3 // 2
+    for k in range(1, keys):
+        want = dev.video_inbetween(key_frame(k - 1, H, W), key_frame(k, H, W), nr, nc, rate)
+        assert np.array_equal(got[k - 1], want), k
