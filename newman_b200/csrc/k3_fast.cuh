@@ -26,6 +26,12 @@
 // rebase at the end of the orbit, or "false alarm" (-> carried into the next sweep, index again a
 // multiple of 4). Every decision is therefore the one k3_perturb.cuh and the oracle take.
 //
+// Quiet segments: most of a sample's life its delta is far too small to come near -Z within the next 16 steps. A
+// per-segment bound on delta's high words (k3_filter.cuh: k3_seg_bound, rebuilt per frame from the orbit and the
+// frame's largest pixel offset) proves that; a warp whose lanes all pass it runs the segment as k3_block_quiet — the
+// recurrence alone, 6.5 SASS instructions per sample-iteration instead of 11.2 — and only the escape filter is
+// looked at when the segment ends (profiles/r01p_*: full levels are entirely quiet, escape levels stay loud).
+//
 // (Two earlier versions replayed flagged blocks inside the warp; on the level where half of the
 // pixels escape that cost 3x, later 1.6x, the time of a full level, and latency-bound tail levels
 // ran 5x slower than the simple kernel — profiles/r01b_*.)
