@@ -347,24 +347,29 @@ static void tables_serial(const ViewHP& v, mpf_srcptr x0re_in, mpf_srcptr x0im_i
   for (auto& x : X) { mpf_clear(x.re); mpf_clear(x.im); }
 }
 
-// The same tables from a 4-stage pipeline: the orbit X and the three coefficient recurrences each on their own thread.
+// The same tables from a pipeline: the orbit X and the three coefficient recurrences each on their own thread.
 // A[i] needs X[i-1] and A[i-1]; B[i] needs X[i-1], B[i-1] and the NEW A[i]; C[i] needs X[i-1], C[i-1] and the new
-// A[i], B[i] (mandelbrot.cpp:118-128) — so stage S at index i only waits for stage S-1 at index i. Every stage issues
-// exactly the mpf operations of tables_serial, in the same order, on private temporaries: the tables are bit-identical
-// (tests/test_host_tables.py compares the two forms and both with the compiled reference). Per index the stages cost
-// 3 / 6 / 9 / 10 multiplications, so the pipeline runs at the pace of C: ~2.8x faster than the serial form, which is what
-// a frame at 1e-400 (M = 5e5 at 1344 bits: 5 s per reference) spends most of its host time in.
+// A[i], B[i] (mandelbrot.cpp:118-128) — so stage S at index i only waits for stage S-1 at index i. Per index the four
+// stages cost 3 / 6 / 9 / 10 multiplications, so the pipeline runs at the pace of C: ~2.7x faster than the serial form.
+// With 6 or more threads the products that do not involve the stage's own previous value — A[i]^2 for B, A[i] B[i] for C
+// — come from two more stages (AA, AB) that run ahead, and A, B, C are left with 6 multiplications each.
+// Every stage issues exactly the mpf operations of tables_serial on operands of the same precision, and every sum is
+// formed in the serial form's order, so the tables are bit-identical (tests/test_host_tables.py compares the forms with
+// each other and with the compiled reference). This is what a deep frame spends most of its host time in: at 1e-400
+// (M = 5e5, 1344 bits) one reference costs 6.6 s serially and a frame builds three.
 namespace {
 
-struct HpPair { mpf_t re, im; };
+template <int K>
+struct HpVals { mpf_t v[K]; };
 
 // Values a stage publishes for the next ones. Blocks of 4096 entries hang off a pointer table of fixed size, so a
 // reader never sees storage move; `ready` = entries published (release / acquire).
+template <int K>
 struct HpStream {
   static const int kBlock = 4096;
   static const long kBatch = 32;        // entries per publication: the counter's cache line changes hands rarely
-  std::vector<HpPair*> blocks;
-  std::vector<mp_limb_t*> limbs;        // one limb pool per block (an mpf_init2 per entry would be a malloc per entry)
+  std::vector<HpVals<K>*> blocks;
+  std::vector<mp_limb_t*> limbs;        // one limb pool per block (an mpf_init2 per value would be a malloc per value)
   int prec_limbs;                        // _mp_prec of an mpf at the stream's precision
   alignas(64) std::atomic<long> ready;
   std::atomic<bool> finished;
@@ -378,24 +383,25 @@ struct HpStream {
     mpf_clear(t);
   }
   ~HpStream() {
-    for (HpPair* b : blocks) delete[] b;
+    for (HpVals<K>* b : blocks) delete[] b;
     for (mp_limb_t* l : limbs) delete[] l;
   }
-  HpPair& at(long i) { return blocks[(size_t)(i / kBlock)][i % kBlock]; }
-  // producer only: a fresh entry (value 0) laid out like mpf_init2 does it — prec + 1 limbs — inside the block's pool;
-  // such an entry is assigned with mpf_set and never passed to mpf_clear / mpf_set_prec
-  HpPair& append() {
+  HpVals<K>& at(long i) { return blocks[(size_t)(i / kBlock)][i % kBlock]; }
+  // producer only: a fresh entry (values 0) laid out like mpf_init2 does it — prec + 1 limbs each — inside the block's
+  // pool; such a value is written by mpf_set / mpf_mul and never passed to mpf_clear / mpf_set_prec
+  HpVals<K>& append() {
     const long i = allocated++;
     const size_t bi = (size_t)(i / kBlock);
     const size_t per = (size_t)prec_limbs + 1;
     if (i % kBlock == 0) {
-      blocks[bi] = new HpPair[kBlock];
-      limbs[bi] = new mp_limb_t[2 * per * kBlock];
+      blocks[bi] = new HpVals<K>[kBlock];
+      limbs[bi] = new mp_limb_t[K * per * kBlock];
     }
-    HpPair& q = at(i);
-    mp_limb_t* base = limbs[bi] + 2 * per * (size_t)(i % kBlock);
-    q.re->_mp_prec = prec_limbs; q.re->_mp_size = 0; q.re->_mp_exp = 0; q.re->_mp_d = base;
-    q.im->_mp_prec = prec_limbs; q.im->_mp_size = 0; q.im->_mp_exp = 0; q.im->_mp_d = base + per;
+    HpVals<K>& q = at(i);
+    mp_limb_t* base = limbs[bi] + K * per * (size_t)(i % kBlock);
+    for (int k = 0; k < K; k++) {
+      q.v[k]->_mp_prec = prec_limbs; q.v[k]->_mp_size = 0; q.v[k]->_mp_exp = 0; q.v[k]->_mp_d = base + k * per;
+    }
     return q;
   }
   void publish(bool force = false) {
@@ -434,74 +440,114 @@ struct CoefOut {  // one coefficient's descended tables
 
 }  // namespace
 
-static void tables_pipelined(const ViewHP& v, mpf_srcptr x0re, mpf_srcptr x0im, DeepTablesHost& out) {
+// split_products: the A[i]^2 and A[i] B[i] products come from their own stages (6 threads in all) instead of from B and C.
+static void tables_pipelined(const ViewHP& v, mpf_srcptr x0re, mpf_srcptr x0im, DeepTablesHost& out, bool split_products) {
   const mp_bitcnt_t P = v.prec;
   // X holds the non-escaped iterates only (what the series reads); A and B hold the new coefficients of index i at
-  // entry i - 1 (index 0 is the constant start value)
-  HpStream X(v.N, P), A(v.N, P), B(v.N, P);
+  // entry i - 1 (index 0 is the constant start value); AA = (A.re^2, A.im^2, A.re A.im) and
+  // AB = (A.re B.re, A.im B.im, A.re B.im, A.im B.re) of the same index at the same entry
+  HpStream<2> X(v.N, P), A(v.N, P), B(v.N, P);
+  HpStream<3> AA(split_products ? v.N : 1, P);
+  HpStream<4> AB(split_products ? v.N : 1, P);
   out.a.clear(); out.b.clear(); out.c.clear(); out.a_m.clear(); out.b_m.clear(); out.c_m.clear();
   out.a_e.clear(); out.b_e.clear(); out.c_e.clear(); out.x_hi.clear(); out.x_lo.clear();
   out.has_escape = false;
+  std::vector<std::thread> stages;
 
-  std::thread tA([&]() {
+  stages.emplace_back([&]() {   // ---- A[i] = 2 X[i-1] A[i-1] + 1
     Mp ar(P), ai(P), nar(P), nai(P), p1(P), p2(P), s(P), u(P), two(64), one(64);
     mpf_set_d(two.v, 2.0); mpf_set_d(one.v, 1.0); mpf_set_d(ar.v, 1.0);
     CoefOut o = {&out.a, &out.a_m, &out.a_e};
     long have_x = 0;
     if (X.wait_for(0, have_x)) o.push(ar.v, ai.v);
     for (long i = 1; X.wait_for(i, have_x); i++) {   // index i exists iff X[i] is a non-escaped iterate
-      mpf_srcptr xr = X.at(i - 1).re, xi = X.at(i - 1).im;
+      mpf_srcptr xr = X.at(i - 1).v[0], xi = X.at(i - 1).v[1];
       mpf_mul(p1.v, xr, ar.v); mpf_mul(p2.v, xi, ai.v); mpf_sub(s.v, p1.v, p2.v);
       mpf_mul(u.v, two.v, s.v); mpf_add(nar.v, u.v, one.v);
       mpf_mul(p1.v, xr, ai.v); mpf_mul(p2.v, xi, ar.v); mpf_add(s.v, p1.v, p2.v);
       mpf_mul(nai.v, two.v, s.v);
       mpf_swap(ar.v, nar.v); mpf_swap(ai.v, nai.v);
-      HpPair& q = A.append();
-      mpf_set(q.re, ar.v); mpf_set(q.im, ai.v);
+      HpVals<2>& q = A.append();
+      mpf_set(q.v[0], ar.v); mpf_set(q.v[1], ai.v);
       A.publish();
       o.push(ar.v, ai.v);
     }
     A.finish();
   });
-  std::thread tB([&]() {
-    Mp br(P), bi(P), nbr(P), nbi(P), p1(P), p2(P), s(P), u(P), two(64);
+  if (split_products)
+    stages.emplace_back([&]() {   // ---- the products of the new A that B[i] adds
+      long have_a = 0;
+      for (long e = 0; A.wait_for(e, have_a); e++) {
+        mpf_srcptr nar = A.at(e).v[0], nai = A.at(e).v[1];
+        HpVals<3>& q = AA.append();
+        mpf_mul(q.v[0], nar, nar); mpf_mul(q.v[1], nai, nai); mpf_mul(q.v[2], nar, nai);
+        AA.publish();
+      }
+      AA.finish();
+    });
+  stages.emplace_back([&]() {   // ---- B[i] = 2 X[i-1] B[i-1] + A[i]^2
+    Mp br(P), bi(P), nbr(P), nbi(P), p1(P), p2(P), s(P), u(P), q1(P), q2(P), q3(P), two(64);
     mpf_set_d(two.v, 2.0);
     CoefOut o = {&out.b, &out.b_m, &out.b_e};
-    long have_x = 0, have_a = 0;
+    long have_x = 0, have_a = 0, have_aa = 0;
     if (X.wait_for(0, have_x)) o.push(br.v, bi.v);
-    for (long i = 1; A.wait_for(i - 1, have_a); i++) {
-      mpf_srcptr xr = X.at(i - 1).re, xi = X.at(i - 1).im, nar = A.at(i - 1).re, nai = A.at(i - 1).im;
+    for (long i = 1; split_products ? AA.wait_for(i - 1, have_aa) : A.wait_for(i - 1, have_a); i++) {
+      mpf_srcptr xr = X.at(i - 1).v[0], xi = X.at(i - 1).v[1];
+      mpf_srcptr a2r, a2i, ari;   // A.re*A.re, A.im*A.im, A.re*A.im of the new A
+      if (split_products) { a2r = AA.at(i - 1).v[0]; a2i = AA.at(i - 1).v[1]; ari = AA.at(i - 1).v[2]; }
+      else {
+        mpf_srcptr nar = A.at(i - 1).v[0], nai = A.at(i - 1).v[1];
+        mpf_mul(q1.v, nar, nar); mpf_mul(q2.v, nai, nai); mpf_mul(q3.v, nar, nai);
+        a2r = q1.v; a2i = q2.v; ari = q3.v;
+      }
       mpf_mul(p1.v, xr, br.v); mpf_mul(p2.v, xi, bi.v); mpf_sub(s.v, p1.v, p2.v);
       mpf_mul(u.v, two.v, s.v);
-      mpf_mul(p1.v, nar, nar); mpf_add(s.v, u.v, p1.v);
-      mpf_mul(p2.v, nai, nai); mpf_sub(nbr.v, s.v, p2.v);
+      mpf_add(s.v, u.v, a2r);
+      mpf_sub(nbr.v, s.v, a2i);
       mpf_mul(p1.v, xr, bi.v); mpf_mul(p2.v, xi, br.v); mpf_add(s.v, p1.v, p2.v);
-      mpf_mul(p1.v, nar, nai); mpf_add(u.v, s.v, p1.v);
+      mpf_add(u.v, s.v, ari);
       mpf_mul(nbi.v, two.v, u.v);
       mpf_swap(br.v, nbr.v); mpf_swap(bi.v, nbi.v);
-      HpPair& q = B.append();
-      mpf_set(q.re, br.v); mpf_set(q.im, bi.v);
+      HpVals<2>& q = B.append();
+      mpf_set(q.v[0], br.v); mpf_set(q.v[1], bi.v);
       B.publish();
       o.push(br.v, bi.v);
     }
     B.finish();
   });
-  std::thread tC([&]() {
-    Mp cr(P), ci(P), ncr(P), nci(P), p1(P), p2(P), s(P), u(P), two(64);
+  if (split_products)
+    stages.emplace_back([&]() {   // ---- the products of the new A and B that C[i] adds
+      long have_b = 0;
+      for (long e = 0; B.wait_for(e, have_b); e++) {   // B[e] published => A[e] is there as well
+        mpf_srcptr nar = A.at(e).v[0], nai = A.at(e).v[1], nbr = B.at(e).v[0], nbi = B.at(e).v[1];
+        HpVals<4>& q = AB.append();
+        mpf_mul(q.v[0], nar, nbr); mpf_mul(q.v[1], nai, nbi); mpf_mul(q.v[2], nar, nbi); mpf_mul(q.v[3], nai, nbr);
+        AB.publish();
+      }
+      AB.finish();
+    });
+  stages.emplace_back([&]() {   // ---- C[i] = 2 (X[i-1] C[i-1] + A[i] B[i])
+    Mp cr(P), ci(P), ncr(P), nci(P), p1(P), p2(P), s(P), u(P), q1(P), q2(P), q3(P), q4(P), two(64);
     mpf_set_d(two.v, 2.0);
     CoefOut o = {&out.c, &out.c_m, &out.c_e};
-    long have_x = 0, have_b = 0;
+    long have_x = 0, have_b = 0, have_ab = 0;
     if (X.wait_for(0, have_x)) o.push(cr.v, ci.v);
-    for (long i = 1; B.wait_for(i - 1, have_b); i++) {
-      mpf_srcptr xr = X.at(i - 1).re, xi = X.at(i - 1).im, nar = A.at(i - 1).re, nai = A.at(i - 1).im;
-      mpf_srcptr nbr = B.at(i - 1).re, nbi = B.at(i - 1).im;
+    for (long i = 1; split_products ? AB.wait_for(i - 1, have_ab) : B.wait_for(i - 1, have_b); i++) {
+      mpf_srcptr xr = X.at(i - 1).v[0], xi = X.at(i - 1).v[1];
+      mpf_srcptr rr, ii, ri, ir;   // A.re*B.re, A.im*B.im, A.re*B.im, A.im*B.re of the new A, B
+      if (split_products) { rr = AB.at(i - 1).v[0]; ii = AB.at(i - 1).v[1]; ri = AB.at(i - 1).v[2]; ir = AB.at(i - 1).v[3]; }
+      else {
+        mpf_srcptr nar = A.at(i - 1).v[0], nai = A.at(i - 1).v[1], nbr = B.at(i - 1).v[0], nbi = B.at(i - 1).v[1];
+        mpf_mul(q1.v, nar, nbr); mpf_mul(q2.v, nai, nbi); mpf_mul(q3.v, nar, nbi); mpf_mul(q4.v, nai, nbr);
+        rr = q1.v; ii = q2.v; ri = q3.v; ir = q4.v;
+      }
       mpf_mul(p1.v, xr, cr.v); mpf_mul(p2.v, xi, ci.v); mpf_sub(s.v, p1.v, p2.v);
-      mpf_mul(p1.v, nar, nbr); mpf_add(u.v, s.v, p1.v);
-      mpf_mul(p2.v, nai, nbi); mpf_sub(s.v, u.v, p2.v);
+      mpf_add(u.v, s.v, rr);
+      mpf_sub(s.v, u.v, ii);
       mpf_mul(ncr.v, two.v, s.v);
       mpf_mul(p1.v, xr, ci.v); mpf_mul(p2.v, xi, cr.v); mpf_add(s.v, p1.v, p2.v);
-      mpf_mul(p1.v, nar, nbi); mpf_add(u.v, s.v, p1.v);
-      mpf_mul(p2.v, nai, nbr); mpf_add(s.v, u.v, p2.v);
+      mpf_add(u.v, s.v, ri);
+      mpf_add(s.v, u.v, ir);
       mpf_mul(nci.v, two.v, s.v);
       mpf_swap(cr.v, ncr.v); mpf_swap(ci.v, nci.v);
       o.push(cr.v, ci.v);
@@ -520,26 +566,26 @@ static void tables_pipelined(const ViewHP& v, mpf_srcptr x0re, mpf_srcptr x0im, 
         mpf_set_d(d64.v, hi); mpf_sub(rem.v, im, d64.v); out.x_lo.push_back(mpf_get_d(rem.v));
       }
     };
-    HpPair& q0 = X.append();
-    mpf_set(q0.re, x0re); mpf_set(q0.im, x0im);
-    descend_pair(q0.re, q0.im, true);
+    HpVals<2>& q0 = X.append();
+    mpf_set(q0.v[0], x0re); mpf_set(q0.v[1], x0im);
+    descend_pair(q0.v[0], q0.v[1], true);
     X.publish(true);
     for (int i = 1; i < v.N; i++) {
-      HpPair& prev = X.at(i - 1);
-      step(nre.v, nim.v, prev.re, prev.im, x0re, x0im);
+      HpVals<2>& prev = X.at(i - 1);
+      step(nre.v, nim.v, prev.v[0], prev.v[1], x0re, x0im);
       if (bailed(nre.v, nim.v)) {   // the escaped iterate: kept in x_hi only (the reference drops it)
         out.has_escape = true;
         descend_pair(nre.v, nim.v, false);
         break;
       }
-      HpPair& q = X.append();
-      mpf_set(q.re, nre.v); mpf_set(q.im, nim.v);
-      descend_pair(q.re, q.im, true);
+      HpVals<2>& q = X.append();
+      mpf_set(q.v[0], nre.v); mpf_set(q.v[1], nim.v);
+      descend_pair(q.v[0], q.v[1], true);
       X.publish();
     }
     X.finish();
   }
-  tA.join(); tB.join(); tC.join();
+  for (std::thread& t : stages) t.join();
   out.M = (int)X.allocated;
 }
 
@@ -553,10 +599,10 @@ void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out, int th
   if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
   static const bool debug = getenv("NM_DEBUG_TABLES") != nullptr;   // NM_DEBUG_TABLES=1: time of orbit + series per call
   const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  if (threads >= 4) tables_pipelined(v, x0re.v, x0im.v, out);
+  if (threads >= 4) tables_pipelined(v, x0re.v, x0im.v, out, threads >= 6);
   else tables_serial(v, x0re.v, x0im.v, out);
   if (debug)
-    fprintf(stderr, "nm build_tables: M %d, %d bits, %s: %.3f s\n", out.M, (int)P, threads >= 4 ? "pipelined" : "serial",
+    fprintf(stderr, "nm build_tables: M %d, %d bits, %s: %.3f s\n", out.M, (int)P, threads >= 6 ? "pipelined (6 stages)" : threads >= 4 ? "pipelined (4 stages)" : "serial",
             std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   out.finite = true;
   for (size_t i = 0; i < out.a.size() && out.finite; i++)

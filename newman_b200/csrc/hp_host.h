@@ -70,7 +70,8 @@ void probe_lengths(const ViewHP& v, const std::vector<std::pair<int, int> >& can
 
 // computeOrbit + computeSeries for the reference point at pixel (row, col), descended; eps arrays
 // relative to that orbit's X[0]. threads: 0 = hardware concurrency; with 4 or more the orbit and the three
-// coefficient recurrences run as a pipeline on four threads (same operations, bit-identical tables), else serially.
+// coefficient recurrences run as a pipeline on four threads, with 6 or more the products A^2 and A B get two stages of
+// their own (same operations, bit-identical tables), else everything runs serially.
 void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out, int threads = 0);
 
 }  // namespace newman_b200

@@ -177,18 +177,20 @@ def same_tables(h1, h4):
 
 @pytest.mark.parametrize("name,scale", [("cfg2", 40), ("cfg3", 80)])
 def test_pipelined_tables_equal_serial_tables(name, scale):
-    """build_tables with 4+ host threads runs orbit, A, B, C as a pipeline (hp_host.cpp: tables_pipelined); it must
+    """build_tables with 4+ host threads runs orbit, A, B, C as a pipeline (hp_host.cpp: tables_pipelined; 6+ threads: two
+    more stages for the products); it must
     deliver what the one-thread form does, bit for bit — the long orbits of the bench views, double and
     mantissa/exponent forms."""
     from newman_b200 import workloads
     cfg = workloads.config(name, scale=scale)
     hs = []
-    for threads in (1, 4):
+    for threads in (1, 4, 6):   # serial, 4 stages, 6 stages (A^2 and A B products on their own threads)
         v = newman_b200.Mandelbrot(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"],
                                    host_threads=threads)
         hs.append(v.host_tables(cfg["nr"] // 2, cfg["nc"] // 2))
     assert hs[0]["M"] > 50000
-    same_tables(*hs)
+    same_tables(hs[0], hs[1])
+    same_tables(hs[0], hs[2])
 
 
 @pytest.mark.parametrize("N", [1, 2, 3, 33, 4097, 9000])
@@ -197,9 +199,10 @@ def test_pipelined_tables_edge_lengths(N):
     and batch sizes) and ones that escape at once."""
     for center in (("-0.1", "0.05"), ("0.4", "0.3"), ("2.5", "0.0")):
         hs = []
-        for threads in (1, 4):
+        for threads in (1, 4, 6):
             v = newman_b200.Mandelbrot(12, 16, N=N, sz=("1e-30", "1e-30"), center=center, host_threads=threads)
             hs.append(v.host_tables(6, 8))
-        same_tables(*hs)
+        same_tables(hs[0], hs[1])
+        same_tables(hs[0], hs[2])
         if center[0] == "-0.1":
             assert hs[0]["M"] == N and not hs[0]["has_escape"]
