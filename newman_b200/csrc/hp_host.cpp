@@ -357,6 +357,8 @@ static void tables_serial(const ViewHP& v, mpf_srcptr x0re_in, mpf_srcptr x0im_i
 // formed in the serial form's order, so the tables are bit-identical (tests/test_host_tables.py compares the forms with
 // each other and with the compiled reference). This is what a deep frame spends most of its host time in: at 1e-400
 // (M = 5e5, 1344 bits) one reference costs 6.6 s serially and a frame builds three.
+// Memory: the streams keep every published value until the call returns — 13 values of prec + 1 limbs per index with
+// all six stages (the serial form keeps X only: 2): 1.2 GB for that reference, transient.
 namespace {
 
 template <int K>
