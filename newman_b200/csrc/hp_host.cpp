@@ -357,8 +357,8 @@ static void tables_serial(const ViewHP& v, mpf_srcptr x0re_in, mpf_srcptr x0im_i
 // formed in the serial form's order, so the tables are bit-identical (tests/test_host_tables.py compares the forms with
 // each other and with the compiled reference). This is what a deep frame spends most of its host time in: at 1e-400
 // (M = 5e5, 1344 bits) one reference costs 6.6 s serially and a frame builds three.
-// Memory: the streams keep every published value until the call returns — 13 values of prec + 1 limbs per index with
-// all six stages (the serial form keeps X only: 2): 1.2 GB for that reference, transient.
+// Memory: a stream gives a block of 4096 entries back once the last stage (C) is past it, so what is held is the lead of
+// each stage over C — mostly the orbit's, which the serial form keeps in full as well.
 namespace {
 
 template <int K>
@@ -376,9 +376,11 @@ struct HpStream {
   alignas(64) std::atomic<long> ready;
   std::atomic<bool> finished;
   alignas(64) long allocated;           // producer's side (the consumers keep their own copies of `ready`)
-  HpStream(long max_entries, mp_bitcnt_t p)
+  long freed_blocks;
+  const std::atomic<long>* dead_below;  // entries below this position are read by nobody any more (the last stage's progress)
+  HpStream(long max_entries, mp_bitcnt_t p, const std::atomic<long>* dead)
       : blocks((size_t)(max_entries / kBlock + 2), nullptr), limbs((size_t)(max_entries / kBlock + 2), nullptr), ready(0),
-        finished(false), allocated(0) {
+        finished(false), allocated(0), freed_blocks(0), dead_below(dead) {
     mpf_t t;
     mpf_init2(t, p);
     prec_limbs = t->_mp_prec;            // what mpf_init2 derives from the bit count
@@ -396,6 +398,14 @@ struct HpStream {
     const size_t bi = (size_t)(i / kBlock);
     const size_t per = (size_t)prec_limbs + 1;
     if (i % kBlock == 0) {
+      // a new block: first give back the blocks every reader is past (producer-side only, so `blocks` never changes
+      // under a reader that could still want the entry)
+      const long dead = dead_below->load(std::memory_order_acquire);
+      while ((freed_blocks + 1) * kBlock <= dead) {
+        delete[] blocks[(size_t)freed_blocks]; blocks[(size_t)freed_blocks] = nullptr;
+        delete[] limbs[(size_t)freed_blocks]; limbs[(size_t)freed_blocks] = nullptr;
+        freed_blocks++;
+      }
       blocks[bi] = new HpVals<K>[kBlock];
       limbs[bi] = new mp_limb_t[K * per * kBlock];
     }
@@ -448,9 +458,12 @@ static void tables_pipelined(const ViewHP& v, mpf_srcptr x0re, mpf_srcptr x0im, 
   // X holds the non-escaped iterates only (what the series reads); A and B hold the new coefficients of index i at
   // entry i - 1 (index 0 is the constant start value); AA = (A.re^2, A.im^2, A.re A.im) and
   // AB = (A.re B.re, A.im B.im, A.re B.im, A.im B.re) of the same index at the same entry
-  HpStream<2> X(v.N, P), A(v.N, P), B(v.N, P);
-  HpStream<3> AA(split_products ? v.N : 1, P);
-  HpStream<4> AB(split_products ? v.N : 1, P);
+  // C is the last stage: whatever position it is past, every other stage is past as well, so the producers give those
+  // blocks back as they go (the orbit may still run far ahead of the series: that part stays, like in the serial form)
+  std::atomic<long> c_done(0);
+  HpStream<2> X(v.N, P, &c_done), A(v.N, P, &c_done), B(v.N, P, &c_done);
+  HpStream<3> AA(split_products ? v.N : 1, P, &c_done);
+  HpStream<4> AB(split_products ? v.N : 1, P, &c_done);
   out.a.clear(); out.b.clear(); out.c.clear(); out.a_m.clear(); out.b_m.clear(); out.c_m.clear();
   out.a_e.clear(); out.b_e.clear(); out.c_e.clear(); out.x_hi.clear(); out.x_lo.clear();
   out.has_escape = false;
@@ -553,6 +566,8 @@ static void tables_pipelined(const ViewHP& v, mpf_srcptr x0re, mpf_srcptr x0im, 
       mpf_mul(nci.v, two.v, s.v);
       mpf_swap(cr.v, ncr.v); mpf_swap(ci.v, nci.v);
       o.push(cr.v, ci.v);
+      // index i is done: C's next reads are X[i] and entry i of A, B, AB; positions below i are dead for everybody
+      if ((i & 255) == 0) c_done.store(i, std::memory_order_release);
     }
   });
 
