@@ -312,3 +312,62 @@ def test_quiet_bound_is_useful_and_degenerates_safely():
     assert seg_bound(lib, z3, gb3, 1e-52, j0=16) >= T   # (the last index was the binding one: the bound relaxes)
     # NaN / inf offsets
     assert seg_bound(lib, z, gb, math.nan, j0=16) == 0 and seg_bound(lib, z, gb, math.inf, j0=16) == 0
+
+
+def test_quiet_bound_on_a_real_frame():
+    """Every sample of a small cfg2 frame (1e-50, M = 54 512) is iterated through the whole reference orbit with the
+    perturbation recurrence (complex128: the bound's 2^-40 slack dwarfs the difference to the kernel's fma order); a
+    sample that the segment bound admits at a segment start may not satisfy the glitch test anywhere in that segment.
+    This pins the table indexing (Z[0] = 0, Z[j] = X[j-1], the new delta pairs with Z[j+1]) and the use of the
+    frame's largest pixel offset on real data; the frame does contain glitches, all of them in loud segments."""
+    from newman_b200 import workloads
+    lib = newman_b200.load()
+    cfg = workloads.config("cfg2", scale=40)
+    v = newman_b200.Mandelbrot(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
+    h = v.host_tables(cfg["nr"] // 2, cfg["nc"] // 2)
+    xh = np.asarray(h["x_hi"]).reshape(-1, 2)
+    J = len(xh)                                   # last valid table index (the escaped iterate included)
+    z = np.zeros((J + 1, 2))
+    z[1:] = xh
+    gtol = 1e-6
+    gb = (z[:, 0] ** 2 + z[:, 1] ** 2) * gtol
+    gb[0] = 0.0
+    if h["has_escape"]:
+        gb[J] = 0.0                               # k_glitch_bounds: the escaped iterate never flags
+    er, ei = np.asarray(h["eps_re"], float), np.asarray(h["eps_im"], float)
+    e_max = math.hypot(np.abs(er).max(), np.abs(ei).max()) * (1 + 2.0 ** -40)
+    nseg = J // 16
+    zc, gbc = np.ascontiguousarray(z), np.ascontiguousarray(gb)
+    T = np.array([lib.nm_k3_seg_bound(zc.ctypes.data_as(C.POINTER(C.c_double)), gbc.ctypes.data_as(C.POINTER(C.c_double)),
+                                      16 * s, J, e_max) for s in range(nseg)], dtype=np.int64)
+    assert (T > 0).mean() > 0.99
+
+    Z = z[:, 0] + 1j * z[:, 1]
+    eps = (er[None, :] + 1j * ei[:, None]).reshape(-1)
+    d = np.zeros_like(eps)
+    alive = np.ones(eps.shape, bool)
+    admitted = np.zeros(eps.shape, bool)
+    glitches = loud_glitches = checked = 0
+    with np.errstate(over="ignore", invalid="ignore"):
+        for j in range(J):
+            if j % 16 == 0:
+                s = j // 16
+                if s < nseg and j + 16 <= J:
+                    hi = np.maximum(np.abs(d.real), np.abs(d.imag)).view(np.uint64) >> np.uint64(32)
+                    admitted = alive & (hi.astype(np.int64) < T[s])
+                    checked += int(admitted.sum())
+                else:
+                    admitted[:] = False
+            d = d * (2.0 * Z[j] + d) + eps
+            zz = Z[j + 1] + d
+            m2 = zz.real ** 2 + zz.imag ** 2
+            g = alive & (m2 < gb[j + 1])
+            if g.any():
+                glitches += int(g.sum())
+                loud_glitches += int((g & ~admitted).sum())
+                assert not (g & admitted).any(), ("glitch inside an admitted segment", j, np.nonzero(g & admitted)[0][:5])
+            alive &= ~g & ~(m2 > 1048576.0) & np.isfinite(m2)
+            if not alive.any():
+                break
+    assert glitches > 0 and glitches == loud_glitches
+    assert checked > 1000000
