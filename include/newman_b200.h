@@ -246,6 +246,9 @@ NM_API int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int
  * bounds, e_max >= |eps| of every sample. Returns the high word T: a state with hi(|dr|) < T and hi(|di|) < T at j0
  * cannot satisfy the glitch test at any of the indices j0+1 .. j0+16 (0 = no state is exempt). */
 NM_API int32_t nm_k3_seg_bound(const double* z, const double* gb, int j0, int jmax, double e_max);
+/* The same bound over 32 iterations (indices j0+1 .. j0+32): the table of the K3F_SEG32 build option (an experiment, off by
+ * default: k3_fast.cuh). */
+NM_API int32_t nm_k3_seg_bound32(const double* z, const double* gb, int j0, int jmax, double e_max);
 NM_API int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes, char* name, int cap);
 
 /* ==== view level: the drop-in class through C ===================================================

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab
     // 24 = a whole segment of k3_fast (the event lies at most 16 steps past the checkpoint) + two blocks: a
     // candidate of the escape filter whose |z|^2 is still below 2^20 at the segment end escapes within the
     // next step or two (|z| > 700 squares), so it is finished here and not carried
-    bool cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, 24, &steps);
+    bool cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, K3F_SEG32 ? 40 : 24, &steps);
     // A state that was just rebased onto the start of the orbit (it outlived the reference: |z| is
     // large) nearly always escapes within a few steps: finish it here rather than carrying it through
     // another sweep of (mostly empty) level launches. Same steps, same decisions, same order.
@@ -416,6 +416,36 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
           if (n4 > nb - b) n4 = nb - b;
           quiet = K3F_QUIET && n4 == 4 && m_hi < __ldg(&p.seg_hi[j >> 4]);
         }
+#if K3F_SEG32
+        // EXPERIMENT (default off; the bound is validated on the CPU — tests/test_k3_filter.py —, this path has not run on
+        // a GPU yet): where the 32-step bound admits every lane of the warp, run two segments on one checkpoint, i.e. half
+        // the bookkeeping (~70 instructions) per 16 iterations. k3_events grants 40 steps instead of 24 accordingly.
+        {
+          bool quiet32 = true;
+          if (act) quiet32 = quiet && (j & 31) == 0 && nb - b >= 8 && m_hi < __ldg(&p.seg32_hi[j >> 5]);
+          if (__all_sync(FULL_MASK, quiet32)) {
+            if (act) {
+              const int j_ck = j;
+#pragma unroll
+              for (int s = 0; s < P; ++s)
+                if (live & (1u << s)) slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) k3_block_quiet<P, SCALED>(dr, di, er, ei, S, sZ2, j - jbase + 4 * q);
+              j += 32;
+              b += 8;
+              m_hi = hi_max();
+              const int esc_hi = sE[j - jbase];
+              if (m_hi >= esc_hi) {
+                bool none[P];
+#pragma unroll
+                for (int s = 0; s < P; ++s) none[s] = false;
+                export_flagged(none, esc_hi, j_ck);
+              }
+            }
+            continue;
+          }
+        }
+#endif
         const bool warp_quiet = K3F_QUIET && __all_sync(FULL_MASK, quiet);
         if (act) {
           const int j_ck = j;

@@ -103,12 +103,14 @@ __host__ __device__ __forceinline__ double k3f_from_hi(uint32_t hi) {
 }
 
 // Z[j] = (zr[j], zi[j]) and gb[j] for j <= jmax (the last valid table index); e_max >= |eps| of every sample.
-__host__ __device__ inline int32_t k3_seg_bound(const double* zr, const double* zi, const double* gb, int zstride, int j0, int jmax,
-                                                double e_max) {
-  if (j0 + 16 > jmax || !(e_max >= 0.0)) return 0;
+// NS = steps the bound covers (16: k3_fast's segments; 32: the double segments of the K3F_SEG32 experiment).
+template <int NS>
+__host__ __device__ inline int32_t k3_seg_bound_n(const double* zr, const double* zi, const double* gb, int zstride, int j0, int jmax,
+                                                  double e_max) {
+  if (j0 + NS > jmax || !(e_max >= 0.0)) return 0;
   const double up = 1.0 + 9.094947017729282e-13;   // 2^-40
-  double g2[16], L[16];                              // 2|Z_{j0+i}| (rounded up), L_{j0+i+1}
-  for (int i = 0; i < 16; ++i) {
+  double g2[NS], L[NS];                              // 2|Z_{j0+i}| (rounded up), L_{j0+i+1}
+  for (int i = 0; i < NS; ++i) {
     const double ar = zr[(size_t)(j0 + i) * zstride], ai = zi[(size_t)(j0 + i) * zstride];
     g2[i] = 2.0 * sqrt(ar * ar + ai * ai) * up;
     if (!(g2[i] < 1e300)) return 0;
@@ -125,13 +127,17 @@ __host__ __device__ inline int32_t k3_seg_bound(const double* zr, const double* 
     const uint32_t mid = lo + (hi - lo) / 2u;
     double D = 1.4142135623730951 * k3f_from_hi(mid) * up;
     bool ok = true;
-    for (int i = 0; i < 16 && ok; ++i) {
+    for (int i = 0; i < NS && ok; ++i) {
       D = (D * (g2[i] + D) + e_max) * up + 1e-290;
       ok = D <= L[i];                                // false for NaN / inf as well
     }
     if (ok) lo = mid; else hi = mid;
   }
   return (int32_t)lo;
+}
+__host__ __device__ inline int32_t k3_seg_bound(const double* zr, const double* zi, const double* gb, int zstride, int j0, int jmax,
+                                                double e_max) {
+  return k3_seg_bound_n<16>(zr, zi, gb, zstride, j0, jmax, e_max);
 }
 
 // The tests as k3_fast evaluates them (scaled_mask: 0 for a plain state, 0xffffffff for a scaled one).

@@ -40,6 +40,10 @@ struct __align__(16) PixState {
   int32_t e;   // scale exponent: delta = (dr, di) * 2^e (0 in plain frames)
 };
 
+#ifndef K3F_SEG32
+#define K3F_SEG32 0     // experiment (unmeasured, see k3_fast.cuh): quiet double segments of 32 iterations
+#endif
+
 struct K3Params {
   const double2* Z;      // [Jmax+1 (+pad)]
   const int32_t* ghi;    // high words of gb[j] = glitch_tol*|Z[j]|^2
@@ -48,6 +52,9 @@ struct K3Params {
   const int4* filt;      // k3_fast: glitch-filter entries (k3_filter.cuh: K3Filt)
   const int32_t* esc_hi; // k3_fast: escape-filter high words
   const int32_t* seg_hi; // k3_fast: per 16-iteration segment, the quiet bound on delta's high words (k3_seg_bound)
+#if K3F_SEG32
+  const int32_t* seg32_hi; // experiment: the same bound over 32 iterations, per index = 0 (mod 32)
+#endif
   int Jmax;              // last valid table index
   int N, CH, k;
   EpsTab eps;

@@ -70,6 +70,7 @@ struct nm_ctx {
   int paldev_n = 0;  // entries of the device-generated palette in paldev (0: none)
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
+  DevBuf seg32_hi;   // K3F_SEG32 experiment only
   DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
       rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
@@ -165,6 +166,15 @@ __global__ void k_seg_bounds(const double2* Z, const double* gb, int jmax, const
   const double* z = (const double*)Z;
   seg_hi[s] = k3_seg_bound(z, z + 1, gb, 2, 16 * s, jmax, *e_max);
 }
+
+#if K3F_SEG32
+__global__ void k_seg_bounds32(const double2* Z, const double* gb, int jmax, const double* e_max, int32_t* seg_hi, int n_seg) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seg) return;
+  const double* z = (const double*)Z;
+  seg_hi[s] = k3_seg_bound_n<32>(z, z + 1, gb, 2, 32 * s, jmax, *e_max);
+}
+#endif
 
 __global__ void k_apply_fixups(nm_escape* out, const int32_t* pix, const float* val, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,6 +406,9 @@ int launch_deep(nm_ctx* ctx) {
   p.Z = ctx->Z.as<double2>(); p.ghi = ctx->ghi.as<int32_t>(); p.gb = ctx->gb.as<double>();
   p.Z2 = ctx->Z2.as<double2>(); p.filt = ctx->k3filt.as<int4>(); p.esc_hi = ctx->esc_hi.as<int32_t>();
   p.seg_hi = ctx->seg_hi.as<int32_t>();
+#if K3F_SEG32
+  p.seg32_hi = ctx->seg32_hi.as<int32_t>();
+#endif
   p.Jmax = ctx->Jmax; p.N = ctx->N; p.CH = CH;
   p.eps = eps; p.nc = ctx->nc;
   p.fresh_ids = ctx->fresh.as<int32_t>();
@@ -669,7 +682,7 @@ void nm_destroy(nm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->own);
-  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->eps_max,
+  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->seg32_hi, &ctx->eps_max,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
                     &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
@@ -865,6 +878,13 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
                                                      ctx->seg_hi.as<int32_t>(), n_seg);
     NM_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 2;
+#if K3F_SEG32
+    NM_CUDA(ctx, ctx->seg32_hi.ensure((size_t)(J1 / 32 + 8) * sizeof(int32_t)));
+    k_seg_bounds32<<<(n_seg / 2 + 128) / 128, 128, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->Jmax, ctx->eps_max.as<double>(),
+                                                           ctx->seg32_hi.as<int32_t>(), n_seg / 2 + 1);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+#endif
   }
   return NM_OK;
 }
@@ -1117,6 +1137,11 @@ void nm_k3_filter_entry(double zr, double zi, double gb, uint32_t entry[5]) {
 int32_t nm_k3_seg_bound(const double* z, const double* gb, int j0, int jmax, double e_max) {
   if (!z || !gb || j0 < 0) return 0;
   return k3_seg_bound(z, z + 1, gb, 2, j0, jmax, e_max);
+}
+
+int32_t nm_k3_seg_bound32(const double* z, const double* gb, int j0, int jmax, double e_max) {
+  if (!z || !gb || j0 < 0) return 0;
+  return k3_seg_bound_n<32>(z, z + 1, gb, 2, j0, jmax, e_max);
 }
 
 int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int scaled, int* glitch, int* escape) {
