@@ -74,6 +74,12 @@ NM_API int nm_sync(nm_ctx* ctx);
  *                          (decided on the device from the queue counters) if it holds at least 303 104 states;
  *                          0: always whole chunks; n > 1: that minimum instead (tests). Same results. */
 #define NM_OPT_K3_SPLIT 4
+/*   NM_OPT_K3_LOUDQ (1)    k3_fast: when only a few lanes of a warp hold a sample whose delta has come within reach of |Z|
+ *                          (in practice: a sample in its last ~30 iterations before it escapes), those samples are handed to
+ *                          a per-level queue that a one-sample-per-lane launch with the exact comparisons in line finishes,
+ *                          and the warp keeps running without the per-iteration glitch filter; 0: the whole warp runs the
+ *                          filter for such segments. Same results; the tests run both. */
+#define NM_OPT_K3_LOUDQ 5
 NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
 /* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
 NM_API int nm_cancel(nm_ctx* ctx);

@@ -32,6 +32,17 @@
 // recurrence alone, 6.5 SASS instructions per sample-iteration instead of 11.2 — and only the escape filter is
 // looked at when the segment ends (profiles/r01p_*: full levels are entirely quiet, escape levels stay loud).
 //
+// Early export (K3F_LOUDQ): on the levels where samples escape nearly every warp holds a sample or two in its last
+// ~30 iterations, whose delta is within the bound's reach of |Z| — so nearly every segment ran loud for all 128
+// slots of the warp (profiles/r01p_cfg2_levels.txt: 1 045-1 405 Giter/s against 2 140 on full levels). Now, if only a
+// few lanes object to a quiet segment, their objecting slots are exported on the spot (state = the checkpoint the
+// segment would have started from) to the level's LOUD queue and parked; the warp runs the segment quiet. After the
+// level's k3_fast launches the loud queue is run by k3_level<REQUEUE, SCALED, FROM_FAST> (k3_perturb.cuh: one state per
+// lane, the exact comparisons in line, chunk tables in shared memory) to escape / glitch / iteration limit / chunk end —
+// the same steps and decisions in the same order, so rasters, glitch lists and executed-iteration counts do not change.
+// If many lanes object (the reference orbit itself passes near 0: every sample is loud at once) the warp runs the
+// segment with the per-iteration filter as before.
+//
 // (Two earlier versions replayed flagged blocks inside the warp; on the level where half of the
 // pixels escape that cost 3x, later 1.6x, the time of a full level, and latency-bound tail levels
 // ran 5x slower than the simple kernel — profiles/r01b_*.)
@@ -52,6 +63,13 @@ constexpr int K3F_THREADS = 256;
 #ifndef K3F_QUIET
 #define K3F_QUIET 1         // quiet segments (k3_filter.cuh: k3_seg_bound) run without the per-iteration glitch filter
 #endif
+#ifndef K3F_LOUDQ
+#define K3F_LOUDQ 1         // early export: a few non-quiet slots of an otherwise quiet warp go to the level's loud queue
+#endif
+#ifndef K3F_LOUDQ_MAX_LANES
+#define K3F_LOUDQ_MAX_LANES 8   // ... if at most this many lanes of the warp object to the quiet segment
+#endif
+constexpr int K3F_LOUD_FLAG = 0x40000000;   // in K3Slots::evj: the exported slot goes to the loud queue, not to k3_events
 #define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? K3F_CTAS_SCALED : K3F_CTAS_PLAIN)
 // shared-memory bytes of the per-chunk tables (2Z, filter entries, escape words) / of everything k3_fast<P> needs
 __host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
@@ -446,6 +464,35 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
           }
         }
 #endif
+#if K3F_LOUDQ && K3F_QUIET
+        if (p.loud) {
+          // lanes that object to a WHOLE segment because of the size of a delta (not because the segment is partial)
+          const bool objects = act && !quiet;
+          const unsigned obj = __ballot_sync(FULL_MASK, objects);
+          if (obj) {
+            const int T = (objects && n4 == 4) ? __ldg(&p.seg_hi[j >> 4]) : 0;
+            const unsigned can = __ballot_sync(FULL_MASK, objects && T > 0);
+            if (can == obj && __popc(obj) <= K3F_LOUDQ_MAX_LANES) {
+              if (objects) {
+#pragma unroll
+                for (int s = 0; s < P; ++s) {
+                  const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
+                  const int hs = max(__double2hiint(dr[s]) & keep, __double2hiint(di[s]) & keep);
+                  if ((live & (1u << s)) && hs >= T) {
+                    live &= ~(1u << s); expo |= 1u << s;
+                    slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
+                    slots.evj[s * K3F_THREADS + tid] = j | K3F_LOUD_FLAG;
+                    executed += (unsigned long long)(j - j_in);
+                    dr[s] = di[s] = er[s] = ei[s] = 0.0;
+                  }
+                }
+                m_hi = hi_max();
+                quiet = m_hi < T;   // true: every remaining delta is below the bound (parked slots are 0)
+              }
+            }
+          }
+        }
+#endif
         const bool warp_quiet = K3F_QUIET && __all_sync(FULL_MASK, quiet);
         if (act) {
           const int j_ck = j;
@@ -495,7 +542,12 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
 #pragma unroll
     for (int s = 0; s < P; ++s) {
       const bool toNext = (live >> s) & 1u;     // reached the chunk end alive
-      const bool toEvents = (expo >> s) & 1u;
+      bool toEvents = (expo >> s) & 1u;
+      int evj = toEvents ? slots.evj[s * K3F_THREADS + tid] : 0;
+#if K3F_LOUDQ && K3F_QUIET
+      const bool toLoud = toEvents && (evj & K3F_LOUD_FLAG);
+      if (toLoud) { toEvents = false; evj &= ~K3F_LOUD_FLAG; }
+#endif
       if (toNext) executed += (unsigned long long)(j - j_in);
       unsigned long long slot = warp_reserve(wk.next_count, toNext);
       if (toNext) {
@@ -506,10 +558,21 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
         const double2 d = slots.ck[s * K3F_THREADS + tid];
-        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = slots.evj[s * K3F_THREADS + tid];
+        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
         q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;  // an exported slot is parked: its exponent is never re-normalised
         events[slot] = q;
       }
+#if K3F_LOUDQ && K3F_QUIET
+      if (p.loud) {
+        slot = warp_reserve(p.loud_count, toLoud);
+        if (toLoud) {
+          const double2 d = slots.ck[s * K3F_THREADS + tid];
+          PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
+          q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;
+          p.loud[slot] = q;
+        }
+      }
+#endif
     }
   }
 

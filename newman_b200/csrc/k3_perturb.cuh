@@ -75,6 +75,10 @@ struct K3Params {
   unsigned long long split_min;   // levels with fewer states are never split
   PixState* restart;
   unsigned long long* restart_count;
+  // k3_fast: the level's "loud" queue (k3_fast.cuh, early export): slots whose delta has come within reach of |Z| are
+  // handed to k3_level<.., FROM_FAST = true>, which is launched on this queue after the level's k3_fast launches
+  PixState* loud;
+  unsigned long long* loud_count;
   unsigned long long* head;
   nm_escape* out;
   unsigned long long* ctr;
@@ -121,8 +125,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // MODE: NM_MODE_REQUEUE (flag glitches) or NM_MODE_REBASE (rebase when |z|^2 < |delta|^2).
 // SCALED: states carry a scale exponent (floatexp.cuh); bursts then stop at every index = 0 (mod 64),
 // where the state is re-normalised before the next step.
-template <int MODE, bool SCALED>
-__global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
+// FROM_FAST: the launch serves the fast path (k3_fast.cuh) — its input is the level's loud queue, and a state
+// that reaches the end of the orbit table is handed, as it is, to the event queue (k3_events rebases it and
+// carries it into the next sweep exactly like one exported by k3_fast) instead of the restart queue.
+template <int MODE, bool SCALED, bool FROM_FAST = false>
+__global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p, PixState* events = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
   const int jbase = p.k * CH;
@@ -309,6 +316,15 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
         active = false;
       }
     }
+    if (FROM_FAST) {
+      unsigned long long slot = warp_reserve(&p.ctr[CTR_EVENTS], rebase);
+      if (rebase) {
+        PixState s; s.dr = dr; s.di = di; s.pix = pix; s.j = j; s.off = off; s.e = e;
+        events[slot] = s;
+        active = false;
+        rebase = false;
+      }
+    }
     if (rebase) {
       // continue from the virtual iterate Z[0] = 0 with delta = z (exact algebra: z' = z^2 + c)
       rebased++;
@@ -346,6 +362,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
   }
   if (lane == 0) {
     if (executed) atomicAdd(&p.ctr[CTR_EXECUTED], executed);
+    if (FROM_FAST && executed) atomicAdd(&p.ctr[CTR_CHECKED], executed);
     if (rebased) atomicAdd(&p.ctr[CTR_REBASED], rebased);
   }
 }

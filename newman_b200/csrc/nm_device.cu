@@ -72,11 +72,13 @@ struct nm_ctx {
   // deep
   DevBuf seg32_hi;   // K3F_SEG32 experiment only
   DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, loud, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
   int opt_k3_split = 1;  // k3_fast: levels that follow an escape-heavy level run as 4 quarter-chunk launches
+  int opt_k3_loudq = 1;  // k3_fast: non-quiet slots of an otherwise quiet warp go to the level's loud queue (k3_level)
+  int occ_k3l[2] = {0, 0};
   long long opt_k3_finish_max = K3_FINISH_MAX_STATES;  // frames / remainders up to this many states: k3_finish
   int occ_k3f[2] = {0, 0}, occ_k3fs[2] = {0, 0};
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
@@ -316,13 +318,15 @@ int launch_deep(nm_ctx* ctx) {
   const int K = ctx->K;
   cudaStream_t st = ctx->stream;
   unsigned long long* qctr = ctx->qctr.as<unsigned long long>();
-  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | rcount[2] | carry_count[2]
+  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | loudcount[K+2] | loudhead[K+2] | rcount[2] | carry_count[2]
   // (head: per level, per quarter-chunk launch, one deal cursor for the 4-states-per-lane waves and one for the
   //  one-state-per-lane remainder: k3_fast.cuh)
   unsigned long long* qcount = qctr;
   unsigned long long* head = qctr + (K + 2);
   unsigned long long* subcount = qctr + 9 * (K + 2);
-  unsigned long long* rcount = qctr + 13 * (K + 2);
+  unsigned long long* loudcount = qctr + 13 * (K + 2);   // per level: states k3_fast exported early (k3_fast.cuh: K3F_LOUDQ)
+  unsigned long long* loudhead = qctr + 14 * (K + 2);    // ... and the deal cursor of the k3_level launch that runs them
+  unsigned long long* rcount = qctr + 15 * (K + 2);
   unsigned long long* ccount = rcount + 2;
   unsigned long long* ctr = ctx->ctr.as<unsigned long long>();
 
@@ -481,7 +485,7 @@ int launch_deep(nm_ctx* ctx) {
       ctx->stats.kernel_launches += 2;
       NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(nbins + 2) * sizeof(unsigned), st));
     }
-    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 13 * (K + 2) * sizeof(unsigned long long), st));
+    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 15 * (K + 2) * sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&rcount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ccount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_EVENTS], 0, sizeof(unsigned long long), st));
@@ -506,6 +510,9 @@ int launch_deep(nm_ctx* ctx) {
       p.tmp[0] = ctx->rq[0].as<PixState>(); p.tmp[1] = ctx->rq[1].as<PixState>();   // idle in the fast path
       p.split_min = ctx->opt_k3_split > 1 ? (unsigned long long)ctx->opt_k3_split : K3F_SPLIT_MIN;
       p.sub_count = (ctx->opt_k3_split && (unsigned long long)ctx->W >= p.split_min) ? &subcount[K3F_SUBS * k] : nullptr;
+      const bool loudq = fast && ctx->opt_k3_loudq && ctx->loud.p != nullptr;
+      p.loud = loudq ? ctx->loud.as<PixState>() : nullptr;
+      p.loud_count = &loudcount[k];
       cudaError_t e = cudaSuccess;
       PixState* evq = ctx->events.as<PixState>();
       if (fast) {   // K3F_SUBS launches per level; all but the first return at once unless the level is split (K3Work)
@@ -519,6 +526,19 @@ int launch_deep(nm_ctx* ctx) {
           else k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
           e = cudaGetLastError();
           if (sub) ctx->stats.kernel_launches++;
+        }
+        if (loudq && e == cudaSuccess) {
+          // the level's loud queue (slots k3_fast exported early because their delta came within reach of |Z|: mostly
+          // samples in their last ~30 iterations): one state per lane with the exact comparisons in line
+          K3Params pl = p;
+          pl.cur = ctx->loud.as<PixState>(); pl.cur_count = &loudcount[k];
+          pl.fresh_off = nullptr; pl.head = &loudhead[k];
+          const size_t smem_l = (size_t)(CH + 4) * (sizeof(double2) + sizeof(double));
+          const unsigned bl = (unsigned)(ctx->sm_count * (scaled ? ctx->occ_k3l[1] : ctx->occ_k3l[0]));
+          if (scaled) k3_level<NM_MODE_REQUEUE, true, true><<<bl, K3_THREADS, smem_l, st>>>(pl, evq);
+          else k3_level<NM_MODE_REQUEUE, false, true><<<bl, K3_THREADS, smem_l, st>>>(pl, evq);
+          e = cudaGetLastError();
+          ctx->stats.kernel_launches++;
         }
       }
       else if (scaled) e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, true>(ctx, p, blocks, smem)
@@ -656,6 +676,8 @@ int nm_create(int device, nm_ctx** out) {
   NM_K3_SETUP((k3_level<NM_MODE_REBASE, false>), K3_THREADS, ctx->occ_k3[1]);
   NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, true>), K3_THREADS, ctx->occ_k3s[0]);
   NM_K3_SETUP((k3_level<NM_MODE_REBASE, true>), K3_THREADS, ctx->occ_k3s[1]);
+  NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, false, true>), K3_THREADS, ctx->occ_k3l[0]);
+  NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, true, true>), K3_THREADS, ctx->occ_k3l[1]);
 #undef NM_K3_SETUP
 #define NM_K3_SETUP(fn, P, occ_out)                                                                             \
   {                                                                                                             \
@@ -685,7 +707,7 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->seg32_hi, &ctx->eps_max,
                     &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->loud, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
                     &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -710,6 +732,7 @@ int nm_set_option(nm_ctx* ctx, int key, int value) {
       if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, NM_EINVAL, "NM_OPT_K3_GROUP must be 0, 1, 2 or 4");
       ctx->opt_k3_group = value;
       return NM_OK;
+    case NM_OPT_K3_LOUDQ: ctx->opt_k3_loudq = value ? 1 : 0; return NM_OK;
     case NM_OPT_K3_SPLIT:
       if (value < 0) return fail(ctx, NM_EINVAL, "NM_OPT_K3_SPLIT must be >= 0");
       ctx->opt_k3_split = value;
@@ -823,10 +846,11 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     NM_CUDA(ctx, ctx->q[i].ensure(Wn * sizeof(PixState)));
     NM_CUDA(ctx, ctx->rq[i].ensure(Wn * sizeof(PixState)));
   }
-  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(13 * (K + 2) + 4) * sizeof(unsigned long long)));
+  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(15 * (K + 2) + 4) * sizeof(unsigned long long)));
   NM_CUDA(ctx, ctx->rq_pix.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->rq_iter.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->events.ensure(Wn * sizeof(PixState)));
+  if (ctx->opt_k3_loudq) NM_CUDA(ctx, ctx->loud.ensure(Wn * sizeof(PixState)));
 
   cudaStream_t s = ctx->stream;
   NM_CUDA(ctx, cudaMemsetAsync(ctx->Z.p, 0, (size_t)(J1 + 8) * sizeof(double2), s));

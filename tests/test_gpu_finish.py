@@ -127,3 +127,34 @@ def test_split_levels_vs_oraclep(kat, group):
         assert launches[1] > launches[0]
     finally:
         dev.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("group", [4, 2])
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D90", "KAT-S"])
+def test_loud_queue_vs_oraclep(kat, group):
+    """NM_OPT_K3_LOUDQ: the few samples of a warp whose delta has come within reach of |Z| (their last ~30
+    iterations) are exported to the level's loud queue and finished by k3_level<REQUEUE, SCALED, FROM_FAST> while
+    the warp runs on without the per-iteration filter (k3_fast.cuh). Rasters, glitch lists and executed-iteration
+    counts must not change — plain, floatexp series and scaled forms, whole and split levels."""
+    t, er, ei = kat_inputs(kat)
+    dev = newman_b200.Device(0)
+    try:
+        dev.set_option(L.OPT_K3_FINISH_MAX, 0)
+        dev.set_option(L.OPT_K3_GROUP, group)
+        base = p_render_deep(t, er, ei, mode=0)
+        checked = {}
+        for loudq in (0, 1):
+            dev.set_option(L.OPT_K3_LOUDQ, loudq)
+            for split in (0, 2):
+                dev.set_option(L.OPT_K3_SPLIT, split)
+                gs = check(dev, t, er, ei, 0, base)
+                checked[(loudq, split)] = gs["checked_steps"]
+                ts, mr, mi = t.floatexp(er, ei)
+                check(dev, t.floatexp(), er, ei, 0, base)
+                check(dev, ts, mr, mi, 0, base)
+        print(kat, group, "checked steps", checked)
+        if kat == "KAT-S":   # ~2000 chaotic iterations past the series: the loud queue is really used
+            assert checked[(1, 0)] != checked[(0, 0)]
+    finally:
+        dev.close()
