@@ -75,10 +75,10 @@ NM_API int nm_sync(nm_ctx* ctx);
  *                          0: always whole chunks; n > 1: that minimum instead (tests). Same results. */
 #define NM_OPT_K3_SPLIT 4
 /*   NM_OPT_K3_LOUDQ (1)    k3_fast: when only a few lanes of a warp hold a sample whose delta has come within reach of |Z|
- *                          (in practice: a sample in its last ~30 iterations before it escapes), those samples are handed to
- *                          a per-level queue that a one-sample-per-lane launch with the exact comparisons in line finishes,
- *                          and the warp keeps running without the per-iteration glitch filter; 0: the whole warp runs the
- *                          filter for such segments. Same results; the tests run both. */
+ *                          (in practice: a sample in its last ~30 iterations before it escapes), those samples are exported
+ *                          early to the kernel that finishes exported states with the exact comparisons (k3_finish), and the
+ *                          warp keeps running without the per-iteration glitch filter; 0: the whole warp runs the filter for
+ *                          such segments. Same results; the tests run both. */
 #define NM_OPT_K3_LOUDQ 5
 NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
 /* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
@@ -252,9 +252,6 @@ NM_API int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int
  * bounds, e_max >= |eps| of every sample. Returns the high word T: a state with hi(|dr|) < T and hi(|di|) < T at j0
  * cannot satisfy the glitch test at any of the indices j0+1 .. j0+16 (0 = no state is exempt). */
 NM_API int32_t nm_k3_seg_bound(const double* z, const double* gb, int j0, int jmax, double e_max);
-/* The same bound over 32 iterations (indices j0+1 .. j0+32): the table of the K3F_SEG32 build option (an experiment, off by
- * default: k3_fast.cuh). */
-NM_API int32_t nm_k3_seg_bound32(const double* z, const double* gb, int j0, int jmax, double e_max);
 NM_API int nm_device_info(nm_ctx* ctx, int* sm_count, int* sm_clock_khz, size_t* hbm_bytes, char* name, int cap);
 
 /* ==== view level: the drop-in class through C ===================================================

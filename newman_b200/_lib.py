@@ -91,7 +91,6 @@ DEVICE_API = {
     "nm_fp64_peak": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "nm_k3_filter_entry": (None, [C.c_double, C.c_double, C.c_double, C.POINTER(C.c_uint32)]),
     "nm_k3_seg_bound": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double]),
-    "nm_k3_seg_bound32": (C.c_int32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double]),
     "nm_k3_filter_fires": (C.c_int, [C.POINTER(C.c_uint32), C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_int)]),
     "nm_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t),

@@ -62,7 +62,7 @@ struct K2Params {
   const int2* Ae;       // ... and binary exponents (floatexp mode only)
   const int2* Be;
   const int2* Ce;
-  const double2* Z;     // Z[0]=0, Z[j]=X[j-1] (truncated doubles)
+  const double2* Xhi;   // [M] X[i] descended (truncated doubles, complex.h:33-35): what phase 2 adds d to
   const double2* Xlo;   // [M] low parts of X[i]
   int M, N;
   double tol;
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
         // ---- phase 2: did the series-approximated point already escape? -------------------------
         int found = L - 1;
         Cplx d = se.d_at(found);
-        double2 xh = p.Z[found + 1], xl = p.Xlo[found];
+        double2 xh = p.Xhi[found], xl = p.Xlo[found];
         double yr = trunc_add3(xh.x, xl.x, d.re);
         double yi = trunc_add3(xh.y, xl.y, d.im);
         double mag = yr * yr + yi * yi;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
           int low = 0, high = L - 1, mid = L / 2;
           while (low <= high) {
             Cplx dm = se.d_at(mid);
-            double2 mh = p.Z[mid + 1], ml = p.Xlo[mid];
+            double2 mh = p.Xhi[mid], ml = p.Xlo[mid];
             double mr = trunc_add3(mh.x, ml.x, dm.re);
             double mi = trunc_add3(mh.y, ml.y, dm.im);
             double mm = mr * mr + mi * mi;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_series(K2Params p) {
             mid = (low + high) / 2;
           }
           d = se.d_at(found);
-          xh = p.Z[found + 1]; xl = p.Xlo[found];
+          xh = p.Xhi[found]; xl = p.Xlo[found];
           yr = trunc_add3(xh.x, xl.x, d.re);
           yi = trunc_add3(xh.y, xl.y, d.im);
           mag = yr * yr + yi * yi;

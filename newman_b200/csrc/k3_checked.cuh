@@ -9,6 +9,15 @@
 
 namespace nm {
 
+struct __align__(16) PixState {   // a K3 state in a queue
+  double dr, di;
+  int32_t pix;
+  int32_t j;
+  int32_t off;
+  int32_t e;   // scale exponent: delta = (dr, di) * 2^e (0 in plain frames)
+};
+typedef PixState PixStateRec;
+
 struct EpsTab {            // separable pixel offsets: per column / per row
   const double* re;        // [nc] doubles, or mantissas (0.5 <= |m| < 1) when re_e != nullptr
   const double* im;        // [nr]

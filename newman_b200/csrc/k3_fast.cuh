@@ -21,10 +21,10 @@
 // orbit table less than 4 steps away). Exported pixels are parked on the reference orbit itself
 // (delta = eps = 0, which stays 0 and never flags) until the lane's pass through the chunk ends, and
 // are appended to the event queue with the same warp-aggregated reservation as the survivors that
-// move on to the next chunk. k3_events then replays at most 24 checked steps per exported pixel with
-// the exact double comparisons — escape (+ smoothing), glitch (-> re-queue list), iteration limit,
-// rebase at the end of the orbit, or "false alarm" (-> carried into the next sweep, index again a
-// multiple of 4). Every decision is therefore the one k3_perturb.cuh and the oracle take.
+// move on to the next chunk. After the sweep k3_finish<REQUEUE, SCALED, EVENTS> (k3_finish.cuh) runs every
+// exported state to its end with the exact double comparisons — escape (+ smoothing), glitch (-> re-queue
+// list), iteration limit, rebase at the end of the orbit and on from Z[0]; a false alarm simply keeps
+// iterating there. Every decision is therefore the one k3_perturb.cuh and the oracle take.
 //
 // Quiet segments: most of a sample's life its delta is far too small to come near -Z within the next 16 steps. A
 // per-segment bound on delta's high words (k3_filter.cuh: k3_seg_bound, rebuilt per frame from the orbit and the
@@ -32,16 +32,15 @@
 // recurrence alone, 6.5 SASS instructions per sample-iteration instead of 11.2 — and only the escape filter is
 // looked at when the segment ends (profiles/r01p_*: full levels are entirely quiet, escape levels stay loud).
 //
-// Early export (K3F_LOUDQ): on the levels where samples escape nearly every warp holds a sample or two in its last
-// ~30 iterations, whose delta is within the bound's reach of |Z| — so nearly every segment ran loud for all 128
-// slots of the warp (profiles/r01p_cfg2_levels.txt: 1 045-1 405 Giter/s against 2 140 on full levels). Now, if only a
-// few lanes object to a quiet segment, their objecting slots are exported on the spot (state = the checkpoint the
-// segment would have started from) to the level's LOUD queue and parked; the warp runs the segment quiet. After the
-// level's k3_fast launches the loud queue is run by k3_level<REQUEUE, SCALED, FROM_FAST> (k3_perturb.cuh: one state per
-// lane, the exact comparisons in line, chunk tables in shared memory) to escape / glitch / iteration limit / chunk end —
-// the same steps and decisions in the same order, so rasters, glitch lists and executed-iteration counts do not change.
-// If many lanes object (the reference orbit itself passes near 0: every sample is loud at once) the warp runs the
-// segment with the per-iteration filter as before.
+// Early export (K3F_LOUDQ, NM_OPT_K3_LOUDQ): on the levels where samples escape nearly every warp holds a sample or
+// two in its last ~30 iterations, whose delta is within the bound's reach of |Z| — so nearly every segment ran loud
+// for all 128 slots of the warp (profiles/r01p_cfg2_levels.txt: 1 045-1 405 Giter/s against 2 140 on full levels).
+// Now, if only a few lanes object to a quiet segment, their objecting slots are exported on the spot (state = the
+// checkpoint the segment would have started from) and parked; the warp runs the segment quiet, and k3_finish takes
+// the exported state through its last iterations one checked step at a time — the same steps and decisions in the
+// same order, so rasters, glitch lists and executed-iteration counts do not change. If many lanes object (the
+// reference orbit itself passes near 0: every sample is loud at once) the warp runs the segment with the
+// per-iteration filter as before.
 //
 // (Two earlier versions replayed flagged blocks inside the warp; on the level where half of the
 // pixels escape that cost 3x, later 1.6x, the time of a full level, and latency-bound tail levels
@@ -64,63 +63,17 @@ constexpr int K3F_THREADS = 256;
 #define K3F_QUIET 1         // quiet segments (k3_filter.cuh: k3_seg_bound) run without the per-iteration glitch filter
 #endif
 #ifndef K3F_LOUDQ
-#define K3F_LOUDQ 1         // early export: a few non-quiet slots of an otherwise quiet warp go to the level's loud queue
+#define K3F_LOUDQ 1         // early export: the few non-quiet slots of an otherwise quiet warp are exported on the spot
 #endif
 #ifndef K3F_LOUDQ_MAX_LANES
 #define K3F_LOUDQ_MAX_LANES 8   // ... if at most this many lanes of the warp object to the quiet segment
 #endif
-constexpr int K3F_LOUD_FLAG = 0x40000000;   // in K3Slots::evj: the exported slot goes to the loud queue, not to k3_events
 #define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? K3F_CTAS_SCALED : K3F_CTAS_PLAIN)
 // shared-memory bytes of the per-chunk tables (2Z, filter entries, escape words) / of everything k3_fast<P> needs
 __host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
   return (((size_t)(CH + 4) * (sizeof(double2) + sizeof(int4) + sizeof(int32_t))) + 15) & ~(size_t)15;
 }
 constexpr unsigned long long K3F_SPLIT_MIN = 4ULL * 148 * 2 * 256;   // levels with fewer states are not split (4 x K3F_SPARSE_MAX)
-constexpr int K3_EVENT_BUDGET = 252;  // extra checked steps k3_events grants a freshly rebased state (multiple of 4)
-
-template <bool SCALED>
-__global__ void __launch_bounds__(256) k3_events(CheckedParams p, EpsTab eps_tab,
-                                                 const PixState* events, const unsigned long long* count,
-                                                 FreshArrays carry, unsigned long long* carry_count, unsigned* hist) {
-  const unsigned long long n = *count;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  unsigned long long executed = 0;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    PixState e = events[i];
-    EpsVal<SCALED> eps;
-    eps.load(eps_tab, e.pix);
-    int steps = 0;
-    // 24 = a whole segment of k3_fast (the event lies at most 16 steps past the checkpoint) + two blocks: a
-    // candidate of the escape filter whose |z|^2 is still below 2^20 at the segment end escapes within the
-    // next step or two (|z| > 700 squares), so it is finished here and not carried
-    bool cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, K3F_SEG32 ? 40 : 24, &steps);
-    // A state that was just rebased onto the start of the orbit (it outlived the reference: |z| is
-    // large) nearly always escapes within a few steps: finish it here rather than carrying it through
-    // another sweep of (mostly empty) level launches. Same steps, same decisions, same order.
-    if (cont && e.j == 0) {
-      int more = 0;
-      cont = advance_checked<SCALED>(p, e.pix, eps, e.off, e.dr, e.di, e.e, e.j, K3_EVENT_BUDGET, &more);
-      steps += more;
-    }
-    if (cont) {
-      // carried into the next sweep (index is a multiple of 4 again: 0 after a rebase, checkpoint + 24 else)
-      unsigned long long slot = atomicAdd(carry_count, 1ULL);
-      carry.d[slot] = make_double2(e.dr, e.di);
-      carry.j[slot] = e.j;
-      carry.off[slot] = e.off;
-      carry.pix[slot] = e.pix;
-      if (SCALED) carry.e[slot] = e.e;
-      atomicAdd(&hist[e.j], 1u);
-      atomicMin(&p.ctr[CTR_MINJ], (unsigned long long)e.j);
-    }
-    executed += (unsigned long long)steps;
-  }
-  for (int o = 16; o; o >>= 1) executed += __shfl_xor_sync(FULL_MASK, executed, o);
-  if ((threadIdx.x & 31) == 0 && executed) {
-    atomicAdd(&p.ctr[CTR_EXECUTED], executed);
-    atomicAdd(&p.ctr[CTR_CHECKED], executed);
-  }
-}
 
 // One branch-free block of 4 iterations for the P slots of a lane, in place. jrel = the block's start index
 // relative to the chunk. bad[s] |= the glitch filter (k3_filter.cuh) fired for slot s in this block.
@@ -231,7 +184,7 @@ __device__ __forceinline__ K3Work k3f_work(const K3Params& p) {
 // Layout [field][slot][thread]: conflict-free for the warp-wide accesses.
 template <int P>
 struct K3Slots {
-  double2* ck;     // delta at the last checkpoint = the state an exported slot hands to k3_events
+  double2* ck;     // delta at the last checkpoint = the state an exported slot hands to k3_finish
   int32_t* pix;
   int32_t* off;
   int32_t* evj;    // orbit index of the checkpoint an exported slot was rolled back to
@@ -253,7 +206,7 @@ struct K3Slots {
 // looked at once per segment (the glitch flags are sticky; the escape filter looks at the segment's last delta:
 // a slot that escaped earlier in the segment has |delta| growing without bound since — inf or NaN at worst,
 // whose high words pass the filter too, and which disturb nobody: slots do not interact). A flagged slot is
-// exported with its checkpoint state, so k3_events replays at most 16 steps to reach the event.
+// exported with its checkpoint state, so k3_finish replays at most 16 steps to reach the event.
 // Against the one-block-at-a-time form (profiles/r01k_*: 250 instructions per 96 FP64, of which 34 register
 // moves for the roll-back copy and 18 for the per-block escape test) this leaves ~150.
 //
@@ -434,38 +387,8 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
           if (n4 > nb - b) n4 = nb - b;
           quiet = K3F_QUIET && n4 == 4 && m_hi < __ldg(&p.seg_hi[j >> 4]);
         }
-#if K3F_SEG32
-        // EXPERIMENT (default off; the bound is validated on the CPU — tests/test_k3_filter.py —, this path has not run on
-        // a GPU yet): where the 32-step bound admits every lane of the warp, run two segments on one checkpoint, i.e. half
-        // the bookkeeping (~70 instructions) per 16 iterations. k3_events grants 40 steps instead of 24 accordingly.
-        {
-          bool quiet32 = true;
-          if (act) quiet32 = quiet && (j & 31) == 0 && nb - b >= 8 && m_hi < __ldg(&p.seg32_hi[j >> 5]);
-          if (__all_sync(FULL_MASK, quiet32)) {
-            if (act) {
-              const int j_ck = j;
-#pragma unroll
-              for (int s = 0; s < P; ++s)
-                if (live & (1u << s)) slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) k3_block_quiet<P, SCALED>(dr, di, er, ei, S, sZ2, j - jbase + 4 * q);
-              j += 32;
-              b += 8;
-              m_hi = hi_max();
-              const int esc_hi = sE[j - jbase];
-              if (m_hi >= esc_hi) {
-                bool none[P];
-#pragma unroll
-                for (int s = 0; s < P; ++s) none[s] = false;
-                export_flagged(none, esc_hi, j_ck);
-              }
-            }
-            continue;
-          }
-        }
-#endif
 #if K3F_LOUDQ && K3F_QUIET
-        if (p.loud) {
+        if (p.early_export) {
           // lanes that object to a WHOLE segment because of the size of a delta (not because the segment is partial)
           const bool objects = act && !quiet;
           const unsigned obj = __ballot_sync(FULL_MASK, objects);
@@ -481,7 +404,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
                   if ((live & (1u << s)) && hs >= T) {
                     live &= ~(1u << s); expo |= 1u << s;
                     slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
-                    slots.evj[s * K3F_THREADS + tid] = j | K3F_LOUD_FLAG;
+                    slots.evj[s * K3F_THREADS + tid] = j;
                     executed += (unsigned long long)(j - j_in);
                     dr[s] = di[s] = er[s] = ei[s] = 0.0;
                   }
@@ -542,12 +465,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
 #pragma unroll
     for (int s = 0; s < P; ++s) {
       const bool toNext = (live >> s) & 1u;     // reached the chunk end alive
-      bool toEvents = (expo >> s) & 1u;
-      int evj = toEvents ? slots.evj[s * K3F_THREADS + tid] : 0;
-#if K3F_LOUDQ && K3F_QUIET
-      const bool toLoud = toEvents && (evj & K3F_LOUD_FLAG);
-      if (toLoud) { toEvents = false; evj &= ~K3F_LOUD_FLAG; }
-#endif
+      const bool toEvents = (expo >> s) & 1u;
       if (toNext) executed += (unsigned long long)(j - j_in);
       unsigned long long slot = warp_reserve(wk.next_count, toNext);
       if (toNext) {
@@ -558,21 +476,10 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
         const double2 d = slots.ck[s * K3F_THREADS + tid];
-        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
+        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = slots.evj[s * K3F_THREADS + tid];
         q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;  // an exported slot is parked: its exponent is never re-normalised
         events[slot] = q;
       }
-#if K3F_LOUDQ && K3F_QUIET
-      if (p.loud) {
-        slot = warp_reserve(p.loud_count, toLoud);
-        if (toLoud) {
-          const double2 d = slots.ck[s * K3F_THREADS + tid];
-          PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
-          q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;
-          p.loud[slot] = q;
-        }
-      }
-#endif
     }
   }
 

@@ -103,7 +103,7 @@ __host__ __device__ __forceinline__ double k3f_from_hi(uint32_t hi) {
 }
 
 // Z[j] = (zr[j], zi[j]) and gb[j] for j <= jmax (the last valid table index); e_max >= |eps| of every sample.
-// NS = steps the bound covers (16: k3_fast's segments; 32: the double segments of the K3F_SEG32 experiment).
+// NS = steps the bound covers (16: k3_fast's segments).
 template <int NS>
 __host__ __device__ inline int32_t k3_seg_bound_n(const double* zr, const double* zi, const double* gb, int zstride, int j0, int jmax,
                                                   double e_max) {

@@ -19,21 +19,38 @@ constexpr int K3_FINISH_THREADS = 128;
 constexpr int K3_FINISH_BURST = 8;
 constexpr long long K3_FINISH_MAX_STATES = 65536;   // above this the level kernels win (measured: DESIGN.md)
 
-template <int MODE, bool SCALED>
+// EVENTS = true: the states are the PixState records k3_fast exported (k3_fast.cuh) — slots a filter fired for,
+// slots at a limit, and the slots exported early because their delta came within reach of |Z| — and every one of
+// them is finished here; nothing is carried into another sweep.
+template <int MODE, bool SCALED, bool EVENTS = false>
 __global__ void __launch_bounds__(K3_FINISH_THREADS) k3_finish(CheckedParams p, EpsTab eps_tab, FreshArrays f,
-                                                              const unsigned long long* count, long long n_max) {
+                                                              const unsigned long long* count, long long n_max,
+                                                              const PixStateRec* events = nullptr) {
   __shared__ double2 park[K3_FINISH_BURST][K3_FINISH_THREADS];   // the burst's deltas, one column per thread
   const unsigned long long n = count ? *count : (unsigned long long)n_max;
   unsigned long long executed = 0, rebased = 0;
   for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < n;
        w += (unsigned long long)gridDim.x * blockDim.x) {
-    int j = f.j[w];
-    if (j < 0) continue;   // K2 finished this sample itself
-    const int pix = f.pix[w];
-    int off = f.off[w];
-    const double2 d0 = f.d[w];
-    double dr = d0.x, di = d0.y;
-    int e = SCALED ? f.e[w] : 0;
+    int j, pix_, off, e;
+    double dr, di;
+    if (EVENTS) {
+      const PixStateRec q = events[w];
+      j = q.j; pix_ = q.pix; off = q.off; dr = q.dr; di = q.di; e = SCALED ? q.e : 0;
+    } else {
+      j = f.j[w];
+      if (j < 0) continue;   // K2 finished this sample itself
+      pix_ = f.pix[w];
+      off = f.off[w];
+      const double2 d0 = f.d[w];
+      dr = d0.x; di = d0.y;
+      e = SCALED ? f.e[w] : 0;
+    }
+    const int pix = pix_;
+    if (EVENTS && j + off + 1 >= p.N) {   // exported AT its iteration limit: the last step's decision, in the oracle's order
+      nm_escape v; v.iterations = p.N; v.smoothing = 0.0f;
+      p.out[pix] = v;
+      continue;
+    }
     EpsVal<SCALED> eps;
     eps.load(eps_tab, pix);
     double S = 1.0, er = eps.r0, ei = eps.i0;

@@ -32,17 +32,7 @@
 
 namespace nm {
 
-struct __align__(16) PixState {
-  double dr, di;
-  int32_t pix;
-  int32_t j;
-  int32_t off;
-  int32_t e;   // scale exponent: delta = (dr, di) * 2^e (0 in plain frames)
-};
 
-#ifndef K3F_SEG32
-#define K3F_SEG32 0     // experiment (unmeasured, see k3_fast.cuh): quiet double segments of 32 iterations
-#endif
 
 struct K3Params {
   const double2* Z;      // [Jmax+1 (+pad)]
@@ -52,9 +42,6 @@ struct K3Params {
   const int4* filt;      // k3_fast: glitch-filter entries (k3_filter.cuh: K3Filt)
   const int32_t* esc_hi; // k3_fast: escape-filter high words
   const int32_t* seg_hi; // k3_fast: per 16-iteration segment, the quiet bound on delta's high words (k3_seg_bound)
-#if K3F_SEG32
-  const int32_t* seg32_hi; // experiment: the same bound over 32 iterations, per index = 0 (mod 32)
-#endif
   int Jmax;              // last valid table index
   int N, CH, k;
   EpsTab eps;
@@ -75,10 +62,7 @@ struct K3Params {
   unsigned long long split_min;   // levels with fewer states are never split
   PixState* restart;
   unsigned long long* restart_count;
-  // k3_fast: the level's "loud" queue (k3_fast.cuh, early export): slots whose delta has come within reach of |Z| are
-  // handed to k3_level<.., FROM_FAST = true>, which is launched on this queue after the level's k3_fast launches
-  PixState* loud;
-  unsigned long long* loud_count;
+  int early_export;      // k3_fast: export the few non-quiet slots of an otherwise quiet warp (k3_fast.cuh: K3F_LOUDQ)
   unsigned long long* head;
   nm_escape* out;
   unsigned long long* ctr;
@@ -125,11 +109,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // MODE: NM_MODE_REQUEUE (flag glitches) or NM_MODE_REBASE (rebase when |z|^2 < |delta|^2).
 // SCALED: states carry a scale exponent (floatexp.cuh); bursts then stop at every index = 0 (mod 64),
 // where the state is re-normalised before the next step.
-// FROM_FAST: the launch serves the fast path (k3_fast.cuh) — its input is the level's loud queue, and a state
-// that reaches the end of the orbit table is handed, as it is, to the event queue (k3_events rebases it and
-// carries it into the next sweep exactly like one exported by k3_fast) instead of the restart queue.
-template <int MODE, bool SCALED, bool FROM_FAST = false>
-__global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p, PixState* events = nullptr) {
+template <int MODE, bool SCALED>
+__global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CH = p.CH;
   const int jbase = p.k * CH;
@@ -316,15 +297,6 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p, PixState* eve
         active = false;
       }
     }
-    if (FROM_FAST) {
-      unsigned long long slot = warp_reserve(&p.ctr[CTR_EVENTS], rebase);
-      if (rebase) {
-        PixState s; s.dr = dr; s.di = di; s.pix = pix; s.j = j; s.off = off; s.e = e;
-        events[slot] = s;
-        active = false;
-        rebase = false;
-      }
-    }
     if (rebase) {
       // continue from the virtual iterate Z[0] = 0 with delta = z (exact algebra: z' = z^2 + c)
       rebased++;
@@ -362,7 +334,6 @@ __global__ void __launch_bounds__(K3_THREADS) k3_level(K3Params p, PixState* eve
   }
   if (lane == 0) {
     if (executed) atomicAdd(&p.ctr[CTR_EXECUTED], executed);
-    if (FROM_FAST && executed) atomicAdd(&p.ctr[CTR_CHECKED], executed);
     if (rebased) atomicAdd(&p.ctr[CTR_REBASED], rebased);
   }
 }

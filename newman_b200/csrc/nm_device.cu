@@ -70,15 +70,13 @@ struct nm_ctx {
   int paldev_n = 0;  // entries of the device-generated palette in paldev (0: none)
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
-  DevBuf seg32_hi;   // K3F_SEG32 experiment only
-  DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, loud, aexp, bexp, cexp, cre_e, cim_e;
+  DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xhi, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
   int opt_k3_split = 1;  // k3_fast: levels that follow an escape-heavy level run as 4 quarter-chunk launches
-  int opt_k3_loudq = 1;  // k3_fast: non-quiet slots of an otherwise quiet warp go to the level's loud queue (k3_level)
-  int occ_k3l[2] = {0, 0};
+  int opt_k3_loudq = 1;  // k3_fast: the few non-quiet slots of an otherwise quiet warp are exported early (k3_fast.cuh)
   long long opt_k3_finish_max = K3_FINISH_MAX_STATES;  // frames / remainders up to this many states: k3_finish
   int occ_k3f[2] = {0, 0}, occ_k3fs[2] = {0, 0};
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
@@ -114,6 +112,18 @@ int fail(nm_ctx* ctx, int code, const char* fmt, ...) {
 
 // Per-index tables derived from the orbit: the glitch bound (and its high word for k3_level), and for
 // k3_fast 2*Z[j] and the candidate-filter entries of k3_filter.cuh.
+// The orbit table the perturbation kernels pair delta with: X rounded TO NEAREST, Z[i + 1] = RN(x_hi[i] + x_lo[i]).
+// x_hi is the truncated double the reference's descend() yields (complex.h:33-35) and phases 1-2 need; iterating
+// against it biases every factor 2Z + delta the same way and the relative error of delta grows linearly with the
+// iteration count (5e-13 after cfg2's 7 000 iterations instead of 5e-15), which moves the escape count of samples whose
+// last few hundred iterations are chaotic (oracle/oracle_p.c makes the same table).
+__global__ void k_round_orbit(double2* Z1, const double2* xhi, const double2* xlo, int M) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const double2 h = xhi[i], l = xlo[i];
+  Z1[i] = make_double2(h.x + l.x, h.y + l.y);
+}
+
 __global__ void k_glitch_bounds(const double2* Z, double* gb, int32_t* ghi, double2* Z2, K3Filt* filt, int32_t* esc_hi,
                                 int n, int pad_n, double gtol, int zero_last) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,14 +179,6 @@ __global__ void k_seg_bounds(const double2* Z, const double* gb, int jmax, const
   seg_hi[s] = k3_seg_bound(z, z + 1, gb, 2, 16 * s, jmax, *e_max);
 }
 
-#if K3F_SEG32
-__global__ void k_seg_bounds32(const double2* Z, const double* gb, int jmax, const double* e_max, int32_t* seg_hi, int n_seg) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_seg) return;
-  const double* z = (const double*)Z;
-  seg_hi[s] = k3_seg_bound_n<32>(z, z + 1, gb, 2, 32 * s, jmax, *e_max);
-}
-#endif
 
 __global__ void k_apply_fixups(nm_escape* out, const int32_t* pix, const float* val, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,15 +320,13 @@ int launch_deep(nm_ctx* ctx) {
   const int K = ctx->K;
   cudaStream_t st = ctx->stream;
   unsigned long long* qctr = ctx->qctr.as<unsigned long long>();
-  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | loudcount[K+2] | loudhead[K+2] | rcount[2] | carry_count[2]
+  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | rcount[2] | carry_count[2]
   // (head: per level, per quarter-chunk launch, one deal cursor for the 4-states-per-lane waves and one for the
   //  one-state-per-lane remainder: k3_fast.cuh)
   unsigned long long* qcount = qctr;
   unsigned long long* head = qctr + (K + 2);
   unsigned long long* subcount = qctr + 9 * (K + 2);
-  unsigned long long* loudcount = qctr + 13 * (K + 2);   // per level: states k3_fast exported early (k3_fast.cuh: K3F_LOUDQ)
-  unsigned long long* loudhead = qctr + 14 * (K + 2);    // ... and the deal cursor of the k3_level launch that runs them
-  unsigned long long* rcount = qctr + 15 * (K + 2);
+  unsigned long long* rcount = qctr + 13 * (K + 2);
   unsigned long long* ccount = rcount + 2;
   unsigned long long* ctr = ctx->ctr.as<unsigned long long>();
 
@@ -350,7 +350,7 @@ int launch_deep(nm_ctx* ctx) {
   K2Params k2;
   k2.A = ctx->a.as<double2>(); k2.B = ctx->b.as<double2>(); k2.C = ctx->c.as<double2>();
   k2.Ae = ctx->aexp.as<int2>(); k2.Be = ctx->bexp.as<int2>(); k2.Ce = ctx->cexp.as<int2>();
-  k2.Z = ctx->Z.as<double2>(); k2.Xlo = ctx->xlo.as<double2>();
+  k2.Xhi = ctx->xhi.as<double2>(); k2.Xlo = ctx->xlo.as<double2>();
   k2.M = ctx->M; k2.N = ctx->N; k2.tol = ctx->tol;
   EpsTab eps;
   eps.re = ctx->cre.as<double>(); eps.im = ctx->cim.as<double>(); eps.nc = ctx->nc;
@@ -410,9 +410,6 @@ int launch_deep(nm_ctx* ctx) {
   p.Z = ctx->Z.as<double2>(); p.ghi = ctx->ghi.as<int32_t>(); p.gb = ctx->gb.as<double>();
   p.Z2 = ctx->Z2.as<double2>(); p.filt = ctx->k3filt.as<int4>(); p.esc_hi = ctx->esc_hi.as<int32_t>();
   p.seg_hi = ctx->seg_hi.as<int32_t>();
-#if K3F_SEG32
-  p.seg32_hi = ctx->seg32_hi.as<int32_t>();
-#endif
   p.Jmax = ctx->Jmax; p.N = ctx->N; p.CH = CH;
   p.eps = eps; p.nc = ctx->nc;
   p.fresh_ids = ctx->fresh.as<int32_t>();
@@ -485,7 +482,7 @@ int launch_deep(nm_ctx* ctx) {
       ctx->stats.kernel_launches += 2;
       NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(nbins + 2) * sizeof(unsigned), st));
     }
-    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 15 * (K + 2) * sizeof(unsigned long long), st));
+    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 13 * (K + 2) * sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&rcount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ccount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_EVENTS], 0, sizeof(unsigned long long), st));
@@ -510,9 +507,7 @@ int launch_deep(nm_ctx* ctx) {
       p.tmp[0] = ctx->rq[0].as<PixState>(); p.tmp[1] = ctx->rq[1].as<PixState>();   // idle in the fast path
       p.split_min = ctx->opt_k3_split > 1 ? (unsigned long long)ctx->opt_k3_split : K3F_SPLIT_MIN;
       p.sub_count = (ctx->opt_k3_split && (unsigned long long)ctx->W >= p.split_min) ? &subcount[K3F_SUBS * k] : nullptr;
-      const bool loudq = fast && ctx->opt_k3_loudq && ctx->loud.p != nullptr;
-      p.loud = loudq ? ctx->loud.as<PixState>() : nullptr;
-      p.loud_count = &loudcount[k];
+      p.early_export = ctx->opt_k3_loudq;
       cudaError_t e = cudaSuccess;
       PixState* evq = ctx->events.as<PixState>();
       if (fast) {   // K3F_SUBS launches per level; all but the first return at once unless the level is split (K3Work)
@@ -526,19 +521,6 @@ int launch_deep(nm_ctx* ctx) {
           else k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
           e = cudaGetLastError();
           if (sub) ctx->stats.kernel_launches++;
-        }
-        if (loudq && e == cudaSuccess) {
-          // the level's loud queue (slots k3_fast exported early because their delta came within reach of |Z|: mostly
-          // samples in their last ~30 iterations): one state per lane with the exact comparisons in line
-          K3Params pl = p;
-          pl.cur = ctx->loud.as<PixState>(); pl.cur_count = &loudcount[k];
-          pl.fresh_off = nullptr; pl.head = &loudhead[k];
-          const size_t smem_l = (size_t)(CH + 4) * (sizeof(double2) + sizeof(double));
-          const unsigned bl = (unsigned)(ctx->sm_count * (scaled ? ctx->occ_k3l[1] : ctx->occ_k3l[0]));
-          if (scaled) k3_level<NM_MODE_REQUEUE, true, true><<<bl, K3_THREADS, smem_l, st>>>(pl, evq);
-          else k3_level<NM_MODE_REQUEUE, false, true><<<bl, K3_THREADS, smem_l, st>>>(pl, evq);
-          e = cudaGetLastError();
-          ctx->stats.kernel_launches++;
         }
       }
       else if (scaled) e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, true>(ctx, p, blocks, smem)
@@ -561,15 +543,15 @@ int launch_deep(nm_ctx* ctx) {
         cudaEventRecord(dbg_ev, st);
       }
     }
-    if (fast) {  // resolve what the branch-free kernel exported: escapes, glitches, limits, rebases, false alarms
+    if (fast) {
+      // finish what the branch-free kernel exported — escapes, glitches, limits, rebases, false alarms and the slots it
+      // exported early (k3_fast.cuh: K3F_LOUDQ) — one thread per state, to the end (k3_finish.cuh); nothing is carried
+      const unsigned fbk = (unsigned)(ctx->sm_count * 16);
+      const FreshArrays none = fresh_set(ctx, par ^ 1);
       if (scaled)
-        k3_events<true><<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(ck, eps, ctx->events.as<PixState>(), &ctr[CTR_EVENTS],
-                                                                      fresh_set(ctx, par ^ 1), &ccount[par ^ 1],
-                                                                      ctx->hist.as<unsigned>());
+        k3_finish<NM_MODE_REQUEUE, true, true><<<fbk, K3_FINISH_THREADS, 0, st>>>(ck, eps, none, &ctr[CTR_EVENTS], 0, ctx->events.as<PixState>());
       else
-        k3_events<false><<<(unsigned)(ctx->sm_count * 8), 256, 0, st>>>(ck, eps, ctx->events.as<PixState>(), &ctr[CTR_EVENTS],
-                                                                       fresh_set(ctx, par ^ 1), &ccount[par ^ 1],
-                                                                       ctx->hist.as<unsigned>());
+        k3_finish<NM_MODE_REQUEUE, false, true><<<fbk, K3_FINISH_THREADS, 0, st>>>(ck, eps, none, &ctr[CTR_EVENTS], 0, ctx->events.as<PixState>());
       NM_CUDA(ctx, cudaGetLastError());
       ctx->stats.kernel_launches++;
     }
@@ -676,8 +658,6 @@ int nm_create(int device, nm_ctx** out) {
   NM_K3_SETUP((k3_level<NM_MODE_REBASE, false>), K3_THREADS, ctx->occ_k3[1]);
   NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, true>), K3_THREADS, ctx->occ_k3s[0]);
   NM_K3_SETUP((k3_level<NM_MODE_REBASE, true>), K3_THREADS, ctx->occ_k3s[1]);
-  NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, false, true>), K3_THREADS, ctx->occ_k3l[0]);
-  NM_K3_SETUP((k3_level<NM_MODE_REQUEUE, true, true>), K3_THREADS, ctx->occ_k3l[1]);
 #undef NM_K3_SETUP
 #define NM_K3_SETUP(fn, P, occ_out)                                                                             \
   {                                                                                                             \
@@ -695,6 +675,7 @@ int nm_create(int device, nm_ctx** out) {
 #undef NM_CREATE_CUDA
   if (ctx->occ_k1 < 1) ctx->occ_k1 = 1;
   if (const char* fm = getenv("NM_K3_FINISH_MAX")) { const long long v = atoll(fm); if (v >= 0) ctx->opt_k3_finish_max = v; }
+  if (const char* lq = getenv("NM_K3_LOUDQ")) ctx->opt_k3_loudq = atoi(lq) ? 1 : 0;   // A/B runs of bench.py
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
   return NM_OK;
@@ -704,10 +685,10 @@ void nm_destroy(nm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->own);
-  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->seg32_hi, &ctx->eps_max,
-                    &ctx->gb, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
+  DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->eps_max,
+                    &ctx->gb, &ctx->xhi, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->loud, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
                     &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -829,6 +810,7 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   NM_CUDA(ctx, ctx->esc_hi.ensure((size_t)(J1 + 8) * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->seg_hi.ensure((size_t)(J1 / 16 + 8) * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->eps_max.ensure(sizeof(double)));
+  NM_CUDA(ctx, ctx->xhi.ensure((size_t)(M + 1) * sizeof(double2)));
   NM_CUDA(ctx, ctx->xlo.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->a.ensure((size_t)M * sizeof(double2)));
   NM_CUDA(ctx, ctx->b.ensure((size_t)M * sizeof(double2)));
@@ -846,15 +828,15 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     NM_CUDA(ctx, ctx->q[i].ensure(Wn * sizeof(PixState)));
     NM_CUDA(ctx, ctx->rq[i].ensure(Wn * sizeof(PixState)));
   }
-  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(15 * (K + 2) + 4) * sizeof(unsigned long long)));
+  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(13 * (K + 2) + 4) * sizeof(unsigned long long)));
   NM_CUDA(ctx, ctx->rq_pix.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->rq_iter.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->events.ensure(Wn * sizeof(PixState)));
-  if (ctx->opt_k3_loudq) NM_CUDA(ctx, ctx->loud.ensure(Wn * sizeof(PixState)));
 
   cudaStream_t s = ctx->stream;
   NM_CUDA(ctx, cudaMemsetAsync(ctx->Z.p, 0, (size_t)(J1 + 8) * sizeof(double2), s));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->Z.as<double2>() + 1, t->x_hi, (size_t)(M + ctx->has_escape) * sizeof(double2), cudaMemcpyDefault, s));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->xhi.p, t->x_hi, (size_t)(M + ctx->has_escape) * sizeof(double2), cudaMemcpyDefault, s));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->xlo.p, t->x_lo, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->a.p, t->a, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->b.p, t->b, (size_t)M * sizeof(double2), cudaMemcpyDefault, s));
@@ -884,6 +866,10 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     NM_CUDA(ctx, cudaMemcpyAsync(ctx->list.p, pix_list, (size_t)ctx->W * sizeof(int32_t), cudaMemcpyDefault, s));
   }
   {
+    // K3 iterates against the orbit rounded to nearest (k_round_orbit); K2's phase 2 keeps the truncated hi/lo pair
+    k_round_orbit<<<(M + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>() + 1, ctx->xhi.as<double2>(), ctx->xlo.as<double2>(), M);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
     int pad_n = J1 + 8;
     k_glitch_bounds<<<(pad_n + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->ghi.as<int32_t>(),
                                                         ctx->Z2.as<double2>(), ctx->k3filt.as<K3Filt>(), ctx->esc_hi.as<int32_t>(), J1,
@@ -902,13 +888,6 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
                                                      ctx->seg_hi.as<int32_t>(), n_seg);
     NM_CUDA(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 2;
-#if K3F_SEG32
-    NM_CUDA(ctx, ctx->seg32_hi.ensure((size_t)(J1 / 32 + 8) * sizeof(int32_t)));
-    k_seg_bounds32<<<(n_seg / 2 + 128) / 128, 128, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->Jmax, ctx->eps_max.as<double>(),
-                                                           ctx->seg32_hi.as<int32_t>(), n_seg / 2 + 1);
-    NM_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches++;
-#endif
   }
   return NM_OK;
 }
@@ -1163,10 +1142,6 @@ int32_t nm_k3_seg_bound(const double* z, const double* gb, int j0, int jmax, dou
   return k3_seg_bound(z, z + 1, gb, 2, j0, jmax, e_max);
 }
 
-int32_t nm_k3_seg_bound32(const double* z, const double* gb, int j0, int jmax, double e_max) {
-  if (!z || !gb || j0 < 0) return 0;
-  return k3_seg_bound_n<32>(z, z + 1, gb, 2, j0, jmax, e_max);
-}
 
 int nm_k3_filter_fires(const uint32_t entry[5], double dr, double di, int scaled, int* glitch, int* escape) {
   K3Filt f; f.lo_r = entry[0]; f.w_r = entry[1]; f.lo_i = entry[2]; f.w_i = entry[3];

@@ -34,6 +34,9 @@ struct RefView : public Mandelbrot {
     return pt;
   }
   void orbit_from(const HPComplex& p) { computeOrbit(p); }
+  void reprec_orbit(mp_bitcnt_t bits) {   // value-preserving when widening, and when narrowing back to the original precision
+    for (size_t i = 0; i < X.size(); i++) { X[i].re.set_prec(bits); X[i].im.set_prec(bits); }
+  }
   void series() { computeSeries(); }
   void clear_tabs() { X.clear(); A.clear(); B.clear(); C.clear(); }
 };
@@ -198,4 +201,73 @@ ORACLE_API int ref_view_string(void* h, int which, char* buf, int cap) {
   int n = snprintf(buf, cap, "%s@%ld", s, (long)e);
   free(s);
   return n;
+}
+
+// Brute-force truth for the listed pixels (ids r*cols+c): the pixel coordinate exactly as the reference forms
+// it (pixel(), mandelbrot.cpp:271, 275, at the view's precision) is widened to `prec_bits` and iterated
+// directly, z <- z^2 + c from z = c, all in mpf at that precision. out_it[k] = index of the first iterate with
+// |z|^2 > 2^20 (the deep path's counting convention, mandelbrot.cpp:212-217: iterate 0 is the pixel) or N;
+// out_r2[k] = |z|^2 of that iterate (truncated to double). This is NOT the reference's algorithm (its own
+// continuation runs at the view's 64-192 bits with truncating operations, SURVEY.md finding 4): it is what the
+// reference's and the CUDA path's escape counts are adjudicated against. tests/golden/make_k3_truth.py.
+ORACLE_API double ref_truth_pixels(void* h, const int* pix, int n, int prec_bits, int* out_it, double* out_r2) {
+  RefView* v = (RefView*)h;
+  const mp_bitcnt_t saved = mpf_get_default_prec();
+  auto t0 = std::chrono::steady_clock::now();
+  mpf_t cr, ci, zr, zi, rr, ii, ri, m;
+  mpf_init2(cr, prec_bits); mpf_init2(ci, prec_bits); mpf_init2(zr, prec_bits); mpf_init2(zi, prec_bits);
+  mpf_init2(rr, prec_bits); mpf_init2(ii, prec_bits); mpf_init2(ri, prec_bits); mpf_init2(m, prec_bits);
+  for (int k = 0; k < n; k++) {
+    HPComplex p = v->pixel(pix[k] / v->cols(), pix[k] % v->cols());
+    mpf_set(cr, p.re.get_mpf_t()); mpf_set(ci, p.im.get_mpf_t());
+    mpf_set(zr, cr); mpf_set(zi, ci);
+    int it = v->N;
+    double r2 = 0.0;
+    for (int i = 1; i < v->N; i++) {
+      mpf_mul(rr, zr, zr); mpf_mul(ii, zi, zi); mpf_mul(ri, zr, zi);
+      mpf_sub(zr, rr, ii); mpf_add(zr, zr, cr);
+      mpf_mul_ui(ri, ri, 2UL); mpf_add(zi, ri, ci);
+      // cheap pre-test in double, exact comparison only near the threshold
+      const double dr = mpf_get_d(zr), di = mpf_get_d(zi);
+      const double mag = dr * dr + di * di;
+      if (mag > 1048570.0) {
+        mpf_mul(rr, zr, zr); mpf_mul(ii, zi, zi); mpf_add(m, rr, ii);
+        if (mpf_cmp_d(m, 1048576.0) > 0) { it = i; r2 = mpf_get_d(m); break; }
+      }
+    }
+    out_it[k] = it;
+    if (out_r2) out_r2[k] = r2;
+  }
+  mpf_clear(cr); mpf_clear(ci); mpf_clear(zr); mpf_clear(zi); mpf_clear(rr); mpf_clear(ii); mpf_clear(ri); mpf_clear(m);
+  mpf_set_default_prec(saved);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// The reference's OWN per-pixel algorithm (getIterations, mandelbrot.cpp:144-229) with its phase-3 continuation run at
+// `prec_bits` instead of the view's precision. The pixel coordinate is formed at the view's precision exactly as
+// computeRow forms it, then widened (value unchanged); the orbit X is widened in place (values unchanged) and narrowed
+// back afterwards; phases 1-2 are double arithmetic on descended values and do not depend on the precision. Phase 3
+// (`Y = X[L-1] + d[L-1]; Yn = Y^2 + Y0`, 209-224) then runs through the same mpf_class operators at the global default
+// precision `prec_bits`: the exact continuation of the reference's own phase-2 state, free of the truncation noise of
+// its 64-192-bit arithmetic (SURVEY.md finding 4). Used to adjudicate reference-vs-CUDA escape-count differences.
+ORACLE_API double ref_compute_pixels_wide(void* h, const int* pix, int n, int prec_bits, void* out) {
+  RefView* v = (RefView*)h;
+  RenderGrid::EscapeValue* o = (RenderGrid::EscapeValue*)out;
+  const mp_bitcnt_t view_prec = mpf_get_default_prec();
+  const mp_bitcnt_t orbit_prec = v->orbit_len() ? v->tab(0)[0].re.get_prec() : view_prec;
+  auto t0 = std::chrono::steady_clock::now();
+  v->reprec_orbit((mp_bitcnt_t)prec_bits);
+  for (int k = 0; k < n; k++) {
+    int r = pix[k] / v->cols(), c = pix[k] % v->cols();
+    mpf_set_default_prec(view_prec);
+    HPComplex p = v->pixel(r, c);
+    mpf_set_default_prec((mp_bitcnt_t)prec_bits);
+    HPComplex pw;
+    pw.re = mpf_class(p.re, (mp_bitcnt_t)prec_bits);
+    pw.im = mpf_class(p.im, (mp_bitcnt_t)prec_bits);
+    o[k] = v->one(pw);
+  }
+  mpf_set_default_prec(view_prec);
+  v->reprec_orbit(orbit_prec);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
