@@ -68,6 +68,7 @@ constexpr int K3F_THREADS = 256;
 #ifndef K3F_LOUDQ_MAX_LANES
 #define K3F_LOUDQ_MAX_LANES 8   // ... if at most this many lanes of the warp object to the quiet segment
 #endif
+constexpr int K3F_LOUD_FLAG = 0x40000000;   // in K3Slots::evj: the exported slot goes to the loud queue, not to the event queue
 #define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? K3F_CTAS_SCALED : K3F_CTAS_PLAIN)
 // shared-memory bytes of the per-chunk tables (2Z, filter entries, escape words) / of everything k3_fast<P> needs
 __host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
@@ -150,9 +151,9 @@ __device__ __forceinline__ K3Work k3f_work(const K3Params& p) {
   const int CH = p.CH, k = p.k, jbase = k * CH;
   int l1 = jbase + CH;
   if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
-  const unsigned long long n_in = (p.cur_count ? *p.cur_count : 0ULL) + (p.fresh_off[l1] - p.fresh_off[jbase]);
+  const unsigned long long n_in = (p.cur_count ? *p.cur_count : 0ULL) + (p.loud_pass ? 0u : p.fresh_off[l1] - p.fresh_off[jbase]);
   bool split = false;
-  if (p.sub_count && k > 0 && n_in >= p.split_min) {
+  if (!p.loud_pass && p.sub_count && k > 0 && n_in >= p.split_min) {
     const unsigned long long prev_in = p.qcount[k - 1] + (p.fresh_off[jbase] - p.fresh_off[jbase - CH]);
     const unsigned long long prev_out = p.qcount[k];
     split = prev_in > prev_out && (prev_in - prev_out) * 32ULL > prev_in;
@@ -175,8 +176,8 @@ __device__ __forceinline__ K3Work k3f_work(const K3Params& p) {
   if (f1 > p.Jmax + 1) f1 = p.Jmax + 1;
   int f0 = w.jlo;
   if (f0 > f1) f0 = f1;
-  w.fresh_begin = p.fresh_off[f0];
-  w.n_fresh = p.fresh_off[f1] - w.fresh_begin;  // multiple of the group size by construction
+  w.fresh_begin = p.loud_pass ? 0u : p.fresh_off[f0];
+  w.n_fresh = p.loud_pass ? 0ULL : p.fresh_off[f1] - w.fresh_begin;  // multiple of the group size by construction
   return w;
 }
 
@@ -388,7 +389,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
           quiet = K3F_QUIET && n4 == 4 && m_hi < __ldg(&p.seg_hi[j >> 4]);
         }
 #if K3F_LOUDQ && K3F_QUIET
-        if (p.early_export) {
+        if (p.loud && !p.loud_pass) {
           // lanes that object to a WHOLE segment because of the size of a delta (not because the segment is partial)
           const bool objects = act && !quiet;
           const unsigned obj = __ballot_sync(FULL_MASK, objects);
@@ -404,7 +405,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
                   if ((live & (1u << s)) && hs >= T) {
                     live &= ~(1u << s); expo |= 1u << s;
                     slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
-                    slots.evj[s * K3F_THREADS + tid] = j;
+                    slots.evj[s * K3F_THREADS + tid] = j | K3F_LOUD_FLAG;
                     executed += (unsigned long long)(j - j_in);
                     dr[s] = di[s] = er[s] = ei[s] = 0.0;
                   }
@@ -465,7 +466,12 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
 #pragma unroll
     for (int s = 0; s < P; ++s) {
       const bool toNext = (live >> s) & 1u;     // reached the chunk end alive
-      const bool toEvents = (expo >> s) & 1u;
+      bool toEvents = (expo >> s) & 1u;
+      int evj = toEvents ? slots.evj[s * K3F_THREADS + tid] : 0;
+#if K3F_LOUDQ && K3F_QUIET
+      const bool toLoud = toEvents && (evj & K3F_LOUD_FLAG);
+      if (toLoud) { toEvents = false; evj &= ~K3F_LOUD_FLAG; }
+#endif
       if (toNext) executed += (unsigned long long)(j - j_in);
       unsigned long long slot = warp_reserve(wk.next_count, toNext);
       if (toNext) {
@@ -476,10 +482,21 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
         const double2 d = slots.ck[s * K3F_THREADS + tid];
-        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = slots.evj[s * K3F_THREADS + tid];
+        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
         q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;  // an exported slot is parked: its exponent is never re-normalised
         events[slot] = q;
       }
+#if K3F_LOUDQ && K3F_QUIET
+      if (p.loud && !p.loud_pass) {
+        slot = warp_reserve(p.loud_count, toLoud);
+        if (toLoud) {
+          const double2 d = slots.ck[s * K3F_THREADS + tid];
+          PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
+          q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;
+          p.loud[slot] = q;
+        }
+      }
+#endif
     }
   }
 
@@ -530,7 +547,8 @@ k3_fast(K3Params p, PixState* events) {
   // a quarter of the time (profiles/r01h_cfg2_levels.txt: 31 against 146 ns per iteration), and at most three
   // of them are needed. (Levels with less than 3/4 of a wave altogether run entirely that way.)
   unsigned long long u_a = u_total;
-  if (P > 1) {
+  if (P > 1 && p.loud_pass) u_a = 0;   // the loud queue's states sit at different indices: one state per lane
+  else if (P > 1) {
     const unsigned long long wave = (unsigned long long)gridDim.x * K3F_THREADS * P;
     const unsigned long long rem = u_total % wave;
     if (rem * 4 <= wave * 3) u_a = u_total - rem;

@@ -71,7 +71,7 @@ struct nm_ctx {
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
   DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xhi, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, loud, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
@@ -320,13 +320,15 @@ int launch_deep(nm_ctx* ctx) {
   const int K = ctx->K;
   cudaStream_t st = ctx->stream;
   unsigned long long* qctr = ctx->qctr.as<unsigned long long>();
-  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | rcount[2] | carry_count[2]
+  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | loudcount[K+2] | loudhead[8(K+2)] | rcount[2] | carry_count[2]
   // (head: per level, per quarter-chunk launch, one deal cursor for the 4-states-per-lane waves and one for the
   //  one-state-per-lane remainder: k3_fast.cuh)
   unsigned long long* qcount = qctr;
   unsigned long long* head = qctr + (K + 2);
   unsigned long long* subcount = qctr + 9 * (K + 2);
-  unsigned long long* rcount = qctr + 13 * (K + 2);
+  unsigned long long* loudcount = qctr + 13 * (K + 2);   // per level: states k3_fast exported early (k3_fast.cuh: K3F_LOUDQ)
+  unsigned long long* loudhead = qctr + 14 * (K + 2);    // ... and the deal cursors of the loud-pass launch that runs them
+  unsigned long long* rcount = qctr + 22 * (K + 2);
   unsigned long long* ccount = rcount + 2;
   unsigned long long* ctr = ctx->ctr.as<unsigned long long>();
 
@@ -482,7 +484,7 @@ int launch_deep(nm_ctx* ctx) {
       ctx->stats.kernel_launches += 2;
       NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(nbins + 2) * sizeof(unsigned), st));
     }
-    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 13 * (K + 2) * sizeof(unsigned long long), st));
+    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 22 * (K + 2) * sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&rcount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ccount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_EVENTS], 0, sizeof(unsigned long long), st));
@@ -507,7 +509,10 @@ int launch_deep(nm_ctx* ctx) {
       p.tmp[0] = ctx->rq[0].as<PixState>(); p.tmp[1] = ctx->rq[1].as<PixState>();   // idle in the fast path
       p.split_min = ctx->opt_k3_split > 1 ? (unsigned long long)ctx->opt_k3_split : K3F_SPLIT_MIN;
       p.sub_count = (ctx->opt_k3_split && (unsigned long long)ctx->W >= p.split_min) ? &subcount[K3F_SUBS * k] : nullptr;
-      p.early_export = ctx->opt_k3_loudq;
+      const bool loudq = fast && ctx->opt_k3_loudq && ctx->loud.p != nullptr && (unsigned long long)ctx->W >= p.split_min;
+      p.loud = loudq ? ctx->loud.as<PixState>() : nullptr;
+      p.loud_count = &loudcount[k];
+      p.loud_pass = 0;
       cudaError_t e = cudaSuccess;
       PixState* evq = ctx->events.as<PixState>();
       if (fast) {   // K3F_SUBS launches per level; all but the first return at once unless the level is split (K3Work)
@@ -521,6 +526,20 @@ int launch_deep(nm_ctx* ctx) {
           else k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
           e = cudaGetLastError();
           if (sub) ctx->stats.kernel_launches++;
+        }
+        if (loudq && e == cudaSuccess) {
+          // the level's loud queue (slots exported early because their delta came within reach of |Z|: samples in their
+          // last iterations before they escape): the same kernel, one state per lane, per-iteration filter, no export
+          K3Params pl = p;
+          pl.cur = ctx->loud.as<PixState>(); pl.cur_count = &loudcount[k];
+          pl.loud_pass = 1; pl.sub = 0; pl.sub_count = nullptr;
+          pl.head = &loudhead[2 * K3F_SUBS * k];
+          if (G == 4 && scaled) k3_fast<4, true><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
+          else if (G == 4) k3_fast<4, false><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
+          else if (scaled) k3_fast<2, true><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
+          else k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
+          e = cudaGetLastError();
+          ctx->stats.kernel_launches++;
         }
       }
       else if (scaled) e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, true>(ctx, p, blocks, smem)
@@ -688,7 +707,7 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->eps_max,
                     &ctx->gb, &ctx->xhi, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->loud, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
                     &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -828,10 +847,11 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     NM_CUDA(ctx, ctx->q[i].ensure(Wn * sizeof(PixState)));
     NM_CUDA(ctx, ctx->rq[i].ensure(Wn * sizeof(PixState)));
   }
-  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(13 * (K + 2) + 4) * sizeof(unsigned long long)));
+  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(22 * (K + 2) + 4) * sizeof(unsigned long long)));
   NM_CUDA(ctx, ctx->rq_pix.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->rq_iter.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->events.ensure(Wn * sizeof(PixState)));
+  if (ctx->opt_k3_loudq) NM_CUDA(ctx, ctx->loud.ensure(Wn * sizeof(PixState)));
 
   cudaStream_t s = ctx->stream;
   NM_CUDA(ctx, cudaMemsetAsync(ctx->Z.p, 0, (size_t)(J1 + 8) * sizeof(double2), s));

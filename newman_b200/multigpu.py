@@ -46,13 +46,22 @@ def gather_bands(band, nr, rank, world):
     (nr, nc, 2) tensor on rank 0 (None elsewhere)."""
     if world == 1:
         return band
+    # rows r, r + world, ...: ceil(nr / world) rows on the first nr % world ranks, one fewer on the rest — every rank
+    # pads its band to the longest one so the gather sees equal shapes, and rank 0 drops the padding
+    longest = -(-nr // world)
+    if band.shape[0] < longest:
+        pad = torch.zeros((longest - band.shape[0],) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+        band = torch.cat([band, pad], dim=0)
+    elif band.shape[0] > longest:
+        raise ValueError(f"gather_bands: band of {band.shape[0]} rows, but rank {rank} of {world} owns at most {longest} of {nr}")
     bufs = [torch.empty_like(band) for _ in range(world)] if rank == 0 else None
     dist.gather(band, bufs, dst=0)
     if rank != 0:
         return None
     full = torch.empty((nr,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
     for r in range(world):
-        full[r::world] = bufs[r]
+        n_r = len(range(r, nr, world))
+        full[r::world] = bufs[r][:n_r]
     return full
 
 
