@@ -74,12 +74,6 @@ NM_API int nm_sync(nm_ctx* ctx);
  *                          (decided on the device from the queue counters) if it holds at least 303 104 states;
  *                          0: always whole chunks; n > 1: that minimum instead (tests). Same results. */
 #define NM_OPT_K3_SPLIT 4
-/*   NM_OPT_K3_LOUDQ (1)    k3_fast: when only a few lanes of a warp hold a sample whose delta has come within reach of |Z|
- *                          (in practice: a sample in its last ~30 iterations before it escapes), those samples are exported
- *                          early to the kernel that finishes exported states with the exact comparisons (k3_finish), and the
- *                          warp keeps running without the per-iteration glitch filter; 0: the whole warp runs the filter for
- *                          such segments. Same results; the tests run both. */
-#define NM_OPT_K3_LOUDQ 5
 NM_API int nm_set_option(nm_ctx* ctx, int key, int value);
 /* Abandon the frame in flight (viewer.cpp:177, 221-231 abort mid-frame). Persistent CTAs poll it. */
 NM_API int nm_cancel(nm_ctx* ctx);
@@ -318,6 +312,10 @@ NM_API int nmv_host_table(const nmv_view* v, int which, double* out);
  * nmv_host_table_exp which 2/3/4 = their binary exponents [2M]; likewise 10/11 = eps_re[nc] / eps_im[nr]
  * mantissas and exponents */
 NM_API int nmv_host_table_exp(const nmv_view* v, int which, int32_t* out);
+/* 1 if the hand-laid-out arbitrary-precision values of the pipelined table build (csrc/hp_host.cpp: HpStream) behave
+ * exactly like mpf_init2 values under the running libgmp (checked once per process); 0: the build falls back to
+ * mpf_init2 per value. */
+NM_API int nmv_host_selfcheck(void);
 NM_API int nmv_host_coords(nmv_view* v, double* c_re, double* c_im);       /* mandelbrot.cpp:271, 275, 234 */
 NM_API int nmv_host_cardioid(nmv_view* v, uint8_t* mask_or_null);          /* returns NM_CARDIOID_* */
 NM_API int nmv_host_in_cardioid(nmv_view* v, int r, int c);                /* mandelbrot.cpp:63-71 */

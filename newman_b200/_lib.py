@@ -22,7 +22,6 @@ OPT_K2_LITERAL = 1
 OPT_K3_GROUP = 2
 OPT_K3_FINISH_MAX = 3
 OPT_K3_SPLIT = 4
-OPT_K3_LOUDQ = 5
 
 
 class NmError(RuntimeError):

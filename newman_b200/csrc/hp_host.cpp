@@ -364,6 +364,42 @@ namespace {
 template <int K>
 struct HpVals { mpf_t v[K]; };
 
+// HpStream::append() lays mpf values out by hand (an mpf_init2 per value would be a malloc per value): {_mp_prec,
+// _mp_size, _mp_exp, _mp_d} with prec + 1 limbs from a pool. That ties this file to GMP's documented-but-private mpf
+// layout, so it is checked once per process against the running libgmp: a hand-built value must take the same results
+// as an mpf_init2 value (same limbs, size, exponent) from mpf_set / mpf_mul / mpf_add at several precisions. If the
+// check fails the pooled layout is not used: every entry falls back to mpf_init2 (slower, always right).
+static_assert(sizeof(mp_limb_t) == 8, "hp_host.cpp assumes 64-bit limbs");
+static_assert(sizeof(__mpf_struct) == 24, "unexpected __mpf_struct layout");
+bool pooled_mpf_layout_ok() {
+  static const bool ok = [] {
+    for (mp_bitcnt_t bits : {64u, 173u, 341u, 1336u}) {
+      mpf_t ref, a, b;
+      mpf_init2(ref, bits); mpf_init2(a, bits); mpf_init2(b, bits);
+      mpf_set_d(a, 1.2345678901234567); mpf_div_ui(a, a, 3UL);
+      mpf_set_d(b, -0.9876543210987654); mpf_div_ui(b, b, 7UL);
+      const int prec = ref->_mp_prec;
+      std::vector<mp_limb_t> pool((size_t)prec + 1, ~(mp_limb_t)0);
+      __mpf_struct hand;
+      hand._mp_prec = prec; hand._mp_size = 0; hand._mp_exp = 0; hand._mp_d = pool.data();
+      bool same = true;
+      for (int op = 0; op < 3 && same; op++) {
+        if (op == 0) { mpf_set(ref, a); mpf_set(&hand, a); }
+        else if (op == 1) { mpf_mul(ref, a, b); mpf_mul(&hand, a, b); }
+        else { mpf_add(ref, ref, b); mpf_add(&hand, &hand, b); }
+        same = ref->_mp_size == hand._mp_size && ref->_mp_exp == hand._mp_exp && mpf_cmp(ref, &hand) == 0;
+        const int n = ref->_mp_size < 0 ? -ref->_mp_size : ref->_mp_size;
+        for (int i = 0; i < n && same; i++) same = ref->_mp_d[i] == hand._mp_d[i];
+        same = same && n <= prec + 1;
+      }
+      mpf_clear(ref); mpf_clear(a); mpf_clear(b);
+      if (!same) return false;
+    }
+    return true;
+  }();
+  return ok;
+}
+
 // Values a stage publishes for the next ones. Blocks of 4096 entries hang off a pointer table of fixed size, so a
 // reader never sees storage move; `ready` = entries published (release / acquire).
 template <int K>
@@ -373,6 +409,8 @@ struct HpStream {
   std::vector<HpVals<K>*> blocks;
   std::vector<mp_limb_t*> limbs;        // one limb pool per block (an mpf_init2 per value would be a malloc per value)
   int prec_limbs;                        // _mp_prec of an mpf at the stream's precision
+  mp_bitcnt_t prec_bits;
+  bool pooled;                           // entries are laid out by hand in a limb pool (pooled_mpf_layout_ok)
   alignas(64) std::atomic<long> ready;
   std::atomic<bool> finished;
   alignas(64) long allocated;           // producer's side (the consumers keep their own copies of `ready`)
@@ -385,8 +423,16 @@ struct HpStream {
     mpf_init2(t, p);
     prec_limbs = t->_mp_prec;            // what mpf_init2 derives from the bit count
     mpf_clear(t);
+    prec_bits = p;
+    pooled = pooled_mpf_layout_ok();
   }
   ~HpStream() {
+    if (!pooled)
+      for (size_t bi = 0; bi < blocks.size(); bi++)
+        if (blocks[bi]) {
+          const long n = std::min<long>(kBlock, allocated - (long)bi * kBlock);
+          for (long i = 0; i < n; i++) for (int k = 0; k < K; k++) mpf_clear(blocks[bi][i].v[k]);
+        }
     for (HpVals<K>* b : blocks) delete[] b;
     for (mp_limb_t* l : limbs) delete[] l;
   }
@@ -402,14 +448,20 @@ struct HpStream {
       // under a reader that could still want the entry)
       const long dead = dead_below->load(std::memory_order_acquire);
       while ((freed_blocks + 1) * kBlock <= dead) {
+        if (!pooled)
+          for (long e = 0; e < kBlock; e++) for (int k = 0; k < K; k++) mpf_clear(blocks[(size_t)freed_blocks][e].v[k]);
         delete[] blocks[(size_t)freed_blocks]; blocks[(size_t)freed_blocks] = nullptr;
         delete[] limbs[(size_t)freed_blocks]; limbs[(size_t)freed_blocks] = nullptr;
         freed_blocks++;
       }
       blocks[bi] = new HpVals<K>[kBlock];
-      limbs[bi] = new mp_limb_t[K * per * kBlock];
+      if (pooled) limbs[bi] = new mp_limb_t[K * per * kBlock];
     }
     HpVals<K>& q = at(i);
+    if (!pooled) {
+      for (int k = 0; k < K; k++) mpf_init2(q.v[k], prec_bits);
+      return q;
+    }
     mp_limb_t* base = limbs[bi] + K * per * (size_t)(i % kBlock);
     for (int k = 0; k < K; k++) {
       q.v[k]->_mp_prec = prec_limbs; q.v[k]->_mp_size = 0; q.v[k]->_mp_exp = 0; q.v[k]->_mp_d = base + k * per;
@@ -648,4 +700,5 @@ void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out, int th
   }
 }
 
+bool host_mpf_layout_ok() { return pooled_mpf_layout_ok(); }
 }  // namespace newman_b200

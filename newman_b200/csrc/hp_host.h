@@ -74,5 +74,8 @@ void probe_lengths(const ViewHP& v, const std::vector<std::pair<int, int> >& can
 // their own (same operations, bit-identical tables), else everything runs serially.
 void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out, int threads = 0);
 
+// true if the pooled, hand-laid-out mpf values of the pipelined table build behave exactly like mpf_init2 values under
+// the running libgmp (checked once per process; if not, the build uses mpf_init2 per value)
+bool host_mpf_layout_ok();
 }  // namespace newman_b200
 #endif

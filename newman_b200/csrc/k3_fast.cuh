@@ -32,15 +32,12 @@
 // recurrence alone, 6.5 SASS instructions per sample-iteration instead of 11.2 — and only the escape filter is
 // looked at when the segment ends (profiles/r01p_*: full levels are entirely quiet, escape levels stay loud).
 //
-// Early export (K3F_LOUDQ, NM_OPT_K3_LOUDQ): on the levels where samples escape nearly every warp holds a sample or
-// two in its last ~30 iterations, whose delta is within the bound's reach of |Z| — so nearly every segment ran loud
-// for all 128 slots of the warp (profiles/r01p_cfg2_levels.txt: 1 045-1 405 Giter/s against 2 140 on full levels).
-// Now, if only a few lanes object to a quiet segment, their objecting slots are exported on the spot (state = the
-// checkpoint the segment would have started from) and parked; the warp runs the segment quiet, and k3_finish takes
-// the exported state through its last iterations one checked step at a time — the same steps and decisions in the
-// same order, so rasters, glitch lists and executed-iteration counts do not change. If many lanes object (the
-// reference orbit itself passes near 0: every sample is loud at once) the warp runs the segment with the
-// per-iteration filter as before.
+// (Measured and dropped, round 2 — profiles/r02_loud_queue_experiments.txt: exporting the few non-quiet slots of an
+// otherwise quiet warp at the segment start so that the warp stays quiet. The level kernels got faster — cfg2's escape
+// levels 5.96 -> 5.0 ms, full levels +3 % — but a sample is first non-quiet ~160 iterations before it escapes, not ~30:
+// 1.35 G of cfg2's 54 G iterations moved to whichever kernel finished the exported states, and none of the three
+// finishers tried — k3_level per level, k3_finish once per sweep, a one-state-per-lane pass of this kernel per level —
+// ran them at more than 1/6 of this kernel's rate, where break-even needs 1/3. All three were bit-identical in results.)
 //
 // (Two earlier versions replayed flagged blocks inside the warp; on the level where half of the
 // pixels escape that cost 3x, later 1.6x, the time of a full level, and latency-bound tail levels
@@ -62,13 +59,6 @@ constexpr int K3F_THREADS = 256;
 #ifndef K3F_QUIET
 #define K3F_QUIET 1         // quiet segments (k3_filter.cuh: k3_seg_bound) run without the per-iteration glitch filter
 #endif
-#ifndef K3F_LOUDQ
-#define K3F_LOUDQ 1         // early export: the few non-quiet slots of an otherwise quiet warp are exported on the spot
-#endif
-#ifndef K3F_LOUDQ_MAX_LANES
-#define K3F_LOUDQ_MAX_LANES 8   // ... if at most this many lanes of the warp object to the quiet segment
-#endif
-constexpr int K3F_LOUD_FLAG = 0x40000000;   // in K3Slots::evj: the exported slot goes to the loud queue, not to the event queue
 #define K3F_MIN_CTAS(P, SCALED) ((SCALED) ? K3F_CTAS_SCALED : K3F_CTAS_PLAIN)
 // shared-memory bytes of the per-chunk tables (2Z, filter entries, escape words) / of everything k3_fast<P> needs
 __host__ __device__ constexpr size_t k3f_table_bytes(int CH) {
@@ -151,9 +141,9 @@ __device__ __forceinline__ K3Work k3f_work(const K3Params& p) {
   const int CH = p.CH, k = p.k, jbase = k * CH;
   int l1 = jbase + CH;
   if (l1 > p.Jmax + 1) l1 = p.Jmax + 1;
-  const unsigned long long n_in = (p.cur_count ? *p.cur_count : 0ULL) + (p.loud_pass ? 0u : p.fresh_off[l1] - p.fresh_off[jbase]);
+  const unsigned long long n_in = (p.cur_count ? *p.cur_count : 0ULL) + (p.fresh_off[l1] - p.fresh_off[jbase]);
   bool split = false;
-  if (!p.loud_pass && p.sub_count && k > 0 && n_in >= p.split_min) {
+  if (p.sub_count && k > 0 && n_in >= p.split_min) {
     const unsigned long long prev_in = p.qcount[k - 1] + (p.fresh_off[jbase] - p.fresh_off[jbase - CH]);
     const unsigned long long prev_out = p.qcount[k];
     split = prev_in > prev_out && (prev_in - prev_out) * 32ULL > prev_in;
@@ -176,8 +166,8 @@ __device__ __forceinline__ K3Work k3f_work(const K3Params& p) {
   if (f1 > p.Jmax + 1) f1 = p.Jmax + 1;
   int f0 = w.jlo;
   if (f0 > f1) f0 = f1;
-  w.fresh_begin = p.loud_pass ? 0u : p.fresh_off[f0];
-  w.n_fresh = p.loud_pass ? 0ULL : p.fresh_off[f1] - w.fresh_begin;  // multiple of the group size by construction
+  w.fresh_begin = p.fresh_off[f0];
+  w.n_fresh = p.fresh_off[f1] - w.fresh_begin;  // multiple of the group size by construction
   return w;
 }
 
@@ -388,35 +378,6 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
           if (n4 > nb - b) n4 = nb - b;
           quiet = K3F_QUIET && n4 == 4 && m_hi < __ldg(&p.seg_hi[j >> 4]);
         }
-#if K3F_LOUDQ && K3F_QUIET
-        if (p.loud && !p.loud_pass) {
-          // lanes that object to a WHOLE segment because of the size of a delta (not because the segment is partial)
-          const bool objects = act && !quiet;
-          const unsigned obj = __ballot_sync(FULL_MASK, objects);
-          if (obj) {
-            const int T = (objects && n4 == 4) ? __ldg(&p.seg_hi[j >> 4]) : 0;
-            const unsigned can = __ballot_sync(FULL_MASK, objects && T > 0);
-            if (can == obj && __popc(obj) <= K3F_LOUDQ_MAX_LANES) {
-              if (objects) {
-#pragma unroll
-                for (int s = 0; s < P; ++s) {
-                  const int keep = SCALED ? (int)(0x7fffffffu & ~sm[s]) : 0x7fffffff;
-                  const int hs = max(__double2hiint(dr[s]) & keep, __double2hiint(di[s]) & keep);
-                  if ((live & (1u << s)) && hs >= T) {
-                    live &= ~(1u << s); expo |= 1u << s;
-                    slots.ck[s * K3F_THREADS + tid] = make_double2(dr[s], di[s]);
-                    slots.evj[s * K3F_THREADS + tid] = j | K3F_LOUD_FLAG;
-                    executed += (unsigned long long)(j - j_in);
-                    dr[s] = di[s] = er[s] = ei[s] = 0.0;
-                  }
-                }
-                m_hi = hi_max();
-                quiet = m_hi < T;   // true: every remaining delta is below the bound (parked slots are 0)
-              }
-            }
-          }
-        }
-#endif
         const bool warp_quiet = K3F_QUIET && __all_sync(FULL_MASK, quiet);
         if (act) {
           const int j_ck = j;
@@ -466,12 +427,7 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
 #pragma unroll
     for (int s = 0; s < P; ++s) {
       const bool toNext = (live >> s) & 1u;     // reached the chunk end alive
-      bool toEvents = (expo >> s) & 1u;
-      int evj = toEvents ? slots.evj[s * K3F_THREADS + tid] : 0;
-#if K3F_LOUDQ && K3F_QUIET
-      const bool toLoud = toEvents && (evj & K3F_LOUD_FLAG);
-      if (toLoud) { toEvents = false; evj &= ~K3F_LOUD_FLAG; }
-#endif
+      const bool toEvents = (expo >> s) & 1u;
       if (toNext) executed += (unsigned long long)(j - j_in);
       unsigned long long slot = warp_reserve(wk.next_count, toNext);
       if (toNext) {
@@ -482,21 +438,10 @@ __device__ __forceinline__ void k3_fast_body(const K3Params& p, const K3Work& wk
       slot = warp_reserve(&p.ctr[CTR_EVENTS], toEvents);
       if (toEvents) {
         const double2 d = slots.ck[s * K3F_THREADS + tid];
-        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
+        PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = slots.evj[s * K3F_THREADS + tid];
         q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;  // an exported slot is parked: its exponent is never re-normalised
         events[slot] = q;
       }
-#if K3F_LOUDQ && K3F_QUIET
-      if (p.loud && !p.loud_pass) {
-        slot = warp_reserve(p.loud_count, toLoud);
-        if (toLoud) {
-          const double2 d = slots.ck[s * K3F_THREADS + tid];
-          PixState q; q.dr = d.x; q.di = d.y; q.pix = slots.pix[s * K3F_THREADS + tid]; q.j = evj;
-          q.off = slots.off[s * K3F_THREADS + tid]; q.e = SCALED ? sc[s] : 0;
-          p.loud[slot] = q;
-        }
-      }
-#endif
     }
   }
 
@@ -547,8 +492,7 @@ k3_fast(K3Params p, PixState* events) {
   // a quarter of the time (profiles/r01h_cfg2_levels.txt: 31 against 146 ns per iteration), and at most three
   // of them are needed. (Levels with less than 3/4 of a wave altogether run entirely that way.)
   unsigned long long u_a = u_total;
-  if (P > 1 && p.loud_pass) u_a = 0;   // the loud queue's states sit at different indices: one state per lane
-  else if (P > 1) {
+  if (P > 1) {
     const unsigned long long wave = (unsigned long long)gridDim.x * K3F_THREADS * P;
     const unsigned long long rem = u_total % wave;
     if (rem * 4 <= wave * 3) u_a = u_total - rem;

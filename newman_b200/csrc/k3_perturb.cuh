@@ -62,11 +62,6 @@ struct K3Params {
   unsigned long long split_min;   // levels with fewer states are never split
   PixState* restart;
   unsigned long long* restart_count;
-  // k3_fast, early export (k3_fast.cuh: K3F_LOUDQ): the few non-quiet slots of an otherwise quiet warp go to the
-  // level's loud queue, which a second launch of k3_fast (loud_pass = 1: one state per lane, no early export) runs
-  PixState* loud;
-  unsigned long long* loud_count;
-  int loud_pass;
   unsigned long long* head;
   nm_escape* out;
   unsigned long long* ctr;

@@ -29,6 +29,7 @@
 #include "k4_resolve.cuh"
 #include "k5_video.cuh"
 #include "k6_palette.cuh"
+#include "fp64_probe.h"
 
 using namespace nm;
 
@@ -71,12 +72,11 @@ struct nm_ctx {
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
   DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xhi, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, loud, aexp, bexp, cexp, cre_e, cim_e;
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
   int opt_k3_split = 1;  // k3_fast: levels that follow an escape-heavy level run as 4 quarter-chunk launches
-  int opt_k3_loudq = 1;  // k3_fast: the few non-quiet slots of an otherwise quiet warp are exported early (k3_fast.cuh)
   long long opt_k3_finish_max = K3_FINISH_MAX_STATES;  // frames / remainders up to this many states: k3_finish
   int occ_k3f[2] = {0, 0}, occ_k3fs[2] = {0, 0};
   int M = 0, Jmax = 0, K = 0, CH = 1024, mode = 0, cardioid_mode = 0, has_escape = 0;
@@ -320,15 +320,13 @@ int launch_deep(nm_ctx* ctx) {
   const int K = ctx->K;
   cudaStream_t st = ctx->stream;
   unsigned long long* qctr = ctx->qctr.as<unsigned long long>();
-  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | loudcount[K+2] | loudhead[8(K+2)] | rcount[2] | carry_count[2]
+  // qctr layout: qcount[K+2] | head[8(K+2)] | subcount[4(K+2)] | rcount[2] | carry_count[2]
   // (head: per level, per quarter-chunk launch, one deal cursor for the 4-states-per-lane waves and one for the
   //  one-state-per-lane remainder: k3_fast.cuh)
   unsigned long long* qcount = qctr;
   unsigned long long* head = qctr + (K + 2);
   unsigned long long* subcount = qctr + 9 * (K + 2);
-  unsigned long long* loudcount = qctr + 13 * (K + 2);   // per level: states k3_fast exported early (k3_fast.cuh: K3F_LOUDQ)
-  unsigned long long* loudhead = qctr + 14 * (K + 2);    // ... and the deal cursors of the loud-pass launch that runs them
-  unsigned long long* rcount = qctr + 22 * (K + 2);
+  unsigned long long* rcount = qctr + 13 * (K + 2);
   unsigned long long* ccount = rcount + 2;
   unsigned long long* ctr = ctx->ctr.as<unsigned long long>();
 
@@ -484,7 +482,7 @@ int launch_deep(nm_ctx* ctx) {
       ctx->stats.kernel_launches += 2;
       NM_CUDA(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(nbins + 2) * sizeof(unsigned), st));
     }
-    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 22 * (K + 2) * sizeof(unsigned long long), st));
+    NM_CUDA(ctx, cudaMemsetAsync(qcount, 0, 13 * (K + 2) * sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&rcount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ccount[par ^ 1], 0, sizeof(unsigned long long), st));
     NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_EVENTS], 0, sizeof(unsigned long long), st));
@@ -509,10 +507,6 @@ int launch_deep(nm_ctx* ctx) {
       p.tmp[0] = ctx->rq[0].as<PixState>(); p.tmp[1] = ctx->rq[1].as<PixState>();   // idle in the fast path
       p.split_min = ctx->opt_k3_split > 1 ? (unsigned long long)ctx->opt_k3_split : K3F_SPLIT_MIN;
       p.sub_count = (ctx->opt_k3_split && (unsigned long long)ctx->W >= p.split_min) ? &subcount[K3F_SUBS * k] : nullptr;
-      const bool loudq = fast && ctx->opt_k3_loudq && ctx->loud.p != nullptr && (unsigned long long)ctx->W >= p.split_min;
-      p.loud = loudq ? ctx->loud.as<PixState>() : nullptr;
-      p.loud_count = &loudcount[k];
-      p.loud_pass = 0;
       cudaError_t e = cudaSuccess;
       PixState* evq = ctx->events.as<PixState>();
       if (fast) {   // K3F_SUBS launches per level; all but the first return at once unless the level is split (K3Work)
@@ -526,20 +520,6 @@ int launch_deep(nm_ctx* ctx) {
           else k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(p, evq);
           e = cudaGetLastError();
           if (sub) ctx->stats.kernel_launches++;
-        }
-        if (loudq && e == cudaSuccess) {
-          // the level's loud queue (slots exported early because their delta came within reach of |Z|: samples in their
-          // last iterations before they escape): the same kernel, one state per lane, per-iteration filter, no export
-          K3Params pl = p;
-          pl.cur = ctx->loud.as<PixState>(); pl.cur_count = &loudcount[k];
-          pl.loud_pass = 1; pl.sub = 0; pl.sub_count = nullptr;
-          pl.head = &loudhead[2 * K3F_SUBS * k];
-          if (G == 4 && scaled) k3_fast<4, true><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
-          else if (G == 4) k3_fast<4, false><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
-          else if (scaled) k3_fast<2, true><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
-          else k3_fast<2, false><<<blocks, K3F_THREADS, smem, st>>>(pl, evq);
-          e = cudaGetLastError();
-          ctx->stats.kernel_launches++;
         }
       }
       else if (scaled) e = ctx->mode == NM_MODE_REBASE ? launch_level<NM_MODE_REBASE, true>(ctx, p, blocks, smem)
@@ -563,8 +543,8 @@ int launch_deep(nm_ctx* ctx) {
       }
     }
     if (fast) {
-      // finish what the branch-free kernel exported — escapes, glitches, limits, rebases, false alarms and the slots it
-      // exported early (k3_fast.cuh: K3F_LOUDQ) — one thread per state, to the end (k3_finish.cuh); nothing is carried
+      // finish what the branch-free kernel exported — escapes, glitches, limits, rebases, false alarms — one thread per
+      // state, to the end (k3_finish.cuh); nothing is carried into another sweep
       const unsigned fbk = (unsigned)(ctx->sm_count * 16);
       const FreshArrays none = fresh_set(ctx, par ^ 1);
       if (scaled)
@@ -694,7 +674,6 @@ int nm_create(int device, nm_ctx** out) {
 #undef NM_CREATE_CUDA
   if (ctx->occ_k1 < 1) ctx->occ_k1 = 1;
   if (const char* fm = getenv("NM_K3_FINISH_MAX")) { const long long v = atoll(fm); if (v >= 0) ctx->opt_k3_finish_max = v; }
-  if (const char* lq = getenv("NM_K3_LOUDQ")) ctx->opt_k3_loudq = atoi(lq) ? 1 : 0;   // A/B runs of bench.py
   memset(&ctx->stats, 0, sizeof ctx->stats);
   *out = ctx;
   return NM_OK;
@@ -707,7 +686,7 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->eps_max,
                     &ctx->gb, &ctx->xhi, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->loud, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
                     &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -732,7 +711,6 @@ int nm_set_option(nm_ctx* ctx, int key, int value) {
       if (value != 0 && value != 1 && value != 2 && value != 4) return fail(ctx, NM_EINVAL, "NM_OPT_K3_GROUP must be 0, 1, 2 or 4");
       ctx->opt_k3_group = value;
       return NM_OK;
-    case NM_OPT_K3_LOUDQ: ctx->opt_k3_loudq = value ? 1 : 0; return NM_OK;
     case NM_OPT_K3_SPLIT:
       if (value < 0) return fail(ctx, NM_EINVAL, "NM_OPT_K3_SPLIT must be >= 0");
       ctx->opt_k3_split = value;
@@ -847,11 +825,10 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     NM_CUDA(ctx, ctx->q[i].ensure(Wn * sizeof(PixState)));
     NM_CUDA(ctx, ctx->rq[i].ensure(Wn * sizeof(PixState)));
   }
-  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(22 * (K + 2) + 4) * sizeof(unsigned long long)));
+  NM_CUDA(ctx, ctx->qctr.ensure((size_t)(13 * (K + 2) + 4) * sizeof(unsigned long long)));
   NM_CUDA(ctx, ctx->rq_pix.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->rq_iter.ensure(Wn * sizeof(int32_t)));
   NM_CUDA(ctx, ctx->events.ensure(Wn * sizeof(PixState)));
-  if (ctx->opt_k3_loudq) NM_CUDA(ctx, ctx->loud.ensure(Wn * sizeof(PixState)));
 
   cudaStream_t s = ctx->stream;
   NM_CUDA(ctx, cudaMemsetAsync(ctx->Z.p, 0, (size_t)(J1 + 8) * sizeof(double2), s));
@@ -1176,41 +1153,8 @@ int nm_fp64_peak(nm_ctx* ctx, int kind, int iters, double* inst_per_s, double* m
   if (!ctx || kind < 0 || kind > 15 || iters < 1) return NM_EINVAL;
   if (int rc = set_device(ctx)) return rc;
   NM_CUDA(ctx, ctx->fixapply.ensure(64));
-  // kinds 4-7: DFMA + 0/8/16/24 integer operations per 8 DFMA at full occupancy (64 warps/SM); 8-11: the
-  // same at 16 warps/SM (k3_fast's occupancy). The rate returned counts the FP64 instructions only.
-  // kinds 12-15: DFMA with 3 / 2 / 1 distinct register operands per instruction, DADD with 2 (64 warps/SM).
-  const unsigned blocks = (unsigned)ctx->sm_count * ((kind >= 8 && kind < 12) ? 2 : 8);
-  cudaEvent_t a, b;
-  NM_CUDA(ctx, cudaEventCreate(&a));
-  NM_CUDA(ctx, cudaEventCreate(&b));
-  float best = 1e30f;
-  for (int rep = 0; rep < 4; rep++) {
-    NM_CUDA(ctx, cudaEventRecord(a, ctx->stream));
-    double* sink = ctx->fixapply.as<double>();
-    if (kind == 0) fp64_peak_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else if (kind == 1) fp64_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else if (kind == 2) fp64_peak_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else if (kind == 3) fp64_k3mix_kernel<<<blocks, 256, 0, ctx->stream>>>(sink, iters / 4 + 1, 0.3, -0.2, 0.31, -0.19);
-    else if (kind == 12) fp64_operand_kernel<3><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else if (kind == 13) fp64_operand_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else if (kind == 14) fp64_operand_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else if (kind == 15) fp64_operand_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9);
-    else if ((kind & 3) == 0) fp64_int_mix_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
-    else if ((kind & 3) == 1) fp64_int_mix_kernel<8><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
-    else if ((kind & 3) == 2) fp64_int_mix_kernel<16><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
-    else fp64_int_mix_kernel<24><<<blocks, 256, 0, ctx->stream>>>(sink, iters, 1.0000001, 1e-9, 3, 5);
-    NM_CUDA(ctx, cudaGetLastError());
-    NM_CUDA(ctx, cudaEventRecord(b, ctx->stream));
-    NM_CUDA(ctx, cudaEventSynchronize(b));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    if (rep > 0 && ms < best) best = ms;
-  }
-  cudaEventDestroy(a); cudaEventDestroy(b);
-  double inst = (double)blocks * 256.0 * (double)iters * 8.0;
-  if (kind == 3) inst = (double)blocks * 256.0 * (double)(iters / 4 + 1) * 4.0 * 10.0;  // 10 counted FP64 inst per pixel-iteration
-  if (inst_per_s) *inst_per_s = inst / (best * 1e-3);
-  if (ms_out) *ms_out = best;
+  const int e = nm_probe_run((void*)ctx->stream, ctx->sm_count, kind, iters, ctx->fixapply.as<double>(), inst_per_s, ms_out);   // fp64_probe.cu
+  if (e != 0) return fail(ctx, NM_ECUDA, "nm_fp64_peak: %s", cudaGetErrorString((cudaError_t)e));
   return NM_OK;
 }
 

@@ -282,4 +282,5 @@ int nmv_host_in_cardioid(nmv_view* v, int r, int c) {
   return guarded(v, [&]() { return newman_b200::in_cardioid_pixel(hp_of(v), r, c) ? 1 : 0; });
 }
 
+int nmv_host_selfcheck(void) { return newman_b200::host_mpf_layout_ok() ? 1 : 0; }
 }  // extern "C"

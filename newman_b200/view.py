@@ -57,6 +57,7 @@ VIEW_API = {
     "nmv_host_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nmv_host_cardioid": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nmv_host_in_cardioid": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "nmv_host_selfcheck": (C.c_int, []),
 }
 
 _bound = False

@@ -128,33 +128,3 @@ def test_split_levels_vs_oraclep(kat, group):
     finally:
         dev.close()
 
-
-@needs_ref
-@pytest.mark.parametrize("group", [4, 2])
-@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D90", "KAT-S"])
-def test_loud_queue_vs_oraclep(kat, group):
-    """NM_OPT_K3_LOUDQ: the few samples of a warp whose delta has come within reach of |Z| (their last iterations
-    before they escape) are exported to the level's loud queue, which a second launch of k3_fast runs one state per
-    lane with the per-iteration filter, while the warp they came from runs on without it (k3_fast.cuh). Rasters,
-    glitch lists and executed-iteration counts must not change — plain, floatexp series and scaled forms. (Like the
-    level split, the loud queue is only used by frames above a minimum size, which NM_OPT_K3_SPLIT = 2 lowers.)"""
-    t, er, ei = kat_inputs(kat)
-    dev = newman_b200.Device(0)
-    try:
-        dev.set_option(L.OPT_K3_FINISH_MAX, 0)
-        dev.set_option(L.OPT_K3_GROUP, group)
-        base = p_render_deep(t, er, ei, mode=0)
-        checked = {}
-        for loudq in (0, 1):
-            dev.set_option(L.OPT_K3_LOUDQ, loudq)
-            for split in (0, 2):
-                dev.set_option(L.OPT_K3_SPLIT, split)
-                gs = check(dev, t, er, ei, 0, base)
-                checked[(loudq, split)] = gs["kernel_launches"]
-                ts, mr, mi = t.floatexp(er, ei)
-                check(dev, t.floatexp(), er, ei, 0, base)
-                check(dev, ts, mr, mi, 0, base)
-        print(kat, group, "launches", checked)
-        assert checked[(1, 2)] > checked[(0, 2)]   # the loud passes were launched
-    finally:
-        dev.close()

@@ -65,16 +65,6 @@ def test_full_size_frame_properties(name, n_sample):
         assert digest(a) == digest(b)
         for s1, s2 in zip(res["stats"], res2["stats"]):
             assert s1["executed_iters"] == s2["executed_iters"] and s1["glitched"] == s2["glitched"]
-        # (b') the loud queue (NM_OPT_K3_LOUDQ, k3_fast.cuh) changes the schedule, never a result
-        dev.set_option(newman_b200._lib.OPT_K3_LOUDQ, 0)
-        it = iter(list(chain))
-        res3 = pipeline.render_rounds(dev, primary, lambda gp: next(it), nc, rows)
-        dev.set_option(newman_b200._lib.OPT_K3_LOUDQ, 1)
-        assert digest(dev.read_rows()) == digest(a)
-        for s1, s3 in zip(res["stats"], res3["stats"]):
-            assert s1["executed_iters"] == s3["executed_iters"] and s1["glitched"] == s3["glitched"]
-        print(name, "k3 ms with / without the loud queue:", [round(s["ms_k3"], 2) for s in res2["stats"]],
-              [round(s["ms_k3"], 2) for s in res3["stats"]])
         # (c) every sample resolved
         assert a["iterations"].min() >= 0 and a["iterations"].max() <= N
         # (a) strided sample vs Oracle-P on the same samples, primary reference

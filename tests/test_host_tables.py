@@ -206,3 +206,10 @@ def test_pipelined_tables_edge_lengths(N):
         same_tables(hs[0], hs[2])
         if center[0] == "-0.1":
             assert hs[0]["M"] == N and not hs[0]["has_escape"]
+
+
+def test_pooled_mpf_layout_selfcheck():
+    """hp_host.cpp lays arbitrary-precision values out by hand in limb pools (the pipelined table build); the library
+    checks once per process that such values behave exactly like mpf_init2 values under the running libgmp."""
+    from newman_b200 import view
+    assert view._lib().nmv_host_selfcheck() == 1
