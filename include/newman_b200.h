@@ -55,6 +55,8 @@ NM_API const char* nm_last_error(const nm_ctx* ctx); /* ctx may be NULL: last er
 NM_API const char* nm_version(void);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream. */
 NM_API int nm_set_stream(nm_ctx* ctx, void* cuda_stream);
+/* the stream the ctx currently runs on (its own, or the one nm_set_stream installed), as a cudaStream_t */
+NM_API int nm_get_stream(nm_ctx* ctx, void** cuda_stream);
 NM_API int nm_sync(nm_ctx* ctx);
 /* Tuning / verification switches (defaults in parentheses):
  *   NM_OPT_K2_LITERAL (0)  1: K2 scans every series index like the reference (mandelbrot.cpp:165-181)
@@ -273,6 +275,9 @@ NM_API int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, in
 /* force: 1 evaluate the series in floatexp, 2 also floatexp eps + scaled delta states, even where doubles
  * suffice (both are automatic once the view needs them); 0 automatic */
 NM_API int nmv_set_floatexp(nmv_view* v, int force);
+/* Mandelbrot::devices / band_rows: n > 1 splits every frame over these GPUs (one host thread, one context and one NCCL
+ * rank per GPU inside the view; see "multi-GPU" below); n = 0 returns to the single `device`. band_rows <= 0 keeps 4. */
+NM_API int nmv_set_devices(nmv_view* v, const int* devices, int n, int band_rows);
 /* findProbe (mandelbrot.cpp:73-95). mode 0: the reference's exhaustive arbitrary-precision search; 1:
  * GPU-assisted (candidates' orbit lengths by K2/K3 against one reference, exact mpf check of the
  * short-list). nmv_set_probe_search picks what precompute() uses (default 1); nmv_find_probe runs one
@@ -319,6 +324,36 @@ NM_API int nmv_host_selfcheck(void);
 NM_API int nmv_host_coords(nmv_view* v, double* c_re, double* c_im);       /* mandelbrot.cpp:271, 275, 234 */
 NM_API int nmv_host_cardioid(nmv_view* v, uint8_t* mask_or_null);          /* returns NM_CARDIOID_* */
 NM_API int nmv_host_in_cardioid(nmv_view* v, int r, int c);                /* mandelbrot.cpp:63-71 */
+
+/* ==== multi-GPU: one frame over several GPUs of a node ==========================================
+ * The path shards by bands of grid rows with no collective on the per-pixel data path (reference viewer.cpp:193-238:
+ * the beauty render computes rows one after another; rows are independent once precompute() has run). A render group
+ * has one nmm_rank per GPU: threads of one process (what `Mandelbrot::devices` sets up by itself) or one process per
+ * GPU (torchrun, MPI ...: rank 0 calls nmm_unique_id and the caller carries the 128 bytes to the others). Rank r renders
+ * the blocks of `band_rows` grid rows b = r, r + world, ... (band_rows a multiple of the multisampling factor, so that a
+ * colour-resolve block never straddles GPUs). Exchanged per frame: each reference's tables (host GMP on rank 0) by
+ * ncclBroadcast; the 8-byte "which glitched sample is the next reference" MIN by ncclAllReduce; the finished bands.
+ * NCCL is bound at run time (dlopen libnccl.so.2). world == 1 needs no NCCL. */
+typedef struct nmm_rank nmm_rank;
+#define NMM_ID_BYTES 128
+#define NMM_RETURN_LOCAL 0 /* every rank copies its own bands into the host image IT was given (threads of one process,
+                              or a shared page-locked mapping): every GPU over its own PCIe link */
+#define NMM_RETURN_ROOT 1  /* bands travel to rank 0 by ncclSend/ncclRecv; rank 0 writes the host image */
+NM_API int nmm_unique_id(uint8_t id[NMM_ID_BYTES]);
+NM_API int nmm_create(int device, int rank, int world, const uint8_t id[NMM_ID_BYTES], nmm_rank** out);
+NM_API void nmm_destroy(nmm_rank* rk);
+NM_API const char* nmm_last_error(const nmm_rank* rk);   /* rk may be NULL: last error of nmm_create / nmm_unique_id */
+NM_API nm_ctx* nmm_ctx(nmm_rank* rk);
+/* Collective: every rank calls it with a view in the SAME state (same size, N, centre, sz, tolerances, options).
+ * precompute() (rank 0: probe search, orbit, series; mandelbrot.cpp:261-267) + every row of this rank's bands.
+ * out_raster: nr*nc records of the whole frame — see NMM_RETURN_*; NULL (on every rank alike) leaves the bands on the
+ * GPUs for nmm_resolve. info (may be NULL): counters summed over the ranks, device_ms the slowest rank's. */
+NM_API int nmm_render(nmm_rank* rk, nmv_view* view, int band_rows, nm_escape* out_raster, int return_mode, nmv_frame_info* info);
+/* Collective colour resolve of the bands of the last nmm_render (K4 per band: getColor/colorLine, viewer.cpp:84-124),
+ * returned as (nr/sc) x (nc/sc) x 3 bytes like nm_resolve. */
+NM_API int nmm_resolve(nmm_rank* rk, const uint8_t* pal_rgb, int n_pal, int sc, int smooth, uint8_t* out_rgb, int return_mode);
+/* host milliseconds this rank has spent inside exchanges (broadcasts, reductions, band return) since nmm_create */
+NM_API double nmm_exchange_ms(const nmm_rank* rk);
 
 /* ==== palette: MultiWaveGenerator through C (include/newman_b200/multiwave.h == reference
  * multiwave.h:8-37). The N-entry RGB table is built on the host, like the reference

@@ -66,6 +66,7 @@ public:
 
 namespace newman_b200 {
 class Engine;  // GPU context + last frame; shared between copies of a Mandelbrot
+class Group;   // one context + one host thread + one NCCL rank per GPU (set `devices`), shared between copies
 struct FrameInfo {
   bool hardware = false;
   int floatexp = 0;                 // 0 double series, 1 floatexp series, 2 floatexp series + scaled deltas
@@ -83,6 +84,7 @@ class NEWMAN_B200_CXX_API Mandelbrot {
 protected:
   RenderGrid grid;
   std::shared_ptr<newman_b200::Engine> engine_;
+  std::shared_ptr<newman_b200::Group> group_;
   struct Signature;  // view parameters the current raster was rendered for
   std::shared_ptr<Signature> rendered_;
   newman_b200::FrameInfo info_;
@@ -100,6 +102,11 @@ public:
   double glitch_tolerance;  // K3 glitch rule |X_n+d_n|^2 < glitch_tolerance*|X_n|^2
   int max_secondary;        // secondary reference rounds before the final rebasing pass
   int device;               // CUDA device ordinal
+  std::vector<int> devices; // not empty: the frame is split over these GPUs — bands of `band_rows` grid rows
+                            // dealt round-robin, one host thread per GPU, tables by ncclBroadcast, every GPU returning its
+                            // bands over its own PCIe link (the beauty render, viewer.cpp:193-238, on all GPUs of the box);
+                            // the raster is byte-identical to the one-GPU one
+  int band_rows;            // rows per band (a multiple of the multisampling factor keeps colour-resolve blocks on one GPU)
   int host_threads;         // probe-search threads (0 = hardware concurrency)
   int probe_search;         // findProbe: 1 (default) GPU-assisted short-list + exact mpf check of the short-list;
                             // 0 the reference's exhaustive arbitrary-precision search (mandelbrot.cpp:73-95)

@@ -60,6 +60,7 @@ DEVICE_API = {
     "nm_last_error": (C.c_char_p, [C.c_void_p]),
     "nm_version": (C.c_char_p, []),
     "nm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nm_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "nm_sync": (C.c_int, [C.c_void_p]),
     "nm_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "nm_cancel": (C.c_int, [C.c_void_p]),

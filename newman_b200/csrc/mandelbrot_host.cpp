@@ -13,6 +13,11 @@
 
 #include "../../include/newman_b200.h"
 #include "hp_host.h"
+#include "multi_host.h"
+
+#include <cstring>
+#include <memory>
+#include <thread>
 
 namespace newman_b200 {
 
@@ -20,11 +25,13 @@ class Engine {
 public:
   nm_ctx* ctx = nullptr;
   int device;
+  bool owned = true;
   explicit Engine(int dev) : device(dev) {
     int rc = nm_create(dev, &ctx);
     if (rc != NM_OK) throw std::runtime_error(std::string("newman_b200: ") + nm_last_error(nullptr));
   }
-  ~Engine() { if (ctx) nm_destroy(ctx); }
+  explicit Engine(nm_ctx* borrowed) : ctx(borrowed), device(-1), owned(false) {}   // a render group's rank context
+  ~Engine() { if (ctx && owned) nm_destroy(ctx); }
   Engine(const Engine&) = delete;
   Engine& operator=(const Engine&) = delete;
   void check(int rc, const char* what) {
@@ -198,10 +205,268 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
 }
 }  // namespace
 
+
+// ---- one frame over several GPUs ---------------------------------------------------------------------------------
+// Every rank of a render group (multi_host.h) runs this with a Mandelbrot in the same state; nothing of `m` is written.
+// Rank r renders the blocks of `band` grid rows b = r, r + world, ... of the raster. Rank 0 does the host
+// arbitrary-precision work (cardioid classification, probe search on its own GPU, orbit + series of every reference) and
+// broadcasts each reference's tables; the choice of the next secondary reference is the single-GPU rule (earliest flag
+// iteration, lowest sample id on ties) taken over all ranks by one 8-byte MIN all-reduce, so the N-GPU raster is
+// byte-identical to the 1-GPU one. out / mode: see nmm_render (include/newman_b200.h).
+namespace newman_b200 {
+
+namespace {
+struct FrameHeader {   // rank 0 -> all, once per reference
+  int32_t kind;        // 2: a deep reference follows; 0: rank 0 failed (text in `msg`)
+  int32_t M, has_escape, fe, cmode, mask_bytes_follow;
+  uint64_t blob_bytes;
+  char msg[160];
+};
+size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+}  // namespace
+
+void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, int mode, FrameInfo& info) {
+  const double t_begin = now_s();
+  nm_ctx* ctx = link.ctx;
+  info = FrameInfo();
+  ViewHP v;
+  v.center_re = m.center.re.get_mpf_t(); v.center_im = m.center.im.get_mpf_t();
+  v.sz_re = m.sz.re.get_mpf_t(); v.sz_im = m.sz.im.get_mpf_t();
+  v.nr = m.rows(); v.nc = m.cols(); v.N = m.N;
+  v.prec = max_prec(m.center, m.sz);
+  info.precision_bits = (int)v.prec;
+  if (band < 1 || v.nr % band) throw std::runtime_error("newman_b200: band_rows must divide the number of grid rows");
+  const int n_blocks = v.nr / band;
+  const int nb_loc = RankLink::blocks_of(link.rank, link.world, n_blocks);
+  const int nr_loc = nb_loc * band;
+  auto global_row = [&](int r_loc) { return ((r_loc / band) * link.world + link.rank) * band + r_loc % band; };
+  auto check = [&](int rc, const char* what) {
+    if (rc != NM_OK) throw std::runtime_error(std::string("newman_b200: ") + what + ": " + nm_last_error(ctx));
+  };
+  auto absorb = [&](const nm_stats& st) {
+    info.executed_iters += st.executed_iters; info.series_evals += st.series_evals;
+    info.skipped_pixels += st.skipped_pixels; info.rebased += st.rebased; info.fixups += st.fixups;
+    info.kernel_launches += st.kernel_launches;
+    info.device_ms += st.ms_k1 + st.ms_k2 + st.ms_k3;
+  };
+
+  if (m.useHardware()) {
+    // plain double: the coordinates are a few thousand mpf operations — every rank forms its own, nothing is exchanged
+    info.hardware = true;
+    std::vector<double> c_re, c_im, c_im_loc((size_t)(nr_loc > 0 ? nr_loc : 1));
+    pixel_coords(v, c_re, c_im);
+    for (int r = 0; r < nr_loc; r++) c_im_loc[(size_t)r] = c_im[(size_t)global_row(r)];
+    info.host_precompute_s = now_s() - t_begin;
+    if (nr_loc > 0) {
+      check(nm_frame_hw(ctx, c_re.data(), v.nc, c_im_loc.data(), nr_loc, m.N), "nm_frame_hw");
+      check(nm_launch(ctx), "nm_launch");
+      int64_t n_amb = nm_frame_ambiguous(ctx, nullptr, 0);
+      if (n_amb < 0) check((int)n_amb, "nm_frame_ambiguous");
+      if (n_amb > 0) {
+        std::vector<int32_t> amb((size_t)n_amb);
+        nm_frame_ambiguous(ctx, amb.data(), n_amb);
+        for (int32_t pix : amb)
+          if (in_cardioid_pixel(v, global_row(pix / v.nc), pix % v.nc)) {
+            nm_escape e; e.iterations = m.N; e.smoothing = 0.0f;
+            check(nm_poke(ctx, pix, e), "nm_poke");
+          }
+        info.ambiguous = (unsigned long long)n_amb;
+      }
+      nm_stats st; check(nm_frame_stats(ctx, &st), "nm_frame_stats"); absorb(st);
+    }
+  } else {
+    RoundParams rp = {m.N, m.max_secondary, m.force_floatexp, m.error_tolerance, m.glitch_tolerance, m.host_threads};
+    DeepTablesHost T;
+    std::vector<uint8_t> mask;
+    int cmode = NM_CARDIOID_NONE;
+    std::string fail;
+    if (link.rank == 0) {
+      try {
+        cmode = classify_cardioid(v, m.host_threads, mask);
+        if (cmode == NM_CARDIOID_ALL) {
+          ViewHP v1 = v; v1.N = 1;
+          build_tables(v1, v.nr / 2, v.nc / 2, T, 1);
+        } else {
+          int prow, pcol, plen;
+          if (m.probe_search == 0) find_probe(v, m.host_threads, prow, pcol, plen);
+          else {
+            Engine probe_eng(ctx);   // borrows the rank's context for the candidate frame
+            find_probe_assisted(probe_eng, v, rp, m.host_threads, cmode, mask, prow, pcol, plen, nullptr, info);
+          }
+          build_tables(v, prow, pcol, T, m.host_threads);
+        }
+        info.orbit_len = T.M; info.probe_row = T.probe_row; info.probe_col = T.probe_col;
+      } catch (const std::exception& e) { fail = e.what(); }
+      info.host_precompute_s = now_s() - t_begin;
+    }
+    std::vector<int32_t> rq_pix, rq_iter;
+    for (int round = 0;; round++) {
+      // ---- rank 0 packs the reference (header + one blob), everyone receives it --------------------------------
+      FrameHeader h;
+      memset(&h, 0, sizeof h);
+      size_t off_xhi = 0, off_xlo = 0, off_a = 0, off_b = 0, off_c = 0, off_ae = 0, off_be = 0, off_ce = 0, off_er = 0, off_ei = 0,
+             off_ere = 0, off_eie = 0, off_mask = 0;
+      auto layout = [&](int M, int he, int fe, bool with_mask) {
+        size_t o = 0;
+        auto take = [&](size_t bytes) { const size_t at = o; o = align16(o + bytes); return at; };
+        off_xhi = take((size_t)2 * (M + he) * 8); off_xlo = take((size_t)2 * M * 8);
+        off_a = take((size_t)2 * M * 8); off_b = take((size_t)2 * M * 8); off_c = take((size_t)2 * M * 8);
+        if (fe) { off_ae = take((size_t)2 * M * 4); off_be = take((size_t)2 * M * 4); off_ce = take((size_t)2 * M * 4); }
+        off_er = take((size_t)v.nc * 8); off_ei = take((size_t)v.nr * 8);
+        if (fe == 2) { off_ere = take((size_t)v.nc * 4); off_eie = take((size_t)v.nr * 4); }
+        if (with_mask) off_mask = take((size_t)v.nr * v.nc);
+        return o;
+      };
+      const char* blob_host = nullptr;
+      if (link.rank == 0) {
+        if (!fail.empty()) { h.kind = 0; snprintf(h.msg, sizeof h.msg, "%s", fail.c_str()); }
+        else {
+          int fe = T.finite ? 0 : 1;
+          if (T.pitch_exp < -380) fe = 2;
+          if (rp.force_floatexp > fe) fe = rp.force_floatexp > 2 ? 2 : rp.force_floatexp;
+          h.kind = 2; h.M = T.M; h.has_escape = T.has_escape ? 1 : 0; h.fe = fe; h.cmode = round == 0 ? cmode : NM_CARDIOID_NONE;
+          h.mask_bytes_follow = (round == 0 && cmode == NM_CARDIOID_MASK) ? 1 : 0;
+          h.blob_bytes = layout(h.M, h.has_escape, fe, h.mask_bytes_follow != 0);
+          char* b = (char*)link.pinned(h.blob_bytes);
+          memcpy(b + off_xhi, T.x_hi.data(), (size_t)2 * (h.M + h.has_escape) * 8);
+          memcpy(b + off_xlo, T.x_lo.data(), (size_t)2 * h.M * 8);
+          memcpy(b + off_a, fe ? T.a_m.data() : T.a.data(), (size_t)2 * h.M * 8);
+          memcpy(b + off_b, fe ? T.b_m.data() : T.b.data(), (size_t)2 * h.M * 8);
+          memcpy(b + off_c, fe ? T.c_m.data() : T.c.data(), (size_t)2 * h.M * 8);
+          if (fe) {
+            memcpy(b + off_ae, T.a_e.data(), (size_t)2 * h.M * 4); memcpy(b + off_be, T.b_e.data(), (size_t)2 * h.M * 4);
+            memcpy(b + off_ce, T.c_e.data(), (size_t)2 * h.M * 4);
+          }
+          memcpy(b + off_er, fe == 2 ? T.eps_re_m.data() : T.eps_re.data(), (size_t)v.nc * 8);
+          memcpy(b + off_ei, fe == 2 ? T.eps_im_m.data() : T.eps_im.data(), (size_t)v.nr * 8);
+          if (fe == 2) { memcpy(b + off_ere, T.eps_re_e.data(), (size_t)v.nc * 4); memcpy(b + off_eie, T.eps_im_e.data(), (size_t)v.nr * 4); }
+          if (h.mask_bytes_follow) memcpy(b + off_mask, mask.data(), (size_t)v.nr * v.nc);
+          blob_host = b;
+        }
+      }
+      link.bcast_host(&h, sizeof h);
+      if (h.kind == 0) throw std::runtime_error(std::string("newman_b200: rank 0 failed: ") + h.msg);
+      layout(h.M, h.has_escape, h.fe, h.mask_bytes_follow != 0);
+      const char* d = (const char*)link.bcast_device(blob_host, h.blob_bytes, 0);
+      info.floatexp = h.fe;
+      if (round == 0) { info.orbit_len = h.M; cmode = h.cmode; }
+
+      // ---- this rank's bands against the reference -------------------------------------------------------------
+      const bool last = round >= rp.max_secondary;
+      const bool listed = round > 0;
+      if (nr_loc > 0 && (!listed || !rq_pix.empty())) {
+        nm_deep_tables t;
+        memset(&t, 0, sizeof t);
+        t.M = h.M; t.N = rp.N; t.has_escape = h.has_escape; t.tol = rp.tol; t.glitch_tol = rp.gtol;
+        t.x_hi = (const double*)(d + off_xhi); t.x_lo = (const double*)(d + off_xlo);
+        t.a = (const double*)(d + off_a); t.b = (const double*)(d + off_b); t.c = (const double*)(d + off_c);
+        if (h.fe) { t.a_exp = (const int32_t*)(d + off_ae); t.b_exp = (const int32_t*)(d + off_be); t.c_exp = (const int32_t*)(d + off_ce); }
+        const double* eps_im_loc = (const double*)link.gather_rows(d + off_ei, 8, band, n_blocks, 0);
+        if (h.fe == 2) {
+          t.eps_re_exp = (const int32_t*)(d + off_ere);
+          t.eps_im_exp = (const int32_t*)link.gather_rows(d + off_eie, 4, band, n_blocks, 1);
+        }
+        const uint8_t* mask_loc = nullptr;
+        if (h.mask_bytes_follow) mask_loc = (const uint8_t*)link.gather_rows(d + off_mask, (size_t)v.nc, band, n_blocks, 2);
+        check(nm_frame_deep(ctx, &t, (const double*)(d + off_er), v.nc, eps_im_loc, nr_loc, listed ? NM_CARDIOID_NONE : h.cmode,
+                            mask_loc, listed ? rq_pix.data() : nullptr, listed ? (int64_t)rq_pix.size() : 0,
+                            last ? NM_MODE_REBASE : NM_MODE_REQUEUE),
+              "nm_frame_deep");
+        check(nm_launch(ctx), "nm_launch");
+        nm_stats st; check(nm_frame_stats(ctx, &st), "nm_frame_stats"); absorb(st);
+        int64_t n_rq = nm_frame_requeue(ctx, nullptr, nullptr, 0);
+        if (n_rq < 0) check((int)n_rq, "nm_frame_requeue");
+        rq_pix.resize((size_t)n_rq); rq_iter.resize((size_t)n_rq);
+        if (n_rq) nm_frame_requeue(ctx, rq_pix.data(), rq_iter.data(), n_rq);
+        info.glitched += (unsigned long long)n_rq;
+      } else {
+        rq_pix.clear(); rq_iter.clear();
+      }
+      info.references++;
+      // ---- next reference: the glitched sample flagged earliest, lowest (global) sample id on ties, over all ranks ----
+      uint64_t key = ~(uint64_t)0;
+      for (size_t i = 0; i < rq_pix.size(); i++) {
+        const uint64_t g = (uint64_t)global_row(rq_pix[i] / v.nc) * (uint64_t)v.nc + (uint64_t)(rq_pix[i] % v.nc);
+        const uint64_t k = ((uint64_t)rq_iter[i] << 40) | g;
+        if (k < key) key = k;
+      }
+      key = link.allreduce_min(key);
+      if (key == ~(uint64_t)0) break;
+      if (link.rank == 0) {
+        const uint64_t g = key & (((uint64_t)1 << 40) - 1);
+        const double t_hp = now_s();
+        try { build_tables(v, (int)(g / (uint64_t)v.nc), (int)(g % (uint64_t)v.nc), T, rp.host_threads); }
+        catch (const std::exception& e) { fail = e.what(); }
+        info.host_precompute_s += now_s() - t_hp;
+      }
+    }
+  }
+
+  // ---- bands back to the host raster ---------------------------------------------------------------------------
+  if (out || mode == NMM_RETURN_LOCAL) {
+    const size_t block_bytes = (size_t)band * v.nc * sizeof(nm_escape);
+    void* bd = link.band_buffer((size_t)(nr_loc > 0 ? nr_loc : 1) * v.nc * sizeof(nm_escape));
+    if (nr_loc > 0) check(nm_read_rows(ctx, 0, nr_loc, (nm_escape*)bd), "nm_read_rows");
+    link.return_band(bd, block_bytes, n_blocks, out, mode);
+  } else if (link.world > 1 && mode == NMM_RETURN_ROOT) {
+    const size_t block_bytes = (size_t)band * v.nc * sizeof(nm_escape);
+    void* bd = link.band_buffer((size_t)(nr_loc > 0 ? nr_loc : 1) * v.nc * sizeof(nm_escape));
+    if (nr_loc > 0) check(nm_read_rows(ctx, 0, nr_loc, (nm_escape*)bd), "nm_read_rows");
+    link.return_band(bd, block_bytes, n_blocks, nullptr, mode);
+  }
+  // ---- counters over the group ----------------------------------------------------------------------------------
+  uint64_t sums[8] = {info.executed_iters, info.series_evals, info.skipped_pixels, info.glitched, info.rebased, info.fixups,
+                      info.kernel_launches, info.ambiguous};
+  link.allreduce_sum(sums, 8);
+  info.executed_iters = sums[0]; info.series_evals = sums[1]; info.skipped_pixels = sums[2]; info.glitched = sums[3];
+  info.rebased = sums[4]; info.fixups = sums[5]; info.kernel_launches = sums[6]; info.ambiguous = sums[7];
+  info.device_ms = (double)link.allreduce_max((uint64_t)(info.device_ms * 1e3)) * 1e-3;
+  info.frame_s = now_s() - t_begin;
+}
+
+}  // namespace newman_b200
+
+
+namespace newman_b200 {
+// The render group behind `Mandelbrot::devices`: one RankLink (context + NCCL rank) per GPU, created by one thread per
+// GPU (ncclCommInitRank is a rendezvous), and one thread per GPU again for every frame.
+class Group {
+public:
+  std::vector<int> devices;
+  std::vector<std::unique_ptr<RankLink> > links;
+  explicit Group(const std::vector<int>& devs) : devices(devs), links(devs.size()) {
+    uint8_t id[NMM_ID_BYTES];
+    RankLink::unique_id(id);
+    std::vector<std::string> errs(devs.size());
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < devs.size(); r++)
+      th.emplace_back([&, r]() {
+        try { links[r].reset(new RankLink(devs[r], (int)r, (int)devs.size(), id)); }
+        catch (const std::exception& e) { errs[r] = e.what(); }
+      });
+    for (std::thread& t : th) t.join();
+    for (const std::string& e : errs) if (!e.empty()) throw std::runtime_error(e);
+  }
+  void render(Mandelbrot& m, int band, nm_escape* out, FrameInfo& info) {
+    std::vector<std::string> errs(links.size());
+    std::vector<FrameInfo> infos(links.size());
+    std::vector<std::thread> th;
+    for (size_t r = 0; r < links.size(); r++)
+      th.emplace_back([&, r]() {
+        try { render_collective(*links[r], m, band, out, NMM_RETURN_LOCAL, infos[r]); }
+        catch (const std::exception& e) { errs[r] = e.what(); }
+      });
+    for (std::thread& t : th) t.join();
+    for (const std::string& e : errs) if (!e.empty()) throw std::runtime_error(e);
+    info = infos[0];
+  }
+};
+}  // namespace newman_b200
+
 Mandelbrot::Mandelbrot() : Mandelbrot(1, 1) {}
 
 Mandelbrot::Mandelbrot(int nr, int nc)
-    : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(1), device(0), host_threads(0),
+    : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(1), device(0), band_rows(4), host_threads(0),
       probe_search(1), force_floatexp(0) {
   // default full view (mandelbrot.cpp:13-14)
   center.re = -0.5;
@@ -278,6 +543,21 @@ void Mandelbrot::computeRow(int r) {
 
 void Mandelbrot::renderFrame() {
   const double t_begin = now_s();
+  if (!devices.empty()) {
+    // one frame over several GPUs (render_collective above): a thread, a context and an NCCL rank per GPU
+    if (!group_ || group_->devices != devices) group_ = std::make_shared<newman_b200::Group>(devices);
+    int band = band_rows > 0 ? band_rows : 1;
+    while (grid.nr % band) band--;   // any raster renders; bands shrink to the largest divisor of the row count
+    group_->render(*this, band, reinterpret_cast<nm_escape*>(grid.values.data()), info_);
+    std::shared_ptr<Signature> sg = std::make_shared<Signature>();
+    sg->N = N; sg->nr = grid.nr; sg->nc = grid.nc; sg->max_secondary = max_secondary;
+    sg->tol = error_tolerance; sg->gtol = glitch_tolerance;
+    sg->cre = mpf_class(center.re, center.re.get_prec()); sg->cim = mpf_class(center.im, center.im.get_prec());
+    sg->sre = mpf_class(sz.re, sz.re.get_prec()); sg->sim = mpf_class(sz.im, sz.im.get_prec());
+    rendered_ = sg;
+    info_.frame_s = now_s() - t_begin;
+    return;
+  }
   if (!engine_ || engine_->device != device) engine_ = std::make_shared<newman_b200::Engine>(device);
   newman_b200::Engine& eng = *engine_;
   nm_ctx* ctx = eng.ctx;

@@ -703,6 +703,12 @@ int nm_set_stream(nm_ctx* ctx, void* cuda_stream) {
   return NM_OK;
 }
 
+int nm_get_stream(nm_ctx* ctx, void** cuda_stream) {
+  if (!ctx || !cuda_stream) return NM_EINVAL;
+  *cuda_stream = (void*)ctx->stream;
+  return NM_OK;
+}
+
 int nm_set_option(nm_ctx* ctx, int key, int value) {
   if (!ctx) return NM_EINVAL;
   switch (key) {

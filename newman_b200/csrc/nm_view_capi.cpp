@@ -3,11 +3,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <memory>
+#include <stdexcept>
 #include <string>
 
 #include "../../include/newman_b200.h"
 #include "../../include/newman_b200/mandelbrot.h"
 #include "hp_host.h"
+#include "multi_host.h"
 
 namespace {
 struct Access : public Mandelbrot {  // reach the protected raster for bulk copies
@@ -24,8 +27,28 @@ struct nmv_view {
   nmv_view(int nr, int nc) : m(nr, nc) {}
 };
 
+struct nmm_rank {
+  std::unique_ptr<newman_b200::RankLink> link;
+  std::string err;
+  int nr = 0, nc = 0, N = 0, band = 0;   // geometry of the last nmm_render (what nmm_resolve resolves)
+};
+
+namespace newman_b200 {
+void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, int mode, FrameInfo& info);   // mandelbrot_host.cpp
+}
+
 namespace {
 std::string g_err;
+
+void fill_info(const newman_b200::FrameInfo& f, nmv_frame_info* out) {
+  out->hardware = f.hardware ? 1 : (f.floatexp ? 1 + f.floatexp : 0); out->precision_bits = f.precision_bits; out->orbit_len = f.orbit_len;
+  out->probe_row = f.probe_row; out->probe_col = f.probe_col; out->references = f.references;
+  out->executed_iters = f.executed_iters; out->series_evals = f.series_evals; out->skipped_pixels = f.skipped_pixels;
+  out->probe_iters = f.probe_iters; out->probe_exact = f.probe_exact;
+  out->glitched = f.glitched; out->rebased = f.rebased; out->fixups = f.fixups; out->kernel_launches = f.kernel_launches;
+  out->ambiguous = f.ambiguous;
+  out->host_precompute_s = f.host_precompute_s; out->device_ms = f.device_ms; out->frame_s = f.frame_s;
+}
 
 newman_b200::ViewHP hp_of(nmv_view* v) {
   newman_b200::ViewHP h;
@@ -280,6 +303,61 @@ int nmv_host_cardioid(nmv_view* v, uint8_t* mask_or_null) {
 
 int nmv_host_in_cardioid(nmv_view* v, int r, int c) {
   return guarded(v, [&]() { return newman_b200::in_cardioid_pixel(hp_of(v), r, c) ? 1 : 0; });
+}
+
+// ---- multi-GPU render groups (multi_host.h; render_collective in mandelbrot_host.cpp) ----------------------------
+int nmm_unique_id(uint8_t id[NMM_ID_BYTES]) {
+  try { newman_b200::RankLink::unique_id(id); return NM_OK; }
+  catch (const std::exception& e) { g_err = e.what(); return NM_ECUDA; }
+}
+int nmm_create(int device, int rank, int world, const uint8_t id[NMM_ID_BYTES], nmm_rank** out) {
+  if (!out) return NM_EINVAL;
+  *out = nullptr;
+  try {
+    nmm_rank* rk = new nmm_rank();
+    rk->link.reset(new newman_b200::RankLink(device, rank, world, id));
+    *out = rk;
+    return NM_OK;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return g_err.find("no CUDA device") != std::string::npos ? NM_ENODEV : NM_ECUDA;
+  }
+}
+void nmm_destroy(nmm_rank* rk) { delete rk; }
+const char* nmm_last_error(const nmm_rank* rk) { return rk ? rk->err.c_str() : g_err.c_str(); }
+nm_ctx* nmm_ctx(nmm_rank* rk) { return rk ? rk->link->ctx : nullptr; }
+double nmm_exchange_ms(const nmm_rank* rk) { return rk ? rk->link->exchange_ms() : 0.0; }
+int nmm_render(nmm_rank* rk, nmv_view* view, int band_rows, nm_escape* out_raster, int return_mode, nmv_frame_info* info) {
+  if (!rk || !view) return NM_EINVAL;
+  try {
+    newman_b200::FrameInfo f;
+    newman_b200::render_collective(*rk->link, view->m, band_rows, out_raster, return_mode, f);
+    rk->nr = view->m.rows(); rk->nc = view->m.cols(); rk->N = view->m.N; rk->band = band_rows;
+    if (info) fill_info(f, info);
+    return NM_OK;
+  } catch (const std::exception& e) { rk->err = e.what(); return NM_ECUDA; }
+}
+int nmm_resolve(nmm_rank* rk, const uint8_t* pal_rgb, int n_pal, int sc, int smooth, uint8_t* out_rgb, int return_mode) {
+  if (!rk || !pal_rgb || sc < 1) return NM_EINVAL;
+  try {
+    newman_b200::RankLink& l = *rk->link;
+    if (rk->band < 1 || rk->band % sc || rk->nc % sc) throw std::runtime_error("nmm_resolve: band_rows of the last nmm_render must be a multiple of sc");
+    const int n_blocks = rk->nr / rk->band;
+    const int nr_loc = newman_b200::RankLink::blocks_of(l.rank, l.world, n_blocks) * rk->band;
+    const size_t block_bytes = (size_t)(rk->band / sc) * (rk->nc / sc) * 3;
+    void* bd = l.band_buffer((size_t)(nr_loc > 0 ? nr_loc / sc : 1) * (rk->nc / sc) * 3);
+    if (nr_loc > 0 && nm_resolve(l.ctx, pal_rgb, n_pal, rk->N, sc, smooth, (uint8_t*)bd) != NM_OK)
+      throw std::runtime_error(std::string("nm_resolve: ") + nm_last_error(l.ctx));
+    l.return_band(bd, block_bytes, n_blocks, out_rgb, return_mode);
+    return NM_OK;
+  } catch (const std::exception& e) { rk->err = e.what(); return NM_ECUDA; }
+}
+
+int nmv_set_devices(nmv_view* v, const int* devices, int n, int band_rows) {
+  if (!v || n < 0 || (n > 0 && !devices)) return NM_EINVAL;
+  v->m.devices.assign(devices, devices + n);
+  if (band_rows > 0) v->m.band_rows = band_rows;
+  return NM_OK;
 }
 
 int nmv_host_selfcheck(void) { return newman_b200::host_mpf_layout_ok() ? 1 : 0; }

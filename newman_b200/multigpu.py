@@ -133,3 +133,75 @@ class SharedHostRaster:
         except BufferError:
             pass
         self._f.close()
+
+
+class RenderGroup:
+    """One rank of a multi-GPU render group behind the C-ABI (nmm_*, include/newman_b200.h): the round loop, the table
+    broadcasts (ncclBroadcast), the 8-byte next-reference MIN (ncclAllReduce) and the band return all run inside
+    libnewman_b200.so; this class only carries the 128-byte NCCL id from rank 0 to the other processes (through
+    torch.distributed, which the launcher has already set up) and hands over views and output buffers.
+
+    One process per GPU (torchrun): RenderGroup(device=LOCAL_RANK, rank=RANK, world=WORLD_SIZE).
+    (Threads of one process need none of this: Mandelbrot.set_devices([...]).)"""
+
+    RETURN_LOCAL, RETURN_ROOT = 0, 1
+
+    def __init__(self, device, rank=0, world=1, backend_device=None):
+        import ctypes as C
+        from . import _lib as L
+        from . import view as V
+        self.C, self.L, self.V = C, L, V
+        self.lib = V._lib()
+        self.rank, self.world, self.device = rank, world, device
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if world > 1:
+            if rank == 0:
+                raw = (C.c_uint8 * 128)()
+                rc = self.lib.nmm_unique_id(raw)
+                if rc < 0:
+                    raise L.NmError(rc, self.lib.nmm_last_error(None).decode())
+                idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+            dev = backend_device if backend_device is not None else (
+                torch.device("cuda", device) if dist.get_backend() == "nccl" else torch.device("cpu"))
+            t = idbuf.to(dev)
+            dist.broadcast(t, 0)
+            idbuf = t.cpu()
+        raw = (C.c_uint8 * 128)(*idbuf.tolist())
+        h = C.c_void_p()
+        rc = self.lib.nmm_create(device, rank, world, raw, C.byref(h))
+        if rc < 0:
+            raise L.NmError(rc, self.lib.nmm_last_error(None).decode())
+        self.h = h
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise self.L.NmError(rc, self.lib.nmm_last_error(self.h).decode())
+        return rc
+
+    def render(self, view, band_rows, out=None, return_mode=1):
+        """Collective. view: newman_b200.Mandelbrot in the same state on every rank. out: (nr, nc) ESCAPE_DTYPE / (nr, nc, 2)
+        int32 host array or torch tensor (rank 0 for RETURN_ROOT; every rank for RETURN_LOCAL) or None. -> frame info dict"""
+        info = self.V.FrameInfo()
+        ptr = None if out is None else self.L.ptr(out)
+        self._ck(self.lib.nmm_render(self.h, view.h, int(band_rows), ptr, int(return_mode), self.C.byref(info)))
+        return info.asdict()
+
+    def resolve(self, pal_rgb, sc, smooth, out=None, return_mode=1):
+        pal = np.ascontiguousarray(pal_rgb, dtype=np.uint8)
+        ptr = None if out is None else self.L.ptr(out)
+        self._ck(self.lib.nmm_resolve(self.h, self.L.ptr(pal), len(pal.reshape(-1)) // 3, int(sc), 1 if smooth else 0, ptr,
+                                      int(return_mode)))
+
+    def exchange_ms(self):
+        return float(self.lib.nmm_exchange_ms(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nmm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -58,6 +58,16 @@ VIEW_API = {
     "nmv_host_cardioid": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nmv_host_in_cardioid": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "nmv_host_selfcheck": (C.c_int, []),
+    "nmv_set_devices": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
+    # multi-GPU render groups (include/newman_b200.h "multi-GPU"; newman_b200/multigpu.py: RenderGroup)
+    "nmm_unique_id": (C.c_int, [C.c_void_p]),
+    "nmm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nmm_destroy": (None, [C.c_void_p]),
+    "nmm_last_error": (C.c_char_p, [C.c_void_p]),
+    "nmm_ctx": (C.c_void_p, [C.c_void_p]),
+    "nmm_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(FrameInfo)]),
+    "nmm_resolve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "nmm_exchange_ms": (C.c_double, [C.c_void_p]),
 }
 
 _bound = False
@@ -113,6 +123,11 @@ class Mandelbrot:
 
     def set_options(self, glitch_tol=-1.0, max_secondary=-1, device=-1, host_threads=-1):
         self.lib.nmv_set_options(self.h, glitch_tol, max_secondary, device, host_threads)
+
+    def set_devices(self, devices, band_rows=0):
+        """Mandelbrot::devices: split every frame of this view over these GPUs (threads + NCCL inside the library)."""
+        arr = (C.c_int * len(devices))(*devices)
+        self._ck(self.lib.nmv_set_devices(self.h, arr, len(devices), int(band_rows)))
 
     def set_floatexp(self, force):
         """0 automatic; 1 floatexp series; 2 also floatexp eps + scaled deltas (even where doubles suffice)."""

@@ -6,6 +6,7 @@
 //
 //   headless_viewer state                      no GPU needed: navigation, copies, precision policy, palette table
 //   headless_viewer render H W N [view file]   needs a GPU: frames through precompute()/computeRow()/at()
+//   headless_viewer beauty H W SC N NGPU view  the beauty render (viewer.cpp:186-253) of a saved view on NGPU GPUs
 #include "mandelbrot.h"   // the include path decides: newman_b200's, not the reference's
 #include "multiwave.h"
 
@@ -171,14 +172,58 @@ static int run_render(int h, int w, int N, const char* view_file) {
   return 0;
 }
 
+// FractalViewer::beautyRender (viewer.cpp:186-253) the way the viewer does it — save a copy, replace `mandel` by a
+// supersampled one, copy N / centre / scaled sz over, precompute(), computeRow() for every row, recolor(), restore —
+// with the one line a multi-GPU box adds: `mandel.devices`. (The reference forgets setPrecision after assigning the
+// centre; a caller that wants the deep centre sets the precision first, as here.)
+static int run_beauty(int h, int w, int sc, int N, int ngpu, const char* view_file) {
+  HeadlessViewer v(h, w);
+  v.mandel.N = N;
+  v.mandel.loadLegacy(view_file);
+  v.pal = v.mw.cache(v.mandel.N);
+  uint64_t raster[2] = {0, 0}, rgb[2] = {0, 0};
+  double secs[2] = {0, 0};
+  for (int pass = 0; pass < 2; pass++) {           // pass 0: one GPU; pass 1: all of them — the frames must be identical
+    Mandelbrot saved = v.mandel;                    // viewer.cpp:193
+    v.mandel = Mandelbrot(h * sc, w * sc);          // :195-196
+    v.mandel.N = saved.N;                           // :197
+    v.mandel.sz.re = saved.sz.re / sc;              // :199-200 (scaled sz first, so that ...
+    v.mandel.sz.im = saved.sz.im / sc;
+    v.mandel.zoom(1.0f);                            // ... setPrecision runs before the centre is assigned)
+    v.mandel.center = saved.center;                 // :198
+    if (pass == 1) {
+      v.mandel.devices.clear();
+      for (int d = 0; d < ngpu; d++) v.mandel.devices.push_back(d);
+      v.mandel.band_rows = sc;
+    }
+    v.sc = sc;
+    v.mandel.precompute();                          // :202
+    for (int r = 0; r < v.mandel.rows(); r++) v.mandel.computeRow(r);   // :209-210
+    for (int r = 0; r < h; r++) v.colorLine(r);     // recolor(), :236-238
+    raster[pass] = v.rasterHash();
+    rgb[pass] = fnv(v.img.data(), v.img.size());
+    secs[pass] = v.mandel.frameInfo().frame_s;
+    printf("beauty pass=%d gpus=%d rows=%d cols=%d M=%d refs=%d executed=%llu frame_s=%.3f device_ms=%.2f raster=%016llx rgb=%016llx\n", pass,
+           pass ? ngpu : 1, v.mandel.rows(), v.mandel.cols(), v.mandel.frameInfo().orbit_len, v.mandel.frameInfo().references,
+           (unsigned long long)v.mandel.frameInfo().executed_iters, secs[pass], v.mandel.frameInfo().device_ms,
+           (unsigned long long)raster[pass], (unsigned long long)rgb[pass]);
+    v.mandel = saved;                               // :250-252
+    v.sc = 1;
+  }
+  printf("beauty identical=%d\n", (int)(raster[0] == raster[1] && rgb[0] == rgb[1]));
+  return raster[0] == raster[1] && rgb[0] == rgb[1] ? 0 : 3;
+}
+
 int main(int argc, char** argv) {
   try {
     if (argc >= 2 && !strcmp(argv[1], "state")) return run_state();
+    if (argc >= 8 && !strcmp(argv[1], "beauty"))
+      return run_beauty(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7]);
     if (argc >= 5 && !strcmp(argv[1], "render")) return run_render(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? argv[5] : nullptr);
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());
     return 2;
   }
-  fprintf(stderr, "usage: headless_viewer state | render H W N [view file]\n");
+  fprintf(stderr, "usage: headless_viewer state | render H W N [view file] | beauty H W SC N NGPU view-file\n");
   return 1;
 }

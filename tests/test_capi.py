@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "newman_b200.h")).read()
-    return sorted(set(re.findall(r"NM_API[^;(]*?\b(nm[vp]?_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"NM_API[^;(]*?\b(nm[vpm]?_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_exported():

@@ -128,6 +128,25 @@ def test_cpp_caller_renders_the_same_frames_as_the_capi(viewer, tmp_path):
     assert (g1["iterations"] < m.frame_N()).any() and (g1["iterations"] > 256).any()   # the deep frame is not trivial
 
 
+@pytest.mark.gpu
+def test_cpp_beauty_render_on_all_gpus(viewer, tmp_path):
+    """FractalViewer::beautyRender (viewer.cpp:186-253) written against the drop-in, with `mandel.devices` = every GPU of
+    the box: the frame must be identical, raster and RGB, to the one-GPU frame. (On a one-GPU box the group has one
+    rank: the collective path still runs.)"""
+    import torch
+    n = max(1, torch.cuda.device_count())
+    cfg = workloads.config("cfg2", scale=40)
+    src = newman_b200.Mandelbrot(600, 800, N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
+    fn = str(tmp_path / "loc.txt")
+    src.save(fn)
+    r = subprocess.run([viewer, "beauty", "54", "96", "3", str(cfg["N"]), str(n), fn], capture_output=True, text=True, cwd=PKG,
+                       timeout=600)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "beauty identical=1" in r.stdout
+    lines = [l for l in r.stdout.splitlines() if l.startswith("beauty pass=")]
+    assert len(lines) == 2 and f"gpus={n}" in lines[1] and "rows=162 cols=288" in lines[1]
+
+
 def key_frame(k, H, W):
     r, c, ch = np.meshgrid(np.arange(H), np.arange(W), np.arange(3), indexing="ij")
     return ((7 * r + 13 * c + 29 * ch + 101 * k + r * c * k) & 255).astype(np.uint8)
