@@ -271,3 +271,31 @@ ORACLE_API double ref_compute_pixels_wide(void* h, const int* pix, int n, int pr
   v->reprec_orbit(orbit_prec);
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+
+// Floatexp form of the tables, for views whose coefficients leave double range (pixel pitch < ~1e-97, where the
+// reference's own per-pixel code dies with SIGFPE but its orbit and series recurrences are fine): mantissa in
+// [0.5, 1) and binary exponent of every component, truncating like descend() — mpf_get_d_2exp. which as ref_dump_table.
+ORACLE_API void ref_dump_table_2exp(void* h, int which, double* mant, int* expo) {
+  RefView* v = (RefView*)h;
+  const std::vector<HPComplex>& t = v->tab(which);
+  for (size_t i = 0; i < t.size(); i++) {
+    long e;
+    mant[2 * i] = mpf_get_d_2exp(&e, t[i].re.get_mpf_t()); expo[2 * i] = (int)e;
+    mant[2 * i + 1] = mpf_get_d_2exp(&e, t[i].im.get_mpf_t()); expo[2 * i + 1] = (int)e;
+  }
+}
+ORACLE_API void ref_dump_eps_2exp(void* h, double* mre, int* ere, double* mim, int* eim) {
+  RefView* v = (RefView*)h;
+  const HPComplex& x0 = v->tab(0)[0];
+  long e;
+  for (int c = 0; c < v->cols(); c++) {
+    HPComplex p = v->pixel(0, c);
+    mpf_class d = p.re - x0.re;
+    mre[c] = mpf_get_d_2exp(&e, d.get_mpf_t()); ere[c] = (int)e;
+  }
+  for (int r = 0; r < v->rows(); r++) {
+    HPComplex p = v->pixel(r, 0);
+    mpf_class d = p.im - x0.im;
+    mim[r] = mpf_get_d_2exp(&e, d.get_mpf_t()); eim[r] = (int)e;
+  }
+}

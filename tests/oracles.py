@@ -165,6 +165,8 @@ class RefView:
             L.ref_dump_orbit_dd.argtypes = [C.c_void_p, C.c_void_p]
             L.ref_orbit_escape.argtypes = [C.c_void_p, C.c_void_p]
             L.ref_dump_eps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            L.ref_dump_table_2exp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            L.ref_dump_eps_2exp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
             L.ref_dump_coords.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             L.ref_in_cardioid.argtypes = [C.c_void_p, C.c_int, C.c_int]
             L.ref_scale.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -255,6 +257,27 @@ class RefView:
             L.ref_dump_table(self.h, which, vp(t))
             tabs.append(t)
         return Tables(x_hi, x_lo, tabs[0], tabs[1], tabs[2], self.N, self.tol, glitch_tol)
+
+    def tables_fe(self, glitch_tol=1e-6, scaled=False):
+        """The tables in floatexp form (mantissa + exponent, mpf_get_d_2exp) straight from the compiled reference's mpf
+        values — for views beyond the depth where its per-pixel code works (bench.py's CPU port leg). scaled: also
+        returns the eps arrays as (mantissa, exponent) pairs. -> Tables[, (eps_re_m, eps_im_m)]"""
+        L = self.lib()
+        t = self.tables(glitch_tol)
+        M = t.M
+        ms, es = [], []
+        for which in (1, 2, 3):
+            m = np.zeros(2 * M); e = np.zeros(2 * M, dtype=np.int32)
+            L.ref_dump_table_2exp(self.h, which, vp(m), vp(e))
+            ms.append(m); es.append(e)
+        tf = Tables(t.x_hi, t.x_lo, ms[0], ms[1], ms[2], self.N, self.tol, glitch_tol, exps=es)
+        if not scaled:
+            return tf
+        mre = np.zeros(self.nc); mim = np.zeros(self.nr)
+        ere = np.zeros(self.nc, dtype=np.int32); eim = np.zeros(self.nr, dtype=np.int32)
+        L.ref_dump_eps_2exp(self.h, vp(mre), vp(ere), vp(mim), vp(eim))
+        tf.eps_exps = [ere, eim]
+        return tf, (mre, mim)
 
     def eps(self):
         er = np.zeros(self.nc); ei = np.zeros(self.nr)
