@@ -391,28 +391,67 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Env:
+    """One rank of the bench: its GPU context, stream, process group and the measured FP64 issue peaks."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import newman_b200
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.devt = torch.device("cuda", self.local)
+        self.dev = newman_b200.Device(self.local)
+        self.stream = torch.cuda.Stream(device=self.devt)
+        torch.cuda.set_stream(self.stream)      # torch ops and NCCL order against the stream our kernels run on
+        self.dev.set_stream(self.stream.cuda_stream)
+        self.peaks = None
+        self.group = None
+
+    def measure_peaks(self):
+        """FP64 issue peaks measured live on this box (MEASURED_PEAKS.json has no FP64 entry), once per process."""
+        if self.peaks is None:
+            d = self.dev
+            self.peaks = (d.fp64_peak(0, 1 << 15)[0], d.fp64_peak(1, 1 << 15)[0], d.fp64_peak(12, 1 << 15)[0])
+            d.sync()
+        return self.peaks
+
+    def render_group(self):
+        from newman_b200 import multigpu
+        if self.group is None:
+            self.group = multigpu.RenderGroup(self.local, self.rank, self.world)
+        return self.group
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allred(self, x, op=None):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.devt)
+        self.dist.all_reduce(t, op=op or self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def measure_frames(env, args, workload, steps, warmup, cpu_baseline, y_mult):
+    """The device-level measurement of one workload on env.world ranks (rows x y_mult, interleaved over the ranks):
+    `value` with tables resident in HBM and device timers, `e2e` with host buffers and wall clock. Returns the JSON
+    line (rank 0; None elsewhere)."""
     import newman_b200
     from newman_b200 import multigpu, pipeline, workloads
+    torch, dist = env.torch, env.dist
+    rank, world, local, devt, dev, stream = env.rank, env.world, env.local, env.devt, env.dev, env.stream
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    devt = torch.device("cuda", local)
-    dev = newman_b200.Device(local)
-    stream = torch.cuda.Stream(device=devt)
-    torch.cuda.set_stream(stream)      # torch ops and NCCL order against the stream our kernels run on
-    dev.set_stream(stream.cuda_stream)
-
-    cfg = workloads.config(args.workload, scale=args.scale, y_mult=args.ymult or world)
+    cfg = workloads.config(workload, scale=args.scale, y_mult=y_mult)
     if args.floatexp:
         cfg["floatexp"] = args.floatexp
     if args.k3_group >= 0:
@@ -514,7 +553,7 @@ def run_ours(args):
             host_pre[0] += time.perf_counter() - t0
             probe_info = {"probe": [pr[0], pr[1]], "orbit_len": pr[2], "probe_exact_checks": pr[3],
                           "probe_search_s": time.perf_counter() - t0}
-            if cfg.get("probe") and (args.ymult or world) == 1:
+            if cfg.get("probe") and y_mult == 1:
                 probe_info["probe_matches_exhaustive"] = tuple(cfg["probe"]) == (pr[0], pr[1])
             pr = (pr[0], pr[1])
         else:
@@ -550,14 +589,11 @@ def run_ours(args):
     # ---- warm-up ------------------------------------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         frame(True)
 
-    # FP64 issue peak measured live on this box (MEASURED_PEAKS.json has no FP64 entry)
-    peak_dfma, _ = dev.fp64_peak(0, 1 << 15)
-    peak_dadd, _ = dev.fp64_peak(1, 1 << 15)
-    peak_dfma3, _ = dev.fp64_peak(12, 1 << 15)   # DFMA reading 3 registers no neighbour shares (operand-port bound)
-    dev.sync()
+    # FP64 issue peaks measured live on this box: DFMA, DADD, DFMA reading 3 registers no neighbour shares
+    peak_dfma, peak_dadd, peak_dfma3 = env.measure_peaks()
 
     # ---- timed: device-resident ---------------------------------------------------------------------
     stats_total.clear()
@@ -565,7 +601,7 @@ def run_ours(args):
     sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         frame(True)
     ev1.record(stream)
     barrier()
@@ -606,7 +642,7 @@ def run_ours(args):
     stats_total.clear()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         frame_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -655,15 +691,12 @@ def run_ours(args):
             k_name, k_inst, k_ms = "k2_series (series scan)", evals / world * K2_INST_PER_EVAL, k2_ms
         achieved = k_inst / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["label"] + (f", rows x{world} (weak scaling)" if world > 1 else ""),
-                       "grid": [nr, nc], "N": N, "tol": cfg["tol"], "glitch_tol": 1e-6,
-                       "parallelism": f"row-interleaved bands x{world}",
-                       "l2": "working set per step (state queues + raster) exceeds L2; tables are meant to be L2/SMEM resident"},
+            "config": config_dict(cfg, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock, barrier+synchronize both sides",
+                    "ms_per_step": 1e3 * e2e_s / steps, "timer": "wall clock, barrier+synchronize both sides",
                     "gather": "single D2H" if world == 1 else
                               ("per-rank pitched D2H into a shared pinned host raster" if shared is not None else
                                "NCCL gather to rank 0 + one D2H")},
@@ -683,12 +716,12 @@ def run_ours(args):
                          "peak_dfma_ginst": peak_dfma / 1e9,
                          "fp64_tflops": executed / world * k3_flops_iter / (k3_ms * 1e-3) / 1e12 if (k3_ms > 0 and not hw) else None,
                          "fp64_tflops_peak_dfma": 2 * peak_dfma / 1e12,
-                         "kernel_ms_per_step": k_ms / args.steps, "k2_ms_per_step": k2_ms / args.steps,
-                         "k3_ms_per_step": k3_ms / args.steps},
-            "executed_iters_per_step": executed / args.steps, "series_evals_per_step": evals / args.steps,
-            "effective_giter_s": effective / (ms / args.steps * 1e-3) / 1e9,
-            "secondary_references": 0 if hw else len(refs), "glitched_per_step": st_dev.get("glitched", 0) / args.steps,
-            "rebased_per_step": st_dev.get("rebased", 0) / args.steps, "fixups_per_step": st_dev.get("fixups", 0) / args.steps,
+                         "kernel_ms_per_step": k_ms / steps, "k2_ms_per_step": k2_ms / steps,
+                         "k3_ms_per_step": k3_ms / steps},
+            "executed_iters_per_step": executed / steps, "series_evals_per_step": evals / steps,
+            "effective_giter_s": effective / (ms / steps * 1e-3) / 1e9,
+            "secondary_references": 0 if hw else len(refs), "glitched_per_step": st_dev.get("glitched", 0) / steps,
+            "rebased_per_step": st_dev.get("rebased", 0) / steps, "fixups_per_step": st_dev.get("fixups", 0) / steps,
             "host_precompute_s": host_pre[0],
         }
         if not hw:
@@ -696,11 +729,12 @@ def run_ours(args):
             line["floatexp_level"] = primary.fe
             if args.k3_group >= 0:
                 line["config"]["k3_group"] = args.k3_group
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and cpu_baseline:
             procs = os.cpu_count() or 1
             probe = (0, 0) if hw else primary.probe
             if not hw and (primary.fe >= 1 or not _have_ref()):
-                r = cpu_port_sample(cfg, view.host_tables(probe[0], probe[1]), primary.fe, max(procs, args.cpu_sample), procs)
+                r = cpu_port_sample(cfg, port_inputs_from_host_tables(cfg, view.host_tables(probe[0], probe[1]), primary.fe),
+                                    max(procs, args.cpu_sample), procs)
             else:
                 r = cpu_reference_sample(cfg, probe, max(procs, args.cpu_sample), procs)
             if r is not None:
@@ -713,46 +747,52 @@ def run_ours(args):
                                "Oracle-P per pixel (the compiled reference cannot render this view: SIGFPE below ~1e-97)") +
                               f", {r['busy']:.1f}s busy on the slowest core; probe search excluded",
                     "frame_s_extrapolated": r["busy"] * (nr * nc) / len(pix),
-                    "parity_on_sample": {"equal_count_frac": eq, "n": int(len(pix))}}
+                    "parity_on_sample": {"equal_count_frac": eq, "n": int(len(pix)),
+                                         **truth_on_sample(cfg, pix, iters.reshape(-1)[pix], r["it"] if r["kind"] == "reference" else None)}}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref not built on this box"}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        if shared is not None:
+            shared.close()
+        return line
+    if shared is not None:
+        shared.close()
+    return None
+
 
 # ---------------------------------------------------------------------------------------------
-def run_video(args):
-    """--workload cfg5: key frames of the zoom video (BASELINE.json configs[4]; video.cpp / viewer.cpp:
-    441-453, 271-285 render one key frame per zoom step). Frames are independent views, so they are
-    sharded over the ranks round-robin with NO collective on the data path ("scaling": "strong": the
-    same set of frames whatever N). A step = every rank renders all of its frames once. The host
-    arbitrary-precision work per frame (GPU-assisted probe search, orbit, series) happens once outside
-    the timed region and is reported."""
-    import torch
-    import torch.distributed as dist
+def measure_video(env, args, steps, warmup, n_frames):
+    """cfg5: key frames of the zoom video (BASELINE.json configs[4]; viewer.cpp:441-453, 271-285 render one key frame
+    per zoom step, recolour it and hand it to VideoZoom::nextFrame, video.cpp:14-34, which makes the 45 in-between
+    frames). Frames are independent views, so they are sharded over the ranks with NO collective on the data path
+    ("scaling": "strong": the same set of frames whatever N) — longest first by an a-priori cost (deeper frames iterate
+    longer), each to the least loaded rank. A step = every rank renders all of its key frames once, resolves each to RGB
+    (K4) and produces the in-between frames towards it (K5, left in HBM: encoding stays with the caller). The host
+    arbitrary-precision work per frame (GPU-assisted probe search, orbit, series) happens once outside the timed region
+    and is reported."""
     import newman_b200
     from newman_b200 import pipeline, workloads
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    devt = torch.device("cuda", local)
-    dev = newman_b200.Device(local)
-    stream = torch.cuda.Stream(device=devt)
-    torch.cuda.set_stream(stream)
-    dev.set_stream(stream.cuda_stream)
+    from newman_b200 import palette as PAL
+    torch, dist = env.torch, env.dist
+    rank, world, local, devt, dev, stream = env.rank, env.world, env.local, env.devt, env.dev, env.stream
 
     all_rows = lambda ts, key: ts.arr[key]   # a rank renders whole frames: no row restriction
     total_frames = workloads.VIDEO_FRAMES
-    n_sel = min(args.frames, total_frames)
+    n_sel = min(n_frames, total_frames)
     sel = sorted(set(int(round(i * (total_frames - 1) / max(n_sel - 1, 1))) for i in range(n_sel)))
-    mine = sel[rank::world]
+    # longest-processing-time-first: cost ~ iterations per sample ~ depth (frame index), plain-double frames are cheap
+    load = [0.0] * world
+    mine = []
+    for k in sorted(sel, reverse=True):
+        r = min(range(world), key=lambda i: load[i])
+        load[r] += 1.0 + 20.0 * k / total_frames
+        if r == rank:
+            mine.append(k)
+    mine.sort()
+    pal_rgb = PAL.MultiWaveGenerator(os.path.join(ROOT, "newman_b200", "default.pal")).cache(workloads.VIDEO_N)
+    pal_d = torch.from_numpy(np.ascontiguousarray(pal_rgb)).to(devt)
+    rgb_prev = [None]
+    tween = [None]
     jobs = []
     host_pre = 0.0
     for k in mine:
@@ -815,6 +855,15 @@ def run_video(args):
                 print("frame", job["k"], "M", job["orbit_len"], "fe", job["primary_h"].fe, "refs", len(job["refs"]),
                       [(round(st["ms_k2"], 2), round(st["ms_k3"], 2), st["series_evals"], st["executed_iters"], st["pixels"])
                        for st in res["stats"]], file=sys.stderr)
+        # recolour (viewer.cpp:271-274) and in-between towards this key frame (video.cpp:14-34), all on the device
+        rgb = torch.empty((nr, nc, 3), dtype=torch.uint8, device=devt)
+        dev.resolve(pal_d, N, sc=1, smooth=True, out=rgb)
+        if rgb_prev[0] is not None and rgb_prev[0].shape == rgb.shape:
+            if tween[0] is None or tween[0].shape[1:3] != (nr, nc):
+                tween[0] = torch.empty((45, nr, nc, 3), dtype=torch.uint8, device=devt)
+            dev.video_inbetween(rgb_prev[0], rgb, nr, nc, rate=45, out=tween[0])
+            tot["tween_frames"] = tot.get("tween_frames", 0) + 45
+        rgb_prev[0] = rgb
         if read:
             dev.read_rows(0, nr, job["out_h"])
 
@@ -825,20 +874,17 @@ def run_video(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         for job in jobs:
             render(job, True, False)
-    peak_dfma, _ = dev.fp64_peak(0, 1 << 15)
-    peak_dadd, _ = dev.fp64_peak(1, 1 << 15)
-    peak_dfma3, _ = dev.fp64_peak(12, 1 << 15)   # DFMA reading 3 registers no neighbour shares (operand-port bound)
-    dev.sync()
+    peak_dfma, peak_dadd, peak_dfma3 = env.measure_peaks()
 
     tot.clear()
     barrier()
     sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         for job in jobs:
             render(job, True, False)
     ev1.record(stream)
@@ -853,7 +899,7 @@ def run_video(args):
     tot.clear()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         for job in jobs:
             render(job, False, True)
     barrier()
@@ -879,21 +925,22 @@ def run_video(args):
                      8 * (j["cfg"]["nr"] + j["cfg"]["nc"]) for j in jobs))
     d2h = allred(sum(j["cfg"]["nr"] * j["cfg"]["nc"] * 8 for j in jobs))
     n_hw = allred(sum(1 for j in jobs if j["hw"]))
+    allred_tw = allred(st_dev.get("tween_frames", 0)) / max(steps, 1)
     if rank == 0:
         # mixed frames: plain-double frames execute 8, perturbation frames 6 FP64 instructions per iteration
         inst = executed / world * K3_INST_PER_ITER
         achieved = inst / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         cfg0 = workloads.video_frame(0, scale=args.scale)
         line = {
-            "metric": METRIC, "value": executed / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "metric": METRIC, "value": executed / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"cfg5: zoom video, {len(sel)} of {total_frames} key frames {cfg0['nc']}x{cfg0['nr']}, depth 1 -> "
-                                   f"1e-{workloads.VIDEO_DEPTH}, N={workloads.VIDEO_N}, frames sharded round-robin over {world} GPU(s)",
+                                   f"1e-{workloads.VIDEO_DEPTH}, N={workloads.VIDEO_N}, frames sharded longest-first over {world} GPU(s); each key frame resolved to RGB (K4) and in-betweened x45 (K5) inside the timed region",
                        "frames": sel, "plain_double_frames": int(n_hw), "parallelism": f"frames x{world}",
                        "l2": "each frame's state queues + raster exceed L2 from ~1e-20 on; tables L2/SMEM resident"},
             "e2e": {"value": executed_e2e / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "timer": "wall clock, barrier+synchronize both sides"},
+                    "ms_per_step": 1e3 * e2e_s / steps, "timer": "wall clock, barrier+synchronize both sides"},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "fp64_pipe", "kernel": "k3_fast/k3_level (FP64 perturbation) + k1_escape on the shallow frames",
                          "achieved": achieved, "peak": peak_dadd / 1e9, "unit": "Ginst/s",
@@ -901,16 +948,167 @@ def run_video(args):
                          "inst_per_iter": K3_INST_PER_ITER,
                          **mix_ceiling(False, False, executed / world, k_ms, peak_dadd, peak_dfma3),
                          "peak_source": "measured live: nm_fp64_peak DADD issue rate", "peak_dfma_ginst": peak_dfma / 1e9,
-                         "kernel_ms_per_step": k_ms / args.steps, "k2_ms_per_step": k2_ms / args.steps},
-            "executed_iters_per_step": executed / args.steps, "frames_per_step": len(sel),
-            "frames_per_s_device": len(sel) / (ms / args.steps * 1e-3), "frames_per_s_e2e": len(sel) / (e2e_s / args.steps),
+                         "kernel_ms_per_step": k_ms / steps, "k2_ms_per_step": k2_ms / steps},
+            "executed_iters_per_step": executed / steps, "frames_per_step": len(sel),
+            "frames_per_s_device": len(sel) / (ms / steps * 1e-3), "frames_per_s_e2e": len(sel) / (e2e_s / steps),
+            "tween_frames_per_step": allred_tw,
             "host_precompute_s": host_max,
             "host_precompute_note": "slowest rank: GPU-assisted probe search + orbit + series + secondary references of its frames, once",
         }
+        return line
+    return None
+
+
+def measure_view(env, args, workload, steps, y_mult=1, band=None):
+    """e2e_view: the frames through the drop-in entry point itself — Mandelbrot::precompute() + every row, i.e. nmv_render
+    on one GPU / nmm_render on a render group — wall clock, host arbitrary-precision work INSIDE the timed region
+    (probe search, orbit, series of every reference), raster returned to host memory. One untimed call first (context
+    and buffer creation, NCCL rendezvous)."""
+    import newman_b200
+    from newman_b200 import workloads
+    cfg = workloads.config(workload, scale=args.scale, y_mult=y_mult)
+    torch = env.torch
+    view = view_for(cfg)
+    view.set_options(device=env.local)
+    out = torch.empty((cfg["nr"], cfg["nc"], 2), dtype=torch.int32).pin_memory() if env.rank == 0 else None
+    band = band or max(cfg["sc"], 1) * (2 if cfg["sc"] < 4 else 1)
+    infos = []
+
+    def once():
+        if env.world == 1:
+            view.render(out)
+            return view.frame_info()
+        return env.render_group().render(view, band, out, 1)
+
+    once()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        infos.append(once())
+    env.barrier()
+    secs = env.allred(time.perf_counter() - t0, env.dist.ReduceOp.MAX if env.world > 1 else None)
+    if env.rank != 0:
+        return None
+    ex = sum(i["executed_iters"] for i in infos)
+    return {"value": ex / secs / 1e9, "unit": UNIT, "ms_per_step": 1e3 * secs / steps, "steps": steps, "warmup": 1,
+            "host_precompute_s_per_step": sum(i["host_precompute_s"] for i in infos) / steps,
+            "device_ms_per_step": sum(i["device_ms"] for i in infos) / steps,
+            "references": infos[-1]["references"], "d2h_bytes_per_step": cfg["nr"] * cfg["nc"] * 8,
+            "entry_point": "nmv_render (Mandelbrot::precompute + computeRow)" if env.world == 1 else
+                           f"nmm_render (render group of {env.world} ranks, bands of {band} rows, bands returned to rank 0 over NCCL)",
+            "timer": "wall clock around the call, barrier + synchronize on both sides; includes the host arbitrary-precision work"}
+
+
+def measure_strong(env, args, steps):
+    """N > 1: ONE frame of the north-star configuration (cfg3: 3840x2160, 4x multisampling => 8640 x 15360 samples, 1e-100,
+    N = 2^20; reference viewer.cpp:186-253) split over the ranks inside libnewman_b200.so — strong scaling. Device time =
+    the slowest rank's K2 + K3 time of the frame; the same frame rendered by rank 0 alone stands beside it, and the two
+    rasters are compared byte for byte."""
+    import hashlib
+    from newman_b200 import workloads
+    torch = env.torch
+    cfg = workloads.config("cfg3", scale=args.scale)
+    band = cfg["sc"]
+    view = view_for(cfg)
+    view.set_options(device=env.local)
+    out = torch.empty((cfg["nr"], cfg["nc"], 2), dtype=torch.int32).pin_memory() if env.rank == 0 else None
+    grp = env.render_group()
+    grp.render(view, band, out, 1)      # untimed: buffers, first-touch
+    ex0 = grp.exchange_ms()
+    env.barrier()
+    infos, walls = [], []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        infos.append(grp.render(view, band, out, 1))
+        env.barrier()
+        walls.append(time.perf_counter() - t0)
+    exch = env.allred((grp.exchange_ms() - ex0) / steps, env.dist.ReduceOp.MAX)
+    peak_dfma, peak_dadd, peak_dfma3 = env.measure_peaks()
+    res = None
+    if env.rank == 0:
+        sha_n = hashlib.sha256(out.numpy().tobytes()).hexdigest()
+        single = view_for(cfg)
+        single.set_options(device=env.local)
+        single.render(out)               # untimed first call
+        t0 = time.perf_counter()
+        single.render(out)
+        wall1 = time.perf_counter() - t0
+        i1 = single.frame_info()
+        sha_1 = hashlib.sha256(out.numpy().tobytes()).hexdigest()
+        dev_ms = statistics.mean(i["device_ms"] for i in infos)
+        ex = infos[-1]["executed_iters"]
+        agg = ex / (dev_ms * 1e-3) / 1e9
+        res = {
+            "workload": cfg["label"], "grid": [cfg["nr"], cfg["nc"]], "N": cfg["N"], "band_rows": band, "n_gpus": env.world,
+            "steps": steps, "warmup": 1, "scaling": "strong",
+            "device_ms_per_frame": dev_ms, "value": agg, "unit": UNIT,
+            "frac": agg * 1e9 * K3_INST_PER_ITER / (env.world * peak_dadd),
+            "frac_note": "executed iterations x 6 FP64 instructions / (slowest rank's device time x N x measured DADD issue peak)",
+            "frame_s": statistics.mean(walls), "host_precompute_s": statistics.mean(i["host_precompute_s"] for i in infos),
+            "exchange_ms_per_frame_slowest_rank": exch, "references": infos[-1]["references"],
+            "executed_iters": ex,
+            "n1": {"device_ms_per_frame": i1["device_ms"], "value": i1["executed_iters"] / (i1["device_ms"] * 1e-3) / 1e9,
+                   "frame_s": wall1, "host_precompute_s": i1["host_precompute_s"], "executed_iters": i1["executed_iters"],
+                   "frac": i1["executed_iters"] * K3_INST_PER_ITER / (i1["device_ms"] * 1e-3) / peak_dadd},
+            "strong_efficiency_device": i1["device_ms"] / (env.world * dev_ms),
+            "raster_sha_matches_n1": sha_n == sha_1, "raster_sha256": sha_n[:16],
+            "limit_note": "frame_s is bound by rank 0's host arbitrary-precision work (probe search + orbit + series of each "
+                          "reference), which does not shard; device time does",
+        }
+    env.barrier()
+    return res
+
+
+def compact(line):
+    """What the `configs` block keeps of a full line."""
+    if line is None:
+        return None
+    r = line.get("roofline", {})
+    d = {"workload": line["config"]["workload"], "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"],
+         "steps": line["steps"], "warmup": line["warmup"], "frac": r.get("frac"), "frac_of_mix_ceiling": r.get("frac_of_mix_ceiling"),
+         "kernel": r.get("kernel"), "e2e": line.get("e2e"), "gpu_launches": line.get("gpu_launches"),
+         "host_precompute_s": line.get("host_precompute_s"), "executed_iters_per_step": line.get("executed_iters_per_step")}
+    for k in ("secondary_references", "glitched_per_step", "floatexp_level", "orbit_len", "frames_per_step", "frames_per_s_device",
+              "frames_per_s_e2e", "tween_frames_per_step", "e2e_view"):
+        if k in line:
+            d[k] = line[k]
+    return d
+
+
+def run_ours(args):
+    env = Env(args)
+    y_mult = args.ymult or env.world
+    main_is_video = args.workload == "cfg5"
+    if main_is_video:
+        line = measure_video(env, args, args.steps, args.warmup, args.frames)
+    else:
+        line = measure_frames(env, args, args.workload, args.steps, args.warmup, not args.no_cpu_baseline, y_mult)
+    if not args.no_extras and args.scale == 1:
+        xs = args.extra_steps
+        if not main_is_video:
+            ev = measure_view(env, args, args.workload, xs, y_mult=y_mult)
+            if line is not None:
+                line["e2e_view"] = ev
+        if env.world > 1:
+            st = measure_strong(env, args, xs)
+            if line is not None:
+                line["strong"] = st
+        elif args.workload == "cfg2":
+            cfgs = {}
+            for w in ("cfg1", "cfg3", "cfg4"):
+                c = compact(measure_frames(env, args, w, xs, 3, False, 1))
+                if w != "cfg4":      # (cfg4's host work is ~10 s per frame: its e2e_view would double the bench time)
+                    c["e2e_view"] = measure_view(env, args, w, 2 if w == "cfg3" else xs)
+                cfgs[w] = c
+            cfgs["cfg5"] = compact(measure_video(env, args, xs, 3, args.frames))
+            line["configs"] = cfgs
+            line["configs_note"] = ("the other BASELINE.json configs measured in this run with 3 warm-up steps and the steps given "
+                                    "per block; cfg5 = %d of its 600 key frames" % args.frames)
+    if env.rank == 0 and line is not None:
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     return 0
 
 
@@ -918,4 +1116,4 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         sys.exit(run_reference(a))
-    sys.exit(run_video(a) if a.workload == "cfg5" else run_ours(a))
+    sys.exit(run_ours(a))
