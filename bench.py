@@ -1097,8 +1097,7 @@ def run_ours(args):
             cfgs = {}
             for w in ("cfg1", "cfg3", "cfg4"):
                 c = compact(measure_frames(env, args, w, xs, 3, False, 1))
-                if w != "cfg4":      # (cfg4's host work is ~10 s per frame: its e2e_view would double the bench time)
-                    c["e2e_view"] = measure_view(env, args, w, 2 if w == "cfg3" else xs)
+                c["e2e_view"] = measure_view(env, args, w, {"cfg3": 2, "cfg4": 1}.get(w, xs))   # (cfg4: ~4 s of host work per call)
                 cfgs[w] = c
             cfgs["cfg5"] = compact(measure_video(env, args, xs, 3, args.frames))
             line["configs"] = cfgs

@@ -262,6 +262,7 @@ typedef struct nmv_frame_info {
   uint64_t executed_iters, series_evals, skipped_pixels, glitched, rebased, fixups, kernel_launches, ambiguous;
   double host_precompute_s, device_ms, frame_s;
   uint64_t probe_iters, probe_exact; /* GPU-assisted findProbe: delta updates on candidates; candidates measured in mpf */
+  int32_t probe_consistent, reserved; /* 0: the exact check contradicts the ranking (ill-conditioned view): see mandelbrot.h */
 } nmv_frame_info;
 
 NM_API nmv_view* nmv_create(int nr, int nc);                      /* Mandelbrot(nr, nc), mandelbrot.cpp:8-17 */

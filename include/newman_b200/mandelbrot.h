@@ -77,6 +77,9 @@ struct FrameInfo {
   double host_precompute_s = 0, device_ms = 0, frame_s = 0;
   // probe search (GPU-assisted): delta updates spent on the candidates, candidates measured in mpf
   unsigned long long probe_iters = 0, probe_exact = 0;
+  // 1: the exact lengths of the short-list agree with the perturbation counts that ranked it (or the list was widened
+  // until they do); 0: they do not — the GPU-assisted probe may differ from the exhaustive search's (probe_search = 0)
+  int probe_consistent = 1;
 };
 }  // namespace newman_b200
 
@@ -108,8 +111,10 @@ public:
                             // the raster is byte-identical to the one-GPU one
   int band_rows;            // rows per band (a multiple of the multisampling factor keeps colour-resolve blocks on one GPU)
   int host_threads;         // probe-search threads (0 = hardware concurrency)
-  int probe_search;         // findProbe: 1 (default) GPU-assisted short-list + exact mpf check of the short-list;
-                            // 0 the reference's exhaustive arbitrary-precision search (mandelbrot.cpp:73-95)
+  int probe_search;         // findProbe: 1 (default) GPU-assisted short-list + exact mpf check of the short-list (with a
+                            // consistency guard: FrameInfo::probe_consistent); 0 the reference's exhaustive
+                            // arbitrary-precision search (mandelbrot.cpp:73-95) — the only mode GUARANTEED to pick the
+                            // reference's probe on every view; the two agree on every view tested down to 1e-97
   int force_floatexp;       // 0 automatic; 1 floatexp series, 2 also floatexp eps + scaled deltas, even where
                             // doubles suffice (verification: same raster wherever both are defined)
 

@@ -157,6 +157,9 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   // than the reference's default (mandelbrot.cpp:9)
   RoundParams rq = rp;
   if (!(rq.tol <= 1e-10)) rq.tol = 1e-10;
+  // glitched candidates are finished by the rebasing pass, not against a secondary reference: the counts only rank the
+  // candidates (the short-list is re-measured exactly below), and a reference build is most of a deep frame's host time
+  rq.max_secondary = 0;
   run_rounds(eng, v, rq, T, cmode, mask, &uniq, scratch);  // cardioid/bulb candidates: (N, 0) without iterating
   info.probe_iters += scratch.executed_iters;  // kept apart from the frame's own counters
   std::vector<nm_escape> got((size_t)n);
@@ -194,6 +197,47 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   }
   std::vector<int> len;
   newman_b200::probe_lengths(v, cand, which, threads, len);
+  // Consistency guard. The short-list is only as good as the perturbation counts that ranked it: if an exact (mpf)
+  // length differs from its candidate's count by more than the list's own width, a candidate outside the list could
+  // be the exhaustive search's winner. Widen the list once — everything within twice the observed disagreement of the
+  // maximum, at most kWide candidates by rank — and report whether that covered it (FrameInfo::probe_consistent = 0:
+  // the criterion is ill-conditioned on this view — e.g. 1e-100, where the exhaustive winner's mpf orbit is 6 % longer
+  // than its perturbation count — and only probe_search = 0 is guaranteed to return the reference's probe).
+  info.probe_consistent = 1;
+  if (first_full < 0) {
+    const int kWide = 256;
+    const int margin = maxc - floor_count;
+    int max_dev = 0;
+    for (size_t k = 0; k < which.size(); k++) {
+      const int d = len[k] > got[which[k]].iterations ? len[k] - got[which[k]].iterations : got[which[k]].iterations - len[k];
+      if (d > max_dev) max_dev = d;
+    }
+    if (max_dev > margin) {
+      const int floor2 = maxc - 2 * max_dev - margin;
+      std::vector<char> have((size_t)n, 0);
+      for (int i : which) have[(size_t)i] = 1;
+      std::vector<int> more;
+      bool covered = true;
+      for (int k = 0; k < n; k++) {
+        const int i = order[k];
+        if (got[i].iterations < floor2) break;
+        if (have[(size_t)i]) continue;
+        if ((int)(which.size() + more.size()) >= kWide) { covered = false; break; }
+        more.push_back(i);
+      }
+      if (!more.empty()) {
+        std::vector<int> len2;
+        newman_b200::probe_lengths(v, cand, more, threads, len2);
+        std::vector<std::pair<int, int> > all;   // (candidate, exact length), then back into scan order
+        for (size_t k = 0; k < which.size(); k++) all.push_back(std::make_pair(which[k], len[k]));
+        for (size_t k = 0; k < more.size(); k++) all.push_back(std::make_pair(more[k], len2[k]));
+        std::sort(all.begin(), all.end());
+        which.clear(); len.clear();
+        for (const std::pair<int, int>& p : all) { which.push_back(p.first); len.push_back(p.second); }
+      }
+      info.probe_consistent = covered ? 1 : 0;
+    }
+  }
   if (n_exact) *n_exact = (int)which.size();
   info.probe_exact = (unsigned long long)which.size();
   size_t best = 0;

@@ -48,6 +48,7 @@ void fill_info(const newman_b200::FrameInfo& f, nmv_frame_info* out) {
   out->glitched = f.glitched; out->rebased = f.rebased; out->fixups = f.fixups; out->kernel_launches = f.kernel_launches;
   out->ambiguous = f.ambiguous;
   out->host_precompute_s = f.host_precompute_s; out->device_ms = f.device_ms; out->frame_s = f.frame_s;
+  out->probe_consistent = f.probe_consistent; out->reserved = 0;
 }
 
 newman_b200::ViewHP hp_of(nmv_view* v) {
@@ -221,14 +222,7 @@ int nmv_view_string(const nmv_view* v, int which, char* buf, int cap) {
 
 int nmv_frame_info_get(const nmv_view* v, nmv_frame_info* out) {
   if (!v || !out) return NM_EINVAL;
-  const newman_b200::FrameInfo& f = v->m.frameInfo();
-  out->hardware = f.hardware ? 1 : (f.floatexp ? 1 + f.floatexp : 0); out->precision_bits = f.precision_bits; out->orbit_len = f.orbit_len;
-  out->probe_row = f.probe_row; out->probe_col = f.probe_col; out->references = f.references;
-  out->executed_iters = f.executed_iters; out->series_evals = f.series_evals; out->skipped_pixels = f.skipped_pixels;
-  out->probe_iters = f.probe_iters; out->probe_exact = f.probe_exact;
-  out->glitched = f.glitched; out->rebased = f.rebased; out->fixups = f.fixups; out->kernel_launches = f.kernel_launches;
-  out->ambiguous = f.ambiguous;
-  out->host_precompute_s = f.host_precompute_s; out->device_ms = f.device_ms; out->frame_s = f.frame_s;
+  fill_info(v->m.frameInfo(), out);
   return NM_OK;
 }
 

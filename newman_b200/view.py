@@ -14,7 +14,8 @@ class FrameInfo(C.Structure):
                 [(n, C.c_uint64) for n in ("executed_iters", "series_evals", "skipped_pixels", "glitched", "rebased",
                                            "fixups", "kernel_launches", "ambiguous")] +
                 [(n, C.c_double) for n in ("host_precompute_s", "device_ms", "frame_s")] +
-                [(n, C.c_uint64) for n in ("probe_iters", "probe_exact")])
+                [(n, C.c_uint64) for n in ("probe_iters", "probe_exact")] +
+                [(n, C.c_int32) for n in ("probe_consistent", "reserved")])
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
