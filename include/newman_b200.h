@@ -160,6 +160,13 @@ NM_API int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst);
  * host raster with pitch N * nc * 8 — every GPU over its own PCIe link, no funnel through one GPU. */
 NM_API int nm_read_rows_pitched(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst_pitch_bytes);
 
+/* The same copy without waiting for it: the rows are snapshot on the device (a device-to-device copy on the ctx stream)
+ * and leave for dst on a second stream, so the ctx can start the next frame — H2D of its tables, K2, K3 — while this
+ * frame's raster is still crossing PCIe. dst should be page-locked. nm_read_wait returns when every copy started this
+ * way has landed. (A second call waits, on the device, for the first one's copy before it reuses the snapshot.) */
+NM_API int nm_read_rows_pitched_async(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst_pitch_bytes);
+NM_API int nm_read_wait(nm_ctx* ctx);
+
 /* Page-lock / release a caller-owned host buffer (e.g. a raster in POSIX shared memory that several ranks
  * write with nm_read_rows_pitched) so that copies to it are DMA transfers. NM_ENOMEM when the OS refuses;
  * the buffer then still works as pageable memory. */

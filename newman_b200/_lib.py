@@ -73,6 +73,8 @@ DEVICE_API = {
     "nm_poke": (C.c_int, [C.c_void_p, C.c_int64, Escape]),
     "nm_read_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nm_read_rows_pitched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "nm_read_rows_pitched_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "nm_read_wait": (C.c_int, [C.c_void_p]),
     "nm_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "nm_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nm_read_pixels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

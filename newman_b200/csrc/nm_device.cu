@@ -72,7 +72,7 @@ struct nm_ctx {
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
   DevBuf Z, ghi, gb, Z2, k3filt, esc_hi, seg_hi, eps_max, xhi, xlo, a, b, c, mask, list, fa_d[2], fa_i[2], hist, offs, cursor, fresh, q[2], rq[2], qctr,
-      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, aexp, bexp, cexp, cre_e, cim_e;
+      rq_pix, rq_iter, pal, rgb, gridtmp, filt, events, snap, aexp, bexp, cexp, cre_e, cim_e;
   int use_fe = 0;   // 0 double series, 1 floatexp series, 2 floatexp series + floatexp eps + scaled K3 states
   int opt_k2_literal = 0;
   int opt_k3_group = 4;  // pixels per lane in k3_fast (0: simple kernel only)
@@ -84,6 +84,8 @@ struct nm_ctx {
 
   nm_stats stats;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;   // nm_read_rows_pitched_async: snapshot taken / copy-out finished
+  bool copy_pending = false;
   unsigned long long* h_ctr = nullptr;  // pinned mirror of the counters
   unsigned long long* h_flag = nullptr; // pinned cancel flag source
   double log_bailout = 0;
@@ -642,6 +644,8 @@ int nm_create(int device, nm_ctx** out) {
   NM_CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
   ctx->stream = ctx->own;
   for (int i = 0; i < 4; i++) NM_CREATE_CUDA(cudaEventCreate(&ctx->ev[i]));
+  NM_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_snap, cudaEventDisableTiming));
+  NM_CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
   NM_CREATE_CUDA(ctx->ctr.ensure(CTR_COUNT * sizeof(unsigned long long)));
   NM_CREATE_CUDA(cudaMemset(ctx->ctr.p, 0, CTR_COUNT * sizeof(unsigned long long)));
   NM_CREATE_CUDA(cudaMallocHost((void**)&ctx->h_ctr, CTR_COUNT * sizeof(unsigned long long)));
@@ -686,10 +690,13 @@ void nm_destroy(nm_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->out, &ctx->cre, &ctx->cim, &ctx->ctr, &ctx->ambig, &ctx->fix, &ctx->fixapply, &ctx->Z, &ctx->ghi, &ctx->Z2, &ctx->k3filt, &ctx->esc_hi, &ctx->seg_hi, &ctx->eps_max,
                     &ctx->gb, &ctx->xhi, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
-                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
+                    &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->snap, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
                     &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout};
   for (DevBuf* b : bufs) b->release();
+  if (ctx->side) cudaStreamSynchronize(ctx->side);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->ev_snap) cudaEventDestroy(ctx->ev_snap);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->own) cudaStreamDestroy(ctx->own);
@@ -958,6 +965,34 @@ int nm_read_rows_pitched(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst
     NM_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch_bytes, ctx->out.as<nm_escape>() + (size_t)r0 * ctx->nc, row_bytes, row_bytes,
                                    (size_t)(r1 - r0), cudaMemcpyDefault, ctx->stream));
   NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_read_rows_pitched_async(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst_pitch_bytes) {
+  if (!ctx) return NM_EINVAL;
+  const size_t row_bytes = (size_t)ctx->nc * sizeof(nm_escape);
+  if (r0 < 0 || r1 > ctx->nr || r0 > r1 || !dst || dst_pitch_bytes < row_bytes)
+    return fail(ctx, NM_EINVAL, "nm_read_rows_pitched_async: bad range or pitch");
+  if (int rc = finish_frame(ctx)) return rc;
+  if (r1 == r0) return NM_OK;
+  const size_t bytes = (size_t)(r1 - r0) * row_bytes;
+  NM_CUDA(ctx, ctx->snap.ensure(bytes));
+  // the snapshot may only be overwritten once the previous copy-out has drained
+  if (ctx->copy_pending) NM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->snap.p, ctx->out.as<nm_escape>() + (size_t)r0 * ctx->nc, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev_snap, ctx->stream));
+  NM_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_snap, 0));
+  NM_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch_bytes, ctx->snap.p, row_bytes, row_bytes, (size_t)(r1 - r0), cudaMemcpyDefault, ctx->side));
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->side));
+  ctx->copy_pending = true;
+  return NM_OK;
+}
+
+int nm_read_wait(nm_ctx* ctx) {
+  if (!ctx) return NM_EINVAL;
+  if (int rc = set_device(ctx)) return rc;
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->side));
+  ctx->copy_pending = false;
   return NM_OK;
 }
 

@@ -127,6 +127,13 @@ class Device:
         """Rows [r0, r1) to host/device address dst_ptr with a row pitch (interleaved bands of a shared raster)."""
         self._ck(self.lib.nm_read_rows_pitched(self.h, r0, r1, C.c_void_p(dst_ptr), pitch_bytes))
 
+    def read_rows_pitched_async(self, r0, r1, dst_ptr, pitch_bytes):
+        """Start the copy-out of rows [r0, r1) (snapshot on the device, copy on a second stream) and return."""
+        self._ck(self.lib.nm_read_rows_pitched_async(self.h, r0, r1, C.c_void_p(dst_ptr), pitch_bytes))
+
+    def read_wait(self):
+        self._ck(self.lib.nm_read_wait(self.h))
+
     def host_register(self, ptr, nbytes):
         """Page-lock a host buffer; False if the OS refuses (the buffer then stays pageable)."""
         return self.lib.nm_host_register(self.h, C.c_void_p(ptr), nbytes) == L.NM_OK

@@ -105,3 +105,29 @@ def test_class_copy_semantics_and_shared_engine():
     ga2 = a.grid()
     assert np.array_equal(ga["iterations"], ga2["iterations"])
     assert gb.shape == (30, 40) and (gb["iterations"] >= 0).all()
+
+
+def test_async_copy_out_overlaps_and_matches(dev):
+    """nm_read_rows_pitched_async / nm_read_wait: the raster leaves from a device-side snapshot on a second stream, so a
+    new frame may be started before the copy has landed; what lands is the frame the call was made for."""
+    import torch
+    z = np.load(oracles.ROOT + "/tests/golden/kat_d30.npz")
+    t = dev.make_tables(z["x_hi"], z["x_lo"], z["a"], z["b"], z["c"], int(z["N"]), float(z["tol"]))
+    nr, nc = len(z["eps_im"]), len(z["eps_re"])
+    want_a = dev.render_deep(t, z["eps_re"], z["eps_im"]).copy()
+    host_a = torch.zeros((nr, nc, 2), dtype=torch.int32).pin_memory()
+    host_b = torch.zeros((nr, 2 * nc, 2), dtype=torch.int32).pin_memory()     # pitched destination: every other column block
+    dev.frame_deep(t, z["eps_re"], z["eps_im"])
+    dev.launch()
+    dev.read_rows_pitched_async(0, nr, host_a.data_ptr(), nc * 8)
+    # a different frame right away (rebasing mode: other records for the glitched samples), read with a pitch
+    dev.frame_deep(t, z["eps_re"], z["eps_im"], mode=L.MODE_REBASE)
+    dev.launch()
+    want_b = dev.read_rows().copy()
+    dev.read_rows_pitched_async(0, nr, host_b.data_ptr(), 2 * nc * 8)
+    dev.read_wait()
+    got_a = host_a.numpy().view(newman_b200.ESCAPE_DTYPE).reshape(nr, nc)
+    got_b = host_b.numpy()[:, :nc].copy().view(newman_b200.ESCAPE_DTYPE).reshape(nr, nc)
+    assert np.array_equal(got_a.view(np.uint8), want_a.view(np.uint8))
+    assert np.array_equal(got_b.view(np.uint8), want_b.view(np.uint8))
+    assert not host_b.numpy()[:, nc:].any()
