@@ -107,4 +107,13 @@ def config(name, scale=1, y_mult=1):
         sz = (_dec(4 * d / nc), _dec(3 * d / (nr * y_mult)))
         return dict(nr=nr * y_mult, nc=nc, N=N, sz=sz, center=CFG4_CENTER, tol=1e-10, sc=sc,
                     label="cfg4: 7680x4320 view at 1e-400, N=4M (floatexp series + scaled floatexp deltas)")
+    if name == "cfg4g":
+        # "glitch-heavy region with secondary reference orbits" (BASELINE.json configs[3]): the same view with the glitch
+        # rule at 1e-3 — the tolerance perturbation renderers commonly run at; the product's default is 1e-6 — and up to
+        # four secondary references before the rebasing pass: tens of thousands of flagged samples per round instead of
+        # a few thousand, every reference built by the host in 1 344-bit arithmetic
+        c = config("cfg4", scale, y_mult)
+        c.update(glitch_tol=1e-3, max_secondary=4,
+                 label="cfg4g: cfg4's view with glitch tolerance 1e-3 and up to 4 secondary references (glitch-heavy)")
+        return c
     raise KeyError(name)
