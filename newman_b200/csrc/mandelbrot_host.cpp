@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <stdexcept>
 #include <string>
@@ -63,6 +64,18 @@ mp_bitcnt_t max_prec(const HPComplex& a, const HPComplex& b) {
   if (b.im.get_prec() > p) p = b.im.get_prec();
   return p;
 }
+
+// NM_DEBUG_HOST=1: where the host time of a frame goes (stderr)
+struct HostTrace {
+  bool on; double t0; const char* what;
+  explicit HostTrace(const char* w) : on(getenv("NM_DEBUG_HOST") != nullptr), t0(now_s()), what(w) {}
+  void lap(const char* stage) {
+    if (!on) return;
+    const double t = now_s();
+    fprintf(stderr, "nm host %-18s %-28s %8.1f ms\n", what, stage, 1e3 * (t - t0));
+    t0 = t;
+  }
+};
 
 struct RoundParams {
   int N, max_secondary, force_floatexp;
@@ -150,8 +163,10 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   std::sort(uniq.begin(), uniq.end());
   uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
 
+  HostTrace tr("findProbe");
   DeepTablesHost T;
   newman_b200::build_tables(v, v.nr / 2, v.nc / 2, T, threads);
+  tr.lap("centre reference");
   newman_b200::FrameInfo scratch;
   // orbit lengths are wanted, not the user's speed/accuracy trade-off: never a looser series tolerance
   // than the reference's default (mandelbrot.cpp:9)
@@ -164,6 +179,7 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   info.probe_iters += scratch.executed_iters;  // kept apart from the frame's own counters
   std::vector<nm_escape> got((size_t)n);
   eng.check(nm_read_pixels(eng.ctx, pix.data(), n, got.data()), "nm_read_pixels");
+  tr.lap("candidates on the GPU");
 
   const int kShort = 16;
   int maxc = 0;
@@ -197,8 +213,8 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   }
   std::vector<int> len;
   newman_b200::probe_lengths(v, cand, which, threads, len);
-  // Consistency guard. The short-list is only as good as the perturbation counts that ranked it: if an exact (mpf)
-  // length differs from its candidate's count by more than the list's own width, a candidate outside the list could
+  // Consistency guard. The short-list is only as good as the perturbation counts that ranked it: if the exact (mpf)
+  // lengths differ from their candidates' counts by more than the list's own width, a candidate outside the list could
   // be the exhaustive search's winner. Widen the list once — everything within twice the observed disagreement of the
   // maximum, at most kWide candidates by rank — and report whether that covered it (FrameInfo::probe_consistent = 0:
   // the criterion is ill-conditioned on this view — e.g. 1e-100, where the exhaustive winner's mpf orbit is 6 % longer
@@ -207,11 +223,13 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   if (first_full < 0) {
     const int kWide = 256;
     const int margin = maxc - floor_count;
-    int max_dev = 0;
-    for (size_t k = 0; k < which.size(); k++) {
-      const int d = len[k] > got[which[k]].iterations ? len[k] - got[which[k]].iterations : got[which[k]].iterations - len[k];
-      if (d > max_dev) max_dev = d;
-    }
+    // (the MEDIAN disagreement: single candidates whose last iterations are chaotic differ by hundreds of iterations on
+    // any deep view — DESIGN.md section 6 — and say nothing about the ranking as a whole)
+    std::vector<int> devs;
+    for (size_t k = 0; k < which.size(); k++)
+      devs.push_back(len[k] > got[which[k]].iterations ? len[k] - got[which[k]].iterations : got[which[k]].iterations - len[k]);
+    std::sort(devs.begin(), devs.end());
+    const int max_dev = devs.empty() ? 0 : devs[devs.size() / 2];
     if (max_dev > margin) {
       const int floor2 = maxc - 2 * max_dev - margin;
       std::vector<char> have((size_t)n, 0);
@@ -238,6 +256,7 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
       info.probe_consistent = covered ? 1 : 0;
     }
   }
+  tr.lap("exact check");
   if (n_exact) *n_exact = (int)which.size();
   info.probe_exact = (unsigned long long)which.size();
   size_t best = 0;
@@ -645,8 +664,10 @@ void Mandelbrot::renderFrame() {
     nm_stats st; nm_frame_stats(ctx, &st); absorb(st);
     info_.references = 0;
   } else {
+    HostTrace tr("renderFrame");
     std::vector<uint8_t> mask;
     int cmode = newman_b200::classify_cardioid(v, host_threads, mask);
+    tr.lap("cardioid classification");
     DeepTablesHost T;
     if (cmode == NM_CARDIOID_ALL) {
       // every sample returns (N, 0) at mandelbrot.cpp:149-153: no probe search, a one-entry orbit
@@ -658,14 +679,18 @@ void Mandelbrot::renderFrame() {
       RoundParams rp0 = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance, host_threads};
       if (probe_search == 0) newman_b200::find_probe(v, host_threads, prow, pcol, plen);
       else find_probe_assisted(eng, v, rp0, host_threads, cmode, mask, prow, pcol, plen, nullptr, info_);
+      tr.lap("findProbe (total)");
       newman_b200::build_tables(v, prow, pcol, T, host_threads);
+      tr.lap("primary reference");
     }
     info_.orbit_len = T.M; info_.probe_row = T.probe_row; info_.probe_col = T.probe_col;
     info_.host_precompute_s = now_s() - t_begin;
     info_.references = 0;
     RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance, host_threads};
     run_rounds(eng, v, rp, T, cmode, mask, nullptr, info_);
+    tr.lap("rounds (GPU + secondary)");
     eng.check(nm_read_rows(ctx, 0, v.nr, out), "nm_read_rows");
+    tr.lap("raster D2H");
   }
 
   std::shared_ptr<Signature> s = std::make_shared<Signature>();

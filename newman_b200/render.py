@@ -48,12 +48,15 @@ def main(argv=None):
     ap.add_argument("--no-smooth", action="store_true", help="S key: smoothing off")
     ap.add_argument("--tolerance", type=float, default=1e-10, help="series error tolerance (E key)")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--devices", default=None, help="comma-separated GPU ordinals: split the frame over these GPUs (Mandelbrot::devices)")
     ap.add_argument("-o", "--output", default="newman.png")
     a = ap.parse_args(argv)
 
     w, h = [int(x) for x in a.size.lower().split("x")]
     nr, nc = h * a.sc, w * a.sc
     m = Mandelbrot(nr, nc, device=a.device)
+    if a.devices:
+        m.set_devices([int(x) for x in a.devices.split(",")], band_rows=a.sc * (2 if a.sc < 4 else 1))
     if a.view:
         m.loadLegacy(a.view)             # rescales sz from the 800x600 window to this grid
         N = m.frame_N()
