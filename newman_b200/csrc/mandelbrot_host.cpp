@@ -243,6 +243,9 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
         if ((int)(which.size() + more.size()) >= kWide) { covered = false; break; }
         more.push_back(i);
       }
+      // a list that cannot be made wide enough is not widened at all (each exact orbit costs as much as a third of a
+      // reference build): the frame keeps the short-list's winner and says so
+      if (!covered) more.clear();
       if (!more.empty()) {
         std::vector<int> len2;
         newman_b200::probe_lengths(v, cand, more, threads, len2);
