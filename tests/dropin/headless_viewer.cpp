@@ -6,7 +6,8 @@
 //
 //   headless_viewer state                      no GPU needed: navigation, copies, precision policy, palette table
 //   headless_viewer render H W N [view file]   needs a GPU: frames through precompute()/computeRow()/at()
-//   headless_viewer beauty H W SC N NGPU view  the beauty render (viewer.cpp:186-253) of a saved view on NGPU GPUs
+//   headless_viewer beauty H W SC N NGPU view [Z]  the beauty render (viewer.cpp:186-253) of a saved view on NGPU GPUs
+//                                                  (Z: zoom in by 10^Z before loading, so that a deep file keeps its digits)
 #include "mandelbrot.h"   // the include path decides: newman_b200's, not the reference's
 #include "multiwave.h"
 
@@ -176,9 +177,12 @@ static int run_render(int h, int w, int N, const char* view_file) {
 // supersampled one, copy N / centre / scaled sz over, precompute(), computeRow() for every row, recolor(), restore —
 // with the one line a multi-GPU box adds: `mandel.devices`. (The reference forgets setPrecision after assigning the
 // centre; a caller that wants the deep centre sets the precision first, as here.)
-static int run_beauty(int h, int w, int sc, int N, int ngpu, const char* view_file) {
+static int run_beauty(int h, int w, int sc, int N, int ngpu, const char* view_file, int prezoom) {
   HeadlessViewer v(h, w);
   v.mandel.N = N;
+  // loadLegacy parses at the CURRENT precision of the fields (mandelbrot.cpp:24-27): a viewer that is shallower than the
+  // file loses the centre's digits. A deep location is loaded by a viewer that is already deep: zoom in first.
+  for (int i = 0; i < prezoom; i++) v.mandel.zoom(10.0f);
   v.mandel.loadLegacy(view_file);
   v.pal = v.mw.cache(v.mandel.N);
   uint64_t raster[2] = {0, 0}, rgb[2] = {0, 0};
@@ -218,7 +222,7 @@ int main(int argc, char** argv) {
   try {
     if (argc >= 2 && !strcmp(argv[1], "state")) return run_state();
     if (argc >= 8 && !strcmp(argv[1], "beauty"))
-      return run_beauty(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7]);
+      return run_beauty(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), argv[7], argc > 8 ? atoi(argv[8]) : 0);
     if (argc >= 5 && !strcmp(argv[1], "render")) return run_render(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc > 5 ? argv[5] : nullptr);
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());

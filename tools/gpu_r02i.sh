@@ -36,4 +36,4 @@ src = newman_b200.Mandelbrot(600, 800, N=c["N"], sz=(_dec(4 * d / 800, 60), _dec
 src.save("gpurun_out/cfg3_view.txt")
 PY
 g++ -std=c++11 -O2 -Iinclude/newman_b200 -Inewman_b200/csrc/compat tests/dropin/headless_viewer.cpp -o /tmp/headless_viewer -Lnewman_b200 -l:libnewman_b200.so -Wl,-rpath,$PWD/newman_b200 -l:libgmp.so.10
-( cd newman_b200 && timeout 600 /tmp/headless_viewer beauty 2160 3840 4 1048576 $N ../gpurun_out/cfg3_view.txt ) > gpurun_out/${T}_beauty_cpp.log 2>&1; cat gpurun_out/${T}_beauty_cpp.log
+( cd newman_b200 && timeout 600 /tmp/headless_viewer beauty 2160 3840 4 1048576 $N ../gpurun_out/cfg3_view.txt 120 ) > gpurun_out/${T}_beauty_cpp.log 2>&1; cat gpurun_out/${T}_beauty_cpp.log
