@@ -347,6 +347,10 @@ typedef struct nmm_rank nmm_rank;
 #define NMM_RETURN_LOCAL 0 /* every rank copies its own bands into the host image IT was given (threads of one process,
                               or a shared page-locked mapping): every GPU over its own PCIe link */
 #define NMM_RETURN_ROOT 1  /* bands travel to rank 0 by ncclSend/ncclRecv; rank 0 writes the host image */
+/* Host-only (no GPU, no NCCL): the global grid rows rank `rank` of `world` owns when an nr-row raster is dealt in blocks of
+ * band_rows rows — what nmm_render uses. rows_out (may be NULL) receives them in the rank's local order; returns their number
+ * or NM_EINVAL (band_rows must divide nr). */
+NM_API int nmm_band_layout(int nr, int band_rows, int rank, int world, int32_t* rows_out);
 NM_API int nmm_unique_id(uint8_t id[NMM_ID_BYTES]);
 NM_API int nmm_create(int device, int rank, int world, const uint8_t id[NMM_ID_BYTES], nmm_rank** out);
 NM_API void nmm_destroy(nmm_rank* rk);

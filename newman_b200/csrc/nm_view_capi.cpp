@@ -300,6 +300,14 @@ int nmv_host_in_cardioid(nmv_view* v, int r, int c) {
 }
 
 // ---- multi-GPU render groups (multi_host.h; render_collective in mandelbrot_host.cpp) ----------------------------
+int nmm_band_layout(int nr, int band_rows, int rank, int world, int32_t* rows_out) {
+  if (nr < 0 || band_rows < 1 || world < 1 || rank < 0 || rank >= world || nr % band_rows) return NM_EINVAL;
+  const int n_blocks = nr / band_rows;
+  const int nb = newman_b200::RankLink::blocks_of(rank, world, n_blocks);
+  if (rows_out)
+    for (int r = 0; r < nb * band_rows; r++) rows_out[r] = ((r / band_rows) * world + rank) * band_rows + r % band_rows;
+  return nb * band_rows;
+}
 int nmm_unique_id(uint8_t id[NMM_ID_BYTES]) {
   try { newman_b200::RankLink::unique_id(id); return NM_OK; }
   catch (const std::exception& e) { g_err = e.what(); return NM_ECUDA; }

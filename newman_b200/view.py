@@ -61,6 +61,7 @@ VIEW_API = {
     "nmv_host_selfcheck": (C.c_int, []),
     "nmv_set_devices": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int]),
     # multi-GPU render groups (include/newman_b200.h "multi-GPU"; newman_b200/multigpu.py: RenderGroup)
+    "nmm_band_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nmm_unique_id": (C.c_int, [C.c_void_p]),
     "nmm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "nmm_destroy": (None, [C.c_void_p]),
