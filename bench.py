@@ -628,8 +628,19 @@ def measure_frames(env, args, workload, steps, warmup, cpu_baseline, y_mult):
 
     overlap = world == 1 or shared is not None   # copy-out of frame k overlaps frame k+1 (nm_read_rows_pitched_async)
 
+    dbg = {"frame": 0.0, "read": 0.0, "drain": 0.0} if os.environ.get("NM_BENCH_DEBUG") else None
+
     def frame_e2e():
+        t_a = time.perf_counter()
         frame(False)
+        t_b = time.perf_counter()
+        if dbg is not None:
+            dbg["frame"] += t_b - t_a
+        _copy_out()
+        if dbg is not None:
+            dbg["read"] += time.perf_counter() - t_b
+
+    def _copy_out():
         if world == 1:
             # D2H straight into pinned host memory, started on a second stream from a device-side snapshot: the next
             # frame's table upload and kernels do not wait for it
@@ -645,9 +656,12 @@ def measure_frames(env, args, workload, steps, warmup, cpu_baseline, y_mult):
             torch.cuda.synchronize()
 
     def drain():
+        t_a = time.perf_counter()
         if overlap:
             dev.read_wait()                                # every started copy has landed in host memory
         torch.cuda.synchronize()
+        if dbg is not None:
+            dbg["drain"] += time.perf_counter() - t_a
 
     frame_e2e()
     drain()
@@ -659,6 +673,9 @@ def measure_frames(env, args, workload, steps, warmup, cpu_baseline, y_mult):
     drain()
     barrier()                                              # rank 0 holds the last assembled raster after this
     e2e_s = time.perf_counter() - t0
+    if dbg is not None:
+        print(f"e2e debug rank {rank}: wall {1e3 * e2e_s / steps:.2f} ms/step; host time in frame() {1e3 * dbg['frame'] / (steps + 1):.2f}, "
+              f"in copy-out call {1e3 * dbg['read'] / (steps + 1):.2f}, final drain {1e3 * dbg['drain'] / 2:.2f}", file=sys.stderr, flush=True)
     st_e2e = dict(stats_total)
 
     # ---- reductions over ranks ------------------------------------------------------------------------
