@@ -87,6 +87,7 @@ struct nm_ctx {
   cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;   // nm_read_rows_pitched_async: snapshot taken / copy-out finished
   bool copy_pending = false;
   unsigned long long* h_ctr = nullptr;  // pinned mirror of the counters
+  uint32_t* h_small = nullptr;          // pinned landing zone of kernel-written read-backs (read_back)
   unsigned long long* h_flag = nullptr; // pinned cancel flag source
   double log_bailout = 0;
   int occ_k1 = 0, occ_k3[2] = {0, 0}, occ_k3s[2] = {0, 0};
@@ -219,19 +220,51 @@ float host_smoothing(double r2) {
   return (float)(1.0 - log2(0.5 * log(r2) / log(bailout)));
 }
 
+// Small device -> host read-backs on a frame's critical path (queue counters after K2 and after every sweep, the frame's
+// counters, the glitch / fix-up / ambiguous lists) are written into page-locked host memory BY A KERNEL, not by a copy
+// engine: the device-to-host engine is shared by all streams of the context and works in order, so an 8-byte read-back
+// queued behind the previous frame's raster (nm_read_rows_pitched_async: 66 MB, 3-6 ms) waited for all of it — measured on
+// 8 x B200: every frame of the overlapped end-to-end loop took 5 ms longer than its kernels (profiles/r02j_*).
+constexpr size_t NM_SMALL_D2H = 256 << 10;
+
+__global__ void k_to_host(const uint32_t* __restrict__ src, volatile uint32_t* dst, unsigned n) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+__global__ void k_three_to_host(const unsigned long long* a, const unsigned long long* b, const unsigned long long* c,
+                                volatile unsigned long long* dst) {
+  if (threadIdx.x == 0) { dst[0] = *a; dst[1] = *b; dst[2] = *c; }
+  __threadfence_system();
+}
+
+// dst <- bytes at device address src, stream-ordered, returns after they have arrived
+int read_back(nm_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return NM_OK;
+  if (bytes <= NM_SMALL_D2H && (bytes & 3) == 0 && ((uintptr_t)src & 3) == 0) {
+    const unsigned n = (unsigned)(bytes / 4);
+    unsigned blocks = (n + 255) / 256;
+    if (blocks > 64) blocks = 64;
+    k_to_host<<<blocks, 256, 0, ctx->stream>>>((const uint32_t*)src, ctx->h_small, n);
+    NM_CUDA(ctx, cudaGetLastError());
+    NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(dst, ctx->h_small, bytes);
+    return NM_OK;
+  }
+  NM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
 int finish_frame(nm_ctx* ctx) {
   if (!ctx->launched) return fail(ctx, NM_ESTATE, "no frame launched");
   if (ctx->finished) return NM_OK;
-  NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->ctr.p, CTR_COUNT * sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, ctx->stream));
-  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (int rc = read_back(ctx, ctx->h_ctr, ctx->ctr.p, CTR_COUNT * sizeof(unsigned long long))) return rc;
   unsigned long long nfix = ctx->h_ctr[CTR_FIXUP];
   if (nfix > ctx->fix_cap) return fail(ctx, NM_ESTATE, "smoothing fix-up list overflow (%llu > %llu)", nfix, ctx->fix_cap);
   if (ctx->h_ctr[CTR_AMBIG] > ctx->ambig_cap) return fail(ctx, NM_ESTATE, "ambiguous list overflow");
   if (nfix) {
     std::vector<FixupRec> recs(nfix);
-    NM_CUDA(ctx, cudaMemcpyAsync(recs.data(), ctx->fix.p, nfix * sizeof(FixupRec), cudaMemcpyDeviceToHost, ctx->stream));
-    NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (int rc = read_back(ctx, recs.data(), ctx->fix.p, nfix * sizeof(FixupRec))) return rc;
     std::vector<int32_t> pix(nfix);
     std::vector<float> val(nfix);
     for (size_t i = 0; i < nfix; i++) { pix[i] = recs[i].pix; val[i] = host_smoothing(recs[i].r2); }
@@ -433,8 +466,7 @@ int launch_deep(nm_ctx* ctx) {
   // Lowest table index any state of the coming sweep starts at: the levels below it have no work and
   // are not launched (an empty launch still costs ~4 us; M/1024 of them per sweep add up on small
   // frames). One 8-byte read-back + sync after K2; later sweeps piggy-back on the sweep-end read.
-  NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr + 2, &ctr[CTR_MINJ], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  NM_CUDA(ctx, cudaStreamSynchronize(st));
+  if (int rc = read_back(ctx, ctx->h_ctr + 2, &ctr[CTR_MINJ], sizeof(unsigned long long))) return rc;
   unsigned long long min_j = ctx->h_ctr[2];
 
   static const bool debug_levels = getenv("NM_DEBUG_LEVELS") != nullptr;
@@ -557,11 +589,12 @@ int launch_deep(nm_ctx* ctx) {
       ctx->stats.kernel_launches++;
     }
     ctx->stats.sweeps++;
-    NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr, fast ? &ccount[par ^ 1] : &rcount[par ^ 1], sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, st));
-    NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr + 1, &ctr[CTR_CANCEL], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    NM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctr + 2, &ctr[CTR_MINJ], sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    // (carried / restart count, cancel flag, lowest start index of the next sweep: one kernel-written read-back)
+    k_three_to_host<<<1, 32, 0, st>>>(fast ? &ccount[par ^ 1] : &rcount[par ^ 1], &ctr[CTR_CANCEL], &ctr[CTR_MINJ],
+                                      (volatile unsigned long long*)ctx->h_small);
+    NM_CUDA(ctx, cudaGetLastError());
     NM_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(ctx->h_ctr, ctx->h_small, 3 * sizeof(unsigned long long));
     min_j = ctx->h_ctr[2];
     if (ctx->h_ctr[0] == 0 || ctx->h_ctr[1] != 0) break;
   }
@@ -650,6 +683,7 @@ int nm_create(int device, nm_ctx** out) {
   NM_CREATE_CUDA(cudaMemset(ctx->ctr.p, 0, CTR_COUNT * sizeof(unsigned long long)));
   NM_CREATE_CUDA(cudaMallocHost((void**)&ctx->h_ctr, CTR_COUNT * sizeof(unsigned long long)));
   NM_CREATE_CUDA(cudaMallocHost((void**)&ctx->h_flag, sizeof(unsigned long long)));
+  NM_CREATE_CUDA(cudaMallocHost((void**)&ctx->h_small, NM_SMALL_D2H));
   *ctx->h_flag = 1ULL;
   ctx->log_bailout = log(1024.0);
   const size_t smem = (size_t)(ctx->CH + 4) * (sizeof(double2) + sizeof(double));
@@ -699,6 +733,7 @@ void nm_destroy(nm_ctx* ctx) {
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
   if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
   if (ctx->own) cudaStreamDestroy(ctx->own);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
@@ -922,7 +957,7 @@ int64_t nm_frame_ambiguous(nm_ctx* ctx, int32_t* pix, int64_t cap) {
   int64_t n = (int64_t)ctx->h_ctr[CTR_AMBIG];
   if (pix && n) {
     int64_t m = n < cap ? n : cap;
-    NM_CUDA(ctx, cudaMemcpy(pix, ctx->ambig.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (int rc = read_back(ctx, pix, ctx->ambig.p, (size_t)m * sizeof(int32_t))) return rc;
   }
   return n;
 }
@@ -932,8 +967,8 @@ int64_t nm_frame_requeue(nm_ctx* ctx, int32_t* pix, int32_t* at_iter, int64_t ca
   if (int rc = finish_frame(ctx)) return rc;
   int64_t n = (int64_t)ctx->h_ctr[CTR_REQUEUE];
   int64_t m = n < cap ? n : cap;
-  if (pix && m) NM_CUDA(ctx, cudaMemcpy(pix, ctx->rq_pix.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (at_iter && m) NM_CUDA(ctx, cudaMemcpy(at_iter, ctx->rq_iter.p, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (pix && m) if (int rc = read_back(ctx, pix, ctx->rq_pix.p, (size_t)m * sizeof(int32_t))) return rc;
+  if (at_iter && m) if (int rc = read_back(ctx, at_iter, ctx->rq_iter.p, (size_t)m * sizeof(int32_t))) return rc;
   return n;
 }
 
