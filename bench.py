@@ -632,7 +632,7 @@ def measure_frames(env, args, workload, steps, warmup, cpu_baseline, y_mult):
 
     def frame_e2e():
         t_a = time.perf_counter()
-        frame(False)
+        frame(bool(os.environ.get("NM_BENCH_E2E_RESIDENT")))   # (debug: resident tables isolate the upload's share)
         t_b = time.perf_counter()
         if dbg is not None:
             dbg["frame"] += t_b - t_a
