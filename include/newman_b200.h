@@ -162,8 +162,10 @@ NM_API int nm_read_rows_pitched(nm_ctx* ctx, int r0, int r1, nm_escape* dst, siz
 
 /* The same copy without waiting for it: the rows are snapshot on the device (a device-to-device copy on the ctx stream)
  * and leave for dst on a second stream, so the ctx can start the next frame — H2D of its tables, K2, K3 — while this
- * frame's raster is still crossing PCIe. dst should be page-locked. nm_read_wait returns when every copy started this
- * way has landed. (A second call waits, on the device, for the first one's copy before it reuses the snapshot.) */
+ * frame's raster is still crossing PCIe. The transfer itself is handed to the copy engine only when the NEXT frame's
+ * kernels are enqueued (nm_launch) or by nm_read_wait: copy engines serve the streams of a context in order, and a raster
+ * started at the frame boundary holds the next frame's uploads back. dst should be page-locked and must stay valid until
+ * nm_read_wait, which returns when every copy started this way has landed. */
 NM_API int nm_read_rows_pitched_async(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size_t dst_pitch_bytes);
 NM_API int nm_read_wait(nm_ctx* ctx);
 

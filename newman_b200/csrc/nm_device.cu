@@ -86,6 +86,8 @@ struct nm_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_snap = nullptr, ev_copy = nullptr;   // nm_read_rows_pitched_async: snapshot taken / copy-out finished
   bool copy_pending = false;
+  // a copy-out whose snapshot is taken but whose device-to-host transfer has not been handed to the copy engine yet
+  struct { nm_escape* dst = nullptr; size_t pitch = 0, row_bytes = 0, rows = 0; bool active = false; } deferred;
   unsigned long long* h_ctr = nullptr;  // pinned mirror of the counters
   uint32_t* h_small = nullptr;          // pinned landing zone of kernel-written read-backs (read_back)
   unsigned long long* h_flag = nullptr; // pinned cancel flag source
@@ -255,6 +257,22 @@ int read_back(nm_ctx* ctx, void* dst, const void* src, size_t bytes) {
   return NM_OK;
 }
 
+// The device-to-host transfer of a deferred copy-out (nm_read_rows_pitched_async). Copies, memsets and uploads of the NEXT
+// frame's set-up share copy engines with it and are served in order: started at the frame boundary, a 66 MB raster held
+// the next frame's first uploads back for milliseconds (8 x B200: 36.3 ms per end-to-end step against 31.1 ms of kernels,
+// profiles/r02j_e2e_debug_n8.txt). So the transfer is handed to the second stream only once the next frame's sweep is
+// enqueued (launch_deep / launch_hw call this), when nothing but long kernels is in flight — or by nm_read_wait.
+int issue_deferred_copy(nm_ctx* ctx) {
+  if (!ctx->deferred.active) return NM_OK;
+  ctx->deferred.active = false;
+  NM_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_snap, 0));
+  NM_CUDA(ctx, cudaMemcpy2DAsync(ctx->deferred.dst, ctx->deferred.pitch, ctx->snap.p, ctx->deferred.row_bytes, ctx->deferred.row_bytes,
+                                 ctx->deferred.rows, cudaMemcpyDefault, ctx->side));
+  NM_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->side));
+  ctx->copy_pending = true;
+  return NM_OK;
+}
+
 int finish_frame(nm_ctx* ctx) {
   if (!ctx->launched) return fail(ctx, NM_ESTATE, "no frame launched");
   if (ctx->finished) return NM_OK;
@@ -323,7 +341,7 @@ int launch_hw(nm_ctx* ctx) {
   ctx->stats.kernel_launches++;
   NM_CUDA(ctx, cudaGetLastError());
   NM_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-  return NM_OK;
+  return issue_deferred_copy(ctx);   // the previous frame's raster leaves while this one's kernel runs
 }
 
 template <int MODE, bool SCALED>
@@ -576,6 +594,7 @@ int launch_deep(nm_ctx* ctx) {
         cudaEventRecord(dbg_ev, st);
       }
     }
+    if (int rc = issue_deferred_copy(ctx)) return rc;   // the previous frame's raster leaves while this sweep runs
     if (fast) {
       // finish what the branch-free kernel exported — escapes, glitches, limits, rebases, false alarms — one thread per
       // state, to the end (k3_finish.cuh); nothing is carried into another sweep
@@ -1010,22 +1029,22 @@ int nm_read_rows_pitched_async(nm_ctx* ctx, int r0, int r1, nm_escape* dst, size
     return fail(ctx, NM_EINVAL, "nm_read_rows_pitched_async: bad range or pitch");
   if (int rc = finish_frame(ctx)) return rc;
   if (r1 == r0) return NM_OK;
+  if (int rc = issue_deferred_copy(ctx)) return rc;   // an earlier request that no launch has picked up
   const size_t bytes = (size_t)(r1 - r0) * row_bytes;
   NM_CUDA(ctx, ctx->snap.ensure(bytes));
   // the snapshot may only be overwritten once the previous copy-out has drained
   if (ctx->copy_pending) NM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
   NM_CUDA(ctx, cudaMemcpyAsync(ctx->snap.p, ctx->out.as<nm_escape>() + (size_t)r0 * ctx->nc, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   NM_CUDA(ctx, cudaEventRecord(ctx->ev_snap, ctx->stream));
-  NM_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_snap, 0));
-  NM_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch_bytes, ctx->snap.p, row_bytes, row_bytes, (size_t)(r1 - r0), cudaMemcpyDefault, ctx->side));
-  NM_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->side));
-  ctx->copy_pending = true;
+  ctx->deferred.dst = dst; ctx->deferred.pitch = dst_pitch_bytes; ctx->deferred.row_bytes = row_bytes;
+  ctx->deferred.rows = (size_t)(r1 - r0); ctx->deferred.active = true;
   return NM_OK;
 }
 
 int nm_read_wait(nm_ctx* ctx) {
   if (!ctx) return NM_EINVAL;
   if (int rc = set_device(ctx)) return rc;
+  if (int rc = issue_deferred_copy(ctx)) return rc;
   NM_CUDA(ctx, cudaStreamSynchronize(ctx->side));
   ctx->copy_pending = false;
   return NM_OK;
