@@ -271,7 +271,8 @@ typedef struct nmv_frame_info {
   uint64_t executed_iters, series_evals, skipped_pixels, glitched, rebased, fixups, kernel_launches, ambiguous;
   double host_precompute_s, device_ms, frame_s;
   uint64_t probe_iters, probe_exact; /* GPU-assisted findProbe: delta updates on candidates; candidates measured in mpf */
-  int32_t probe_consistent, reserved; /* 0: the exact check contradicts the ranking (ill-conditioned view): see mandelbrot.h */
+  int32_t probe_consistent; /* 0: the exact check contradicts the ranking (ill-conditioned view): see mandelbrot.h */
+  int32_t cancelled;        /* 1: the frame was abandoned by nmv_cancel: the raster is not current */
 } nmv_frame_info;
 
 NM_API nmv_view* nmv_create(int nr, int nc);                      /* Mandelbrot(nr, nc), mandelbrot.cpp:8-17 */
@@ -301,6 +302,9 @@ NM_API int nmv_use_hardware(nmv_view* v);                          /* mandelbrot
 NM_API int nmv_precision_bits(const nmv_view* v);                  /* what setPrecision chose, 37-51 */
 NM_API int nmv_precompute(nmv_view* v);                            /* mandelbrot.cpp:261-267 (+ GPU frame) */
 NM_API int nmv_compute_row(nmv_view* v, int r);                    /* mandelbrot.cpp:269-283 */
+/* Abandon the frame nmv_precompute / nmv_render is rendering in ANOTHER thread (viewer.cpp:177, 221-231: the viewer stops
+ * calling computeRow): that call returns early with nmv_frame_info.cancelled = 1. Thread-safe, never blocks. */
+NM_API int nmv_cancel(nmv_view* v);
 NM_API int nmv_render(nmv_view* v, nm_escape* out);                /* precompute + every row, raster copied out */
 NM_API int nmv_read_grid(const nmv_view* v, nm_escape* out);       /* at(r,c) for all r,c: mandelbrot.cpp:318 */
 NM_API int nmv_write_grid(nmv_view* v, const nm_escape* in);

@@ -80,6 +80,7 @@ struct FrameInfo {
   // 1: the exact lengths of the short-list agree with the perturbation counts that ranked it (or the list was widened
   // until they do); 0: they do not — the GPU-assisted probe may differ from the exhaustive search's (probe_search = 0)
   int probe_consistent = 1;
+  bool cancelled = false;           // the frame was abandoned by Mandelbrot::cancel(): the raster is not current
 };
 }  // namespace newman_b200
 
@@ -95,6 +96,7 @@ protected:
   void setPrecision();  // mandelbrot.cpp:37-56
   bool frameCurrent() const;
   void renderFrame();
+  void renderFrameImpl();
 
 public:
   double error_tolerance;
@@ -129,6 +131,10 @@ public:
   bool useHardware();
   void precompute();
   void computeRow(int r);
+  // Not in the reference, whose viewer abandons a frame by no longer calling computeRow (viewer.cpp:177, 221-231): here
+  // precompute() renders the whole frame, so abandoning it is a call of its own, from any other thread (the UI's).
+  // precompute() then returns early with frameInfo().cancelled set; the next precompute() starts afresh.
+  void cancel();
 
   HPComplex pointAt(int r, int c, int sc = 1) const;
   void translate(int dr, int dc, int sc = 1);

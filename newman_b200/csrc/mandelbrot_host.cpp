@@ -16,17 +16,23 @@
 #include "hp_host.h"
 #include "multi_host.h"
 
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <thread>
 
 namespace newman_b200 {
 
+struct Cancelled : public std::runtime_error {   // thrown through a frame that Mandelbrot::cancel() abandoned
+  Cancelled() : std::runtime_error("newman_b200: frame cancelled") {}
+};
+
 class Engine {
 public:
   nm_ctx* ctx = nullptr;
   int device;
   bool owned = true;
+  std::atomic<bool> cancel_requested{false};   // set by cancel() (any thread), cleared when the next frame starts
   explicit Engine(int dev) : device(dev) {
     int rc = nm_create(dev, &ctx);
     if (rc != NM_OK) throw std::runtime_error(std::string("newman_b200: ") + nm_last_error(nullptr));
@@ -36,6 +42,7 @@ public:
   Engine(const Engine&) = delete;
   Engine& operator=(const Engine&) = delete;
   void check(int rc, const char* what) {
+    if (rc == NM_ECANCELLED || cancel_requested.load()) throw Cancelled();
     if (rc != NM_OK) throw std::runtime_error(std::string("newman_b200: ") + what + ": " + nm_last_error(ctx));
   }
 };
@@ -291,7 +298,8 @@ struct FrameHeader {   // rank 0 -> all, once per reference
 size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 }  // namespace
 
-void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, int mode, FrameInfo& info) {
+void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, int mode, FrameInfo& info,
+                       const std::atomic<bool>* cancel) {
   const double t_begin = now_s();
   nm_ctx* ctx = link.ctx;
   info = FrameInfo();
@@ -456,7 +464,11 @@ void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, 
         const uint64_t k = ((uint64_t)rq_iter[i] << 40) | g;
         if (k < key) key = k;
       }
+      // a cancel request (Mandelbrot::cancel, any thread) travels with the same reduction, so every rank leaves the frame
+      // at the same point and nobody is left waiting in a collective
+      if (cancel && cancel->load()) key = 0;
       key = link.allreduce_min(key);
+      if (key == 0) { info.cancelled = true; break; }
       if (key == ~(uint64_t)0) break;
       if (link.rank == 0) {
         const uint64_t g = key & (((uint64_t)1 << 40) - 1);
@@ -469,6 +481,10 @@ void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, 
   }
 
   // ---- bands back to the host raster ---------------------------------------------------------------------------
+  if (info.cancelled) {
+    info.frame_s = now_s() - t_begin;
+    return;
+  }
   if (out || mode == NMM_RETURN_LOCAL) {
     const size_t block_bytes = (size_t)band * v.nc * sizeof(nm_escape);
     void* bd = link.band_buffer((size_t)(nr_loc > 0 ? nr_loc : 1) * v.nc * sizeof(nm_escape));
@@ -500,6 +516,7 @@ class Group {
 public:
   std::vector<int> devices;
   std::vector<std::unique_ptr<RankLink> > links;
+  std::atomic<bool> cancel_requested{false};
   explicit Group(const std::vector<int>& devs) : devices(devs), links(devs.size()) {
     uint8_t id[NMM_ID_BYTES];
     RankLink::unique_id(id);
@@ -514,12 +531,13 @@ public:
     for (const std::string& e : errs) if (!e.empty()) throw std::runtime_error(e);
   }
   void render(Mandelbrot& m, int band, nm_escape* out, FrameInfo& info) {
+    cancel_requested.store(false);
     std::vector<std::string> errs(links.size());
     std::vector<FrameInfo> infos(links.size());
     std::vector<std::thread> th;
     for (size_t r = 0; r < links.size(); r++)
       th.emplace_back([&, r]() {
-        try { render_collective(*links[r], m, band, out, NMM_RETURN_LOCAL, infos[r]); }
+        try { render_collective(*links[r], m, band, out, NMM_RETURN_LOCAL, infos[r], &cancel_requested); }
         catch (const std::exception& e) { errs[r] = e.what(); }
       });
     for (std::thread& t : th) t.join();
@@ -607,7 +625,26 @@ void Mandelbrot::computeRow(int r) {
   if (!frameCurrent()) renderFrame();  // rows of a current frame are already in `grid`
 }
 
+void Mandelbrot::cancel() {
+  // any thread: the frame in flight is abandoned — persistent CTAs poll the flag (nm_cancel), the host loop checks it
+  // between stages — and precompute() returns with frameInfo().cancelled set; the raster is then not current
+  std::shared_ptr<newman_b200::Engine> e = engine_;
+  if (e) { e->cancel_requested.store(true); nm_cancel(e->ctx); }
+  std::shared_ptr<newman_b200::Group> g = group_;
+  if (g) g->cancel_requested.store(true);
+}
+
 void Mandelbrot::renderFrame() {
+  try {
+    renderFrameImpl();
+  } catch (const newman_b200::Cancelled&) {
+    info_.cancelled = true;
+    rendered_.reset();
+  }
+  if (engine_) engine_->cancel_requested.store(false);   // a request only ever concerns the frame in flight
+}
+
+void Mandelbrot::renderFrameImpl() {
   const double t_begin = now_s();
   if (!devices.empty()) {
     // one frame over several GPUs (render_collective above): a thread, a context and an NCCL rank per GPU
@@ -615,6 +652,7 @@ void Mandelbrot::renderFrame() {
     int band = band_rows > 0 ? band_rows : 1;
     while (grid.nr % band) band--;   // any raster renders; bands shrink to the largest divisor of the row count
     group_->render(*this, band, reinterpret_cast<nm_escape*>(grid.values.data()), info_);
+    if (info_.cancelled) { rendered_.reset(); info_.frame_s = now_s() - t_begin; return; }
     std::shared_ptr<Signature> sg = std::make_shared<Signature>();
     sg->N = N; sg->nr = grid.nr; sg->nc = grid.nc; sg->max_secondary = max_secondary;
     sg->tol = error_tolerance; sg->gtol = glitch_tolerance;
@@ -628,6 +666,7 @@ void Mandelbrot::renderFrame() {
   newman_b200::Engine& eng = *engine_;
   nm_ctx* ctx = eng.ctx;
   info_ = newman_b200::FrameInfo();
+  eng.cancel_requested.store(false);
 
   ViewHP v;
   v.center_re = center.re.get_mpf_t(); v.center_im = center.im.get_mpf_t();

@@ -2,6 +2,7 @@
 // bindings drive the same drop-in object the reference's viewer would. No exception crosses.
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <exception>
 #include <memory>
 #include <stdexcept>
@@ -34,7 +35,8 @@ struct nmm_rank {
 };
 
 namespace newman_b200 {
-void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, int mode, FrameInfo& info);   // mandelbrot_host.cpp
+void render_collective(RankLink& link, Mandelbrot& m, int band, nm_escape* out, int mode, FrameInfo& info,
+                       const std::atomic<bool>* cancel);   // mandelbrot_host.cpp
 }
 
 namespace {
@@ -48,7 +50,7 @@ void fill_info(const newman_b200::FrameInfo& f, nmv_frame_info* out) {
   out->glitched = f.glitched; out->rebased = f.rebased; out->fixups = f.fixups; out->kernel_launches = f.kernel_launches;
   out->ambiguous = f.ambiguous;
   out->host_precompute_s = f.host_precompute_s; out->device_ms = f.device_ms; out->frame_s = f.frame_s;
-  out->probe_consistent = f.probe_consistent; out->reserved = 0;
+  out->probe_consistent = f.probe_consistent; out->cancelled = f.cancelled ? 1 : 0;
 }
 
 newman_b200::ViewHP hp_of(nmv_view* v) {
@@ -333,7 +335,7 @@ int nmm_render(nmm_rank* rk, nmv_view* view, int band_rows, nm_escape* out_raste
   if (!rk || !view) return NM_EINVAL;
   try {
     newman_b200::FrameInfo f;
-    newman_b200::render_collective(*rk->link, view->m, band_rows, out_raster, return_mode, f);
+    newman_b200::render_collective(*rk->link, view->m, band_rows, out_raster, return_mode, f, nullptr);
     rk->nr = view->m.rows(); rk->nc = view->m.cols(); rk->N = view->m.N; rk->band = band_rows;
     if (info) fill_info(f, info);
     return NM_OK;
@@ -353,6 +355,12 @@ int nmm_resolve(nmm_rank* rk, const uint8_t* pal_rgb, int n_pal, int sc, int smo
     l.return_band(bd, block_bytes, n_blocks, out_rgb, return_mode);
     return NM_OK;
   } catch (const std::exception& e) { rk->err = e.what(); return NM_ECUDA; }
+}
+
+int nmv_cancel(nmv_view* v) {
+  if (!v) return NM_EINVAL;
+  v->m.cancel();   // no exception: atomics and nm_cancel only
+  return NM_OK;
 }
 
 int nmv_set_devices(nmv_view* v, const int* devices, int n, int band_rows) {

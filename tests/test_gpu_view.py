@@ -250,3 +250,37 @@ def test_random_views_class_equals_oracle_rounds(case):
     assert np.array_equal(bits(got["smoothing"]), bits(exp["smoothing"])), (k, info)
     assert info["references"] == 1 + len(res["refs"])
     assert info["executed_iters"] == sum(s["executed_iters"] for s in res["stats"])
+
+
+def test_cancel_a_frame_from_another_thread():
+    """Mandelbrot::cancel / nmv_cancel (the viewer abandons a frame on user input, viewer.cpp:177, 221-231): precompute()
+    in one thread, cancel() from another; the call returns early with frame_info().cancelled, and the next render of the
+    same object is complete and identical to an undisturbed one."""
+    import threading
+    import time
+    cfg = workloads.config("cfg3", scale=2)     # ~130 ms of device time, ~0.3 s of host work
+    k = dict(nr=cfg["nr"], nc=cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
+    want = newman_b200.Mandelbrot(**k).render()
+    m = newman_b200.Mandelbrot(**k)
+    m.render()                                   # context and buffers exist
+    t_full = m.frame_info()["frame_s"]
+    outcomes = []
+    for delay in (0.02, 0.3 * t_full, 0.6 * t_full, 0.9 * t_full):
+        done = {}
+
+        def work():
+            t0 = time.perf_counter()
+            m.render()
+            done["s"] = time.perf_counter() - t0
+        th = threading.Thread(target=work)
+        th.start()
+        time.sleep(delay)
+        m.cancel()
+        th.join(timeout=60)
+        assert not th.is_alive()
+        outcomes.append((round(delay, 3), bool(m.frame_info()["cancelled"]), round(done["s"], 3)))
+    print("full frame", round(t_full, 3), "s; (delay, cancelled, returned after):", outcomes)
+    assert any(c for _, c, _ in outcomes), "no request arrived while a frame was in flight"
+    got = m.render()                              # the object recovers
+    assert not m.frame_info()["cancelled"]
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
