@@ -175,6 +175,7 @@ int nmv_compute_row(nmv_view* v, int r) {
 int nmv_render(nmv_view* v, nm_escape* out) {
   return guarded(v, [&]() {
     v->m.precompute();
+    if (v->m.frameInfo().cancelled) return NM_ECANCELLED;   // nmv_cancel from another thread: no second attempt
     for (int r = 0; r < v->m.rows(); r++) v->m.computeRow(r);
     if (out) std::memcpy(out, v->m.g().values.data(), v->m.g().values.size() * sizeof(nm_escape));
     return NM_OK;

@@ -1,17 +1,18 @@
 #!/bin/bash
-# r02i: the 8-GPU evidence: group tests, bench.py --gpus 8 (weak cfg2 + strong cfg3 + e2e_view), cfg5 with all 600 key
+# usage: gpurun --gpus 8 --timeout 2400 -- 'bash tools/gpu_round_multi.sh 8 <tag>'
+# The multi-GPU evidence: group tests, bench.py --gpus 8 (weak cfg2 + strong cfg3 + e2e_view), cfg5 with all 600 key
 # frames, and the C++ caller's beauty render of the cfg3 view on all GPUs
-T=r02i; N=${1:-8}; mkdir -p gpurun_out
+N=${1:-8}; T=${2:-r02z}; mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_dropin_cpp.py tests/test_render_cli.py -m gpu -q -s > gpurun_out/${T}_pytest.log 2>&1; tail -3 gpurun_out/${T}_pytest.log
 grep -i "MULTI-RANK\|DIFFERS\|beauty pass\|beauty identical" gpurun_out/${T}_pytest.log | head
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29733"
 ( time timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 5 ) > gpurun_out/${T}_bench_n${N}.log 2> gpurun_out/${T}_bench_n${N}.err; tail -4 gpurun_out/${T}_bench_n${N}.err
 ( time timeout 1500 $TR bench.py --gpus $N --workload cfg5 --frames 600 --steps 1 --warmup 3 ) > gpurun_out/${T}_cfg5_n${N}.log 2> gpurun_out/${T}_cfg5_n${N}.err; tail -4 gpurun_out/${T}_cfg5_n${N}.err
-python - $N <<'PY'
+python - $N $T <<'PY'
 import json, sys
-n = sys.argv[1]
-for f in (f"r02i_bench_n{n}", f"r02i_cfg5_n{n}"):
+n, t = sys.argv[1], sys.argv[2]
+for f in (f"{t}_bench_n{n}", f"{t}_cfg5_n{n}"):
     try:
         d = json.loads([x for x in open(f"gpurun_out/{f}.log") if x.startswith("{")][-1])
         r = d["roofline"]
