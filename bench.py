@@ -45,10 +45,12 @@ K3_INST_PER_ITER = 6
 K3_FLOPS_PER_ITER = 10
 K3_INST_PER_ITER_SIMPLE = 10
 K3_FLOPS_PER_ITER_SIMPLE = 17
-# DRAM bytes per state and full-level launch of the dominant kernel, from the ncu --set full capture
-# profiles/r01p_k3_fast_cfg3_metrics.txt (1.064 GB read + 1.018 GB written for 33 177 600 states): the
-# 32-byte state of every sample in and out once = the algorithmic traffic (64 B), nothing re-read.
-K3_DRAM_B_PER_STATE = (1.063988e9 + 1.018290e9) / 33177600
+# DRAM bytes per state and full-level launch of the dominant kernel, from this round's ncu --set full capture
+# profiles/r02h_k3_fast_cfg3_full_level_metrics.txt (1.063922 GB read + 1.017441 GB written for 33 177 600 states; round 1:
+# 1.063988 + 1.018290): the 32-byte state of every sample in and out once = the algorithmic traffic (64 B), nothing
+# re-read. It comes from a profiler run, so it is a constant of the kernel generation, not of this bench run; the number
+# that moves with the run is roofline.achieved.
+K3_DRAM_B_PER_STATE = (1.063922e9 + 1.017441e9) / 33177600
 K2_INST_PER_EVAL = 19   # 12 DMUL + 6 DADD + ... (k2_series.cuh phase-1 body incl. the compare)
 
 
@@ -743,7 +745,8 @@ def measure_frames(env, args, workload, steps, warmup, cpu_baseline, y_mult):
                          **mix_ceiling(hw, simple, executed / world, k_ms, peak_dadd, peak_dfma3),
                          "traffic": None if hw else K3_DRAM_B_PER_STATE * len(rows) * nc,
                          "traffic_note": None if hw else "bytes per full-level launch of k3_fast for this rank's states, from the "
-                                         "ncu capture profiles/r01p_k3_fast_cfg3_metrics.txt (62.8 B per state; algorithmic 64 B)",
+                                         "ncu capture profiles/r02h_k3_fast_cfg3_full_level_metrics.txt (62.7 B per state; algorithmic 64 B): a constant of the kernel "
+                                         "generation (a profiler run), not a measurement of this run",
                          "peak_source": "measured live: nm_fp64_peak DADD issue rate (MEASURED_PEAKS.json has no FP64 entry)",
                          "peak_dfma_ginst": peak_dfma / 1e9,
                          "fp64_tflops": executed / world * k3_flops_iter / (k3_ms * 1e-3) / 1e12 if (k3_ms > 0 and not hw) else None,

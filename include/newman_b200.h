@@ -99,7 +99,7 @@ typedef struct nm_deep_tables {
   int32_t M;            /* orbit length = X.size() (mandelbrot.cpp:106) */
   int32_t N;            /* iteration limit */
   int32_t has_escape;   /* 1: x_hi holds M+1 entries, entry M = the escaped iterate the reference drops */
-  int32_t reserved;
+  int32_t flags;        /* NM_TABLES_* */
   double tol;           /* error_tolerance (isUnstable, mandelbrot.cpp:138-142) */
   double glitch_tol;    /* glitch rule |X_n+d_n|^2 < glitch_tol*|X_n|^2 (same squared-magnitude form) */
   const double* x_hi;   /* [2*(M+has_escape)] re,im interleaved: truncated doubles of X[i] */
@@ -120,7 +120,12 @@ typedef struct nm_deep_tables {
    * pitch of ~1e-150 need (delta*delta, then delta and eps themselves, leave double range). */
   const int32_t* eps_re_exp; /* [nc] */
   const int32_t* eps_im_exp; /* [nr] */
+  /* NM_MODE_DD only (may be NULL = zero): the low parts of the pixel offsets, trunc((pixel - X[0]) - eps) in mpf */
+  const double* eps_re_lo;   /* [nc] */
+  const double* eps_im_lo;   /* [nr] */
 } nm_deep_tables;
+#define NM_TABLES_ORBIT_TRUNCATED 1 /* K3 iterates against the orbit TRUNCATED to doubles (x_hi as it is) instead of rounded to
+                                       nearest (x_hi + x_lo): the second rendering of the exact mode's sensitivity probe */
 
 #define NM_CARDIOID_NONE 0 /* no pixel of the view is inside cardioid/bulb (mandelbrot.cpp:149) */
 #define NM_CARDIOID_ALL 1  /* every pixel is */
@@ -128,6 +133,8 @@ typedef struct nm_deep_tables {
 
 #define NM_MODE_REQUEUE 0 /* glitched pixels are flagged and listed for a secondary reference */
 #define NM_MODE_REBASE 1  /* final pass: no glitch flagging; rebase onto orbit start when |z|<|d| */
+#define NM_MODE_DD 2      /* listed samples only: phase 3 in double-double arithmetic (csrc/k3_dd.cuh), the refinement pass
+                             of the exact mode; not for scaled frames (floatexp eps) */
 
 /* Starts a deep frame over the whole raster (pix_list == NULL) or over the listed pixel ids
  * (secondary-reference rounds, probe search; ids are r*nc+c; unlisted samples keep their values when
@@ -154,6 +161,17 @@ NM_API int nm_poke(nm_ctx* ctx, int64_t pix, nm_escape v);
  * whose smoothing value sits within the device libm's error of a float32 rounding boundary are
  * re-evaluated with the host libm the reference uses (mandelbrot.cpp:133-136). */
 NM_API int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst);
+
+/* Exact mode (Mandelbrot::exact). The frame renders twice — against the orbit rounded to nearest and
+ * against the truncated one (NM_TABLES_ORBIT_TRUNCATED) — and the samples whose escape COUNT depends on that are the ones FP64
+ * perturbation cannot resolve: they are repeated with NM_MODE_DD.
+ *   nm_raster_keep     remember the current raster on the device
+ *   nm_raster_diff     the ids of the samples whose count differs between the current raster and the remembered one; returns
+ *                      their number (pix may be NULL to query; at most cap ids are copied) or a negative code
+ *   nm_raster_restore  the remembered raster becomes the current one again */
+NM_API int nm_raster_keep(nm_ctx* ctx);
+NM_API int64_t nm_raster_diff(nm_ctx* ctx, int32_t* pix, int64_t cap);
+NM_API int nm_raster_restore(nm_ctx* ctx);
 
 /* Same with a destination row pitch: row r lands at dst + (r - r0) * dst_pitch_bytes. A rank that renders
  * the interleaved rows rank, rank+N, ... of a frame writes its band straight into the shared (pinned)
@@ -273,6 +291,8 @@ typedef struct nmv_frame_info {
   uint64_t probe_iters, probe_exact; /* GPU-assisted findProbe: delta updates on candidates; candidates measured in mpf */
   int32_t probe_consistent; /* 0: the exact check contradicts the ranking (ill-conditioned view): see mandelbrot.h */
   int32_t cancelled;        /* 1: the frame was abandoned by nmv_cancel: the raster is not current */
+  uint64_t refined;         /* exact mode: samples repeated in double-double arithmetic */
+  double refine_ms;         /* exact mode: device time of the probe rendering + the double-double pass */
 } nmv_frame_info;
 
 NM_API nmv_view* nmv_create(int nr, int nc);                      /* Mandelbrot(nr, nc), mandelbrot.cpp:8-17 */
@@ -286,6 +306,10 @@ NM_API int nmv_set_options(nmv_view* v, double glitch_tol, int max_secondary, in
 /* force: 1 evaluate the series in floatexp, 2 also floatexp eps + scaled delta states, even where doubles
  * suffice (both are automatic once the view needs them); 0 automatic */
 NM_API int nmv_set_floatexp(nmv_view* v, int force);
+/* Mandelbrot::exact: 1 = after the frame, find the samples FP64 perturbation cannot resolve (the frame is rendered a second
+ * time against the truncated orbit; counts that differ) and repeat them in double-double arithmetic. ~2.3x the frame time;
+ * on cfg2 every sampled escape count then equals the reference's. Not applied to scaled frames (pitch < 2^-380). */
+NM_API int nmv_set_exact(nmv_view* v, int on);
 /* Mandelbrot::devices / band_rows: n > 1 splits every frame over these GPUs (one host thread, one context and one NCCL
  * rank per GPU inside the view; see "multi-GPU" below); n = 0 returns to the single `device`. band_rows <= 0 keeps 4. */
 NM_API int nmv_set_devices(nmv_view* v, const int* devices, int n, int band_rows);

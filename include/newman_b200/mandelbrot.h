@@ -80,6 +80,8 @@ struct FrameInfo {
   // 1: the exact lengths of the short-list agree with the perturbation counts that ranked it (or the list was widened
   // until they do); 0: they do not — the GPU-assisted probe may differ from the exhaustive search's (probe_search = 0)
   int probe_consistent = 1;
+  unsigned long long refined = 0, refine_iters = 0;   // exact mode: samples repeated in double-double, their iterations
+  double refine_ms = 0;             // exact mode: device time of the probe rendering + the double-double pass
   bool cancelled = false;           // the frame was abandoned by Mandelbrot::cancel(): the raster is not current
 };
 }  // namespace newman_b200
@@ -117,6 +119,10 @@ public:
                             // consistency guard: FrameInfo::probe_consistent); 0 the reference's exhaustive
                             // arbitrary-precision search (mandelbrot.cpp:73-95) — the only mode GUARANTEED to pick the
                             // reference's probe on every view; the two agree on every view tested down to 1e-97
+  int exact;                // 1: exact mode — after the frame, the samples FP64 perturbation cannot resolve (found by rendering
+                            // the frame a second time against the truncated orbit: counts that differ) are repeated in
+                            // double-double arithmetic. ~2.3x the frame time; every sampled count of the 1e-50 bench view then
+                            // equals the reference's. One GPU, frames with plain (not scaled) states.
   int force_floatexp;       // 0 automatic; 1 floatexp series, 2 also floatexp eps + scaled deltas, even where
                             // doubles suffice (verification: same raster wherever both are defined)
 

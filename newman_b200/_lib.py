@@ -17,7 +17,8 @@ ESCAPE_DTYPE = np.dtype([("iterations", "<i4"), ("smoothing", "<f4")])  # grid.h
 
 NM_OK, NM_EINVAL, NM_ENODEV, NM_ECUDA, NM_ENOMEM, NM_ESTATE, NM_ERANGE, NM_ECANCELLED = 0, -1, -2, -3, -4, -5, -6, -7
 CARDIOID_NONE, CARDIOID_ALL, CARDIOID_MASK = 0, 1, 2
-MODE_REQUEUE, MODE_REBASE = 0, 1
+MODE_REQUEUE, MODE_REBASE, MODE_DD = 0, 1, 2
+TABLES_ORBIT_TRUNCATED = 1
 OPT_K2_LITERAL = 1
 OPT_K3_GROUP = 2
 OPT_K3_FINISH_MAX = 3
@@ -32,11 +33,12 @@ class NmError(RuntimeError):
 
 class DeepTables(C.Structure):
     _fields_ = [
-        ("M", C.c_int32), ("N", C.c_int32), ("has_escape", C.c_int32), ("reserved", C.c_int32),
+        ("M", C.c_int32), ("N", C.c_int32), ("has_escape", C.c_int32), ("flags", C.c_int32),
         ("tol", C.c_double), ("glitch_tol", C.c_double),
         ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
         ("a_exp", C.c_void_p), ("b_exp", C.c_void_p), ("c_exp", C.c_void_p),      # floatexp series (or NULL)
         ("eps_re_exp", C.c_void_p), ("eps_im_exp", C.c_void_p),                    # floatexp eps => scaled deltas
+        ("eps_re_lo", C.c_void_p), ("eps_im_lo", C.c_void_p),                      # NM_MODE_DD: low parts of eps (or NULL)
     ]
 
 
@@ -73,6 +75,9 @@ DEVICE_API = {
     "nm_poke": (C.c_int, [C.c_void_p, C.c_int64, Escape]),
     "nm_read_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nm_read_rows_pitched": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "nm_raster_keep": (C.c_int, [C.c_void_p]),
+    "nm_raster_diff": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "nm_raster_restore": (C.c_int, [C.c_void_p]),
     "nm_read_rows_pitched_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "nm_read_wait": (C.c_int, [C.c_void_p]),
     "nm_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -678,22 +678,28 @@ void build_tables(const ViewHP& v, int row, int col, DeepTablesHost& out, int th
     if (!std::isfinite(out.a[i]) || !std::isfinite(out.b[i]) || !std::isfinite(out.c[i])) out.finite = false;
 
   // ---- eps arrays: trunc((pixel - X[0])) per column / per row (mandelbrot.cpp:155-159) ------------
-  out.eps_re.resize(v.nc); out.eps_re_m.resize(v.nc); out.eps_re_e.resize(v.nc);
-  out.eps_im.resize(v.nr); out.eps_im_m.resize(v.nr); out.eps_im_e.resize(v.nr);
+  out.eps_re.resize(v.nc); out.eps_re_m.resize(v.nc); out.eps_re_e.resize(v.nc); out.eps_re_lo.resize(v.nc);
+  out.eps_im.resize(v.nr); out.eps_im_m.resize(v.nr); out.eps_im_e.resize(v.nr); out.eps_im_lo.resize(v.nr);
   {
-    Mp p(P), y(P);
+    Mp p(P), y(P), hi(64), lo(P);
     long ex = 0;
     for (int c = 0; c < v.nc; c++) {
       pixel_re(v, c, tmp.v, p.v);
       mpf_sub(y.v, p.v, x0re.v);
       out.eps_re[c] = mpf_get_d(y.v);
       out.eps_re_m[c] = mpf_get_d_2exp(&ex, y.v); out.eps_re_e[c] = (int32_t)ex;
+      mpf_set_d(hi.v, std::isfinite(out.eps_re[c]) ? out.eps_re[c] : 0.0);
+      mpf_sub(lo.v, y.v, hi.v);
+      out.eps_re_lo[c] = mpf_get_d(lo.v);
     }
     for (int r = 0; r < v.nr; r++) {
       pixel_im(v, r, tmp.v, p.v);
       mpf_sub(y.v, p.v, x0im.v);
       out.eps_im[r] = mpf_get_d(y.v);
       out.eps_im_m[r] = mpf_get_d_2exp(&ex, y.v); out.eps_im_e[r] = (int32_t)ex;
+      mpf_set_d(hi.v, std::isfinite(out.eps_im[r]) ? out.eps_im[r] : 0.0);
+      mpf_sub(lo.v, y.v, hi.v);
+      out.eps_im_lo[r] = mpf_get_d(lo.v);
     }
     mpf_get_d_2exp(&ex, v.sz_re);
     out.pitch_exp = (int)ex;

@@ -35,6 +35,8 @@ struct DeepTablesHost {
   std::vector<double> a_m, b_m, c_m;
   std::vector<int32_t> a_e, b_e, c_e;
   std::vector<double> eps_re, eps_im;
+  // low parts of the pixel offsets, trunc((pixel - X[0]) - eps): the double-double refinement pass (NM_MODE_DD) adds them
+  std::vector<double> eps_re_lo, eps_im_lo;
   // eps as mantissa * 2^exponent (mpf_get_d_2exp, truncating): what scaled frames hand to the device
   std::vector<double> eps_re_m, eps_im_m;
   std::vector<int32_t> eps_re_e, eps_im_e;

@@ -88,6 +88,7 @@ struct RoundParams {
   int N, max_secondary, force_floatexp;
   double tol, gtol;
   int host_threads;   // build_tables: 4 or more (0 = all cores) pipelines orbit and series
+  bool orbit_trunc;   // exact mode's probe rendering: K3 iterates against the truncated orbit (NM_TABLES_ORBIT_TRUNCATED)
 };
 
 // One reference after another until no sample is left glitched: the frame (or the listed samples)
@@ -109,7 +110,8 @@ void run_rounds(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp
     if (T.pitch_exp < -380) fe = 2;
     if (rp.force_floatexp > fe) fe = rp.force_floatexp > 2 ? 2 : rp.force_floatexp;
     nm_deep_tables t;
-    t.M = T.M; t.N = rp.N; t.has_escape = T.has_escape ? 1 : 0; t.reserved = 0;
+    memset(&t, 0, sizeof t);
+    t.M = T.M; t.N = rp.N; t.has_escape = T.has_escape ? 1 : 0; t.flags = rp.orbit_trunc ? NM_TABLES_ORBIT_TRUNCATED : 0;
     t.tol = rp.tol; t.glitch_tol = rp.gtol;
     t.x_hi = T.x_hi.data(); t.x_lo = T.x_lo.data();
     t.a = fe ? T.a_m.data() : T.a.data(); t.b = fe ? T.b_m.data() : T.b.data(); t.c = fe ? T.c_m.data() : T.c.data();
@@ -275,6 +277,55 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   row = cand[which[best]].first;
   col = cand[which[best]].second;
   length = len[best];
+}
+// Exact mode (Mandelbrot::exact). After the frame: (1) keep its raster, (2) render the frame once more against the orbit
+// TRUNCATED to doubles instead of rounded to nearest — same probe, same rounds —, (3) the samples whose escape COUNT differs
+// between the two are the ones whose last iterations amplify FP64's 5e-15 past 1, (4) the first raster
+// comes back and those samples are repeated from K2's hand-over in double-double arithmetic against the primary reference
+// (k3_dd.cuh). On cfg2's 6 144-sample adjudication set the probe flags 72 samples, among them every one of the 26 the FP64
+// frame gets wrong, and the double-double pass reproduces the reference's count on all of them.
+void refine_exact(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp, const DeepTablesHost& T0, int cmode,
+                  const std::vector<uint8_t>& mask, newman_b200::FrameInfo& info) {
+  nm_ctx* ctx = eng.ctx;
+  eng.check(nm_raster_keep(ctx), "nm_raster_keep");
+  newman_b200::FrameInfo probe;
+  {
+    DeepTablesHost Tb = T0;
+    RoundParams rq = rp;
+    rq.orbit_trunc = true;
+    run_rounds(eng, v, rq, Tb, cmode, mask, nullptr, probe);
+  }
+  info.refine_ms += probe.device_ms;
+  info.kernel_launches += probe.kernel_launches;
+  info.host_precompute_s += probe.host_precompute_s;
+  int64_t n = nm_raster_diff(ctx, nullptr, 0);
+  if (n < 0) eng.check((int)n, "nm_raster_diff");
+  std::vector<int32_t> list((size_t)n);
+  if (n > 0) {
+    const int64_t m = nm_raster_diff(ctx, list.data(), n);
+    if (m != n) eng.check(m < 0 ? (int)m : NM_ESTATE, "nm_raster_diff");
+  }
+  eng.check(nm_raster_restore(ctx), "nm_raster_restore");
+  info.refined = (unsigned long long)n;
+  if (n == 0) return;
+  const int fe = T0.finite ? (rp.force_floatexp == 1 ? 1 : 0) : 1;
+  nm_deep_tables t;
+  memset(&t, 0, sizeof t);
+  t.M = T0.M; t.N = rp.N; t.has_escape = T0.has_escape ? 1 : 0;
+  t.tol = rp.tol; t.glitch_tol = rp.gtol;
+  t.x_hi = T0.x_hi.data(); t.x_lo = T0.x_lo.data();
+  t.a = fe ? T0.a_m.data() : T0.a.data(); t.b = fe ? T0.b_m.data() : T0.b.data(); t.c = fe ? T0.c_m.data() : T0.c.data();
+  t.a_exp = fe ? T0.a_e.data() : nullptr; t.b_exp = fe ? T0.b_e.data() : nullptr; t.c_exp = fe ? T0.c_e.data() : nullptr;
+  t.eps_re_lo = T0.eps_re_lo.data(); t.eps_im_lo = T0.eps_im_lo.data();
+  eng.check(nm_frame_deep(ctx, &t, T0.eps_re.data(), v.nc, T0.eps_im.data(), v.nr, NM_CARDIOID_NONE, nullptr, list.data(), n,
+                          NM_MODE_DD),
+            "nm_frame_deep (double-double)");
+  eng.check(nm_launch(ctx), "nm_launch");
+  nm_stats st; eng.check(nm_frame_stats(ctx, &st), "nm_frame_stats");
+  info.refine_ms += st.ms_k2 + st.ms_k3;
+  info.refine_iters += st.executed_iters;
+  info.kernel_launches += st.kernel_launches;
+  info.fixups += st.fixups;
 }
 }  // namespace
 
@@ -551,7 +602,7 @@ Mandelbrot::Mandelbrot() : Mandelbrot(1, 1) {}
 
 Mandelbrot::Mandelbrot(int nr, int nc)
     : grid(nr, nc), error_tolerance(1e-10), N(256), glitch_tolerance(1e-6), max_secondary(1), device(0), band_rows(4), host_threads(0),
-      probe_search(1), force_floatexp(0) {
+      probe_search(1), exact(0), force_floatexp(0) {
   // default full view (mandelbrot.cpp:13-14)
   center.re = -0.5;
   center.im = 0.0;
@@ -729,8 +780,15 @@ void Mandelbrot::renderFrameImpl() {
     info_.host_precompute_s = now_s() - t_begin;
     info_.references = 0;
     RoundParams rp = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance, host_threads};
+    DeepTablesHost T0;
+    const bool refine = exact != 0 && cmode != NM_CARDIOID_ALL;
+    if (refine) T0 = T;   // run_rounds overwrites T with the secondary references
     run_rounds(eng, v, rp, T, cmode, mask, nullptr, info_);
     tr.lap("rounds (GPU + secondary)");
+    if (refine && info_.floatexp != 2) {
+      refine_exact(eng, v, rp, T0, cmode, mask, info_);
+      tr.lap("exact mode (probe + dd)");
+    }
     eng.check(nm_read_rows(ctx, 0, v.nr, out), "nm_read_rows");
     tr.lap("raster D2H");
   }

@@ -26,6 +26,7 @@
 #include "k3_perturb.cuh"
 #include "k3_fast.cuh"
 #include "k3_finish.cuh"
+#include "k3_dd.cuh"
 #include "k4_resolve.cuh"
 #include "k5_video.cuh"
 #include "k6_palette.cuh"
@@ -68,6 +69,9 @@ struct nm_ctx {
   bool launched = false, finished = false;
 
   DevBuf out, cre, cim, ctr, ambig, fix, fixapply, palpar, paldev, vprev, vnext, vout;
+  DevBuf kept, difflist, cre_lo, cim_lo;   // exact mode: the remembered raster (nm_raster_keep); low parts of the pixel offsets (NM_MODE_DD)
+  long long kept_pixels = 0;
+  bool have_eps_lo = false;
   int paldev_n = 0;  // entries of the device-generated palette in paldev (0: none)
   unsigned long long ambig_cap = 0, fix_cap = 0;
   // deep
@@ -481,6 +485,26 @@ int launch_deep(nm_ctx* ctx) {
   const unsigned blocks = (unsigned)(ctx->sm_count * occ);
   NM_CUDA(ctx, cudaMemsetAsync(ccount, 0, 2 * sizeof(unsigned long long), st));
 
+  if (ctx->mode == NM_MODE_DD) {   // exact mode: the listed samples once more, phase 3 in double-double (k3_dd.cuh)
+    DDParams q;
+    q.Xhi = ctx->xhi.as<double2>(); q.Xlo = ctx->xlo.as<double2>();
+    q.M = ctx->M; q.Jmax = ctx->Jmax; q.N = ctx->N; q.nc = ctx->nc;
+    q.eps_re = ctx->cre.as<double>(); q.eps_im = ctx->cim.as<double>();
+    q.eps_re_lo = ctx->have_eps_lo ? ctx->cre_lo.as<double>() : nullptr;
+    q.eps_im_lo = ctx->have_eps_lo ? ctx->cim_lo.as<double>() : nullptr;
+    q.out = ctx->out.as<nm_escape>(); q.ctr = ctr;
+    q.fix = ctx->fix.as<FixupRec>(); q.fix_cap = ctx->fix_cap; q.log_bailout = ctx->log_bailout;
+    long long bd = (ctx->W + K3_DD_THREADS - 1) / K3_DD_THREADS;
+    if (bd > (long long)ctx->sm_count * 16) bd = (long long)ctx->sm_count * 16;
+    if (bd < 1) bd = 1;
+    k3_dd<<<(unsigned)bd, K3_DD_THREADS, 0, st>>>(q, fresh_set(ctx, 0), ctx->W);
+    NM_CUDA(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    ctx->stats.sweeps++;
+    NM_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    return NM_OK;
+  }
+
   // Lowest table index any state of the coming sweep starts at: the levels below it have no work and
   // are not launched (an empty launch still costs ~4 us; M/1024 of them per sweep add up on small
   // frames). One 8-byte read-back + sync after K2; later sweeps piggy-back on the sweep-end read.
@@ -744,7 +768,7 @@ void nm_destroy(nm_ctx* ctx) {
                     &ctx->gb, &ctx->xhi, &ctx->xlo, &ctx->a, &ctx->b, &ctx->c, &ctx->mask, &ctx->list, &ctx->fa_d[0], &ctx->fa_d[1], &ctx->fa_i[0], &ctx->fa_i[1],
                     &ctx->hist, &ctx->offs, &ctx->cursor, &ctx->fresh, &ctx->q[0], &ctx->q[1], &ctx->rq[0], &ctx->rq[1],
                     &ctx->qctr, &ctx->rq_pix, &ctx->rq_iter, &ctx->pal, &ctx->rgb, &ctx->gridtmp, &ctx->filt, &ctx->events, &ctx->snap, &ctx->aexp, &ctx->bexp, &ctx->cexp, &ctx->cre_e, &ctx->cim_e,
-                    &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout};
+                    &ctx->palpar, &ctx->paldev, &ctx->vprev, &ctx->vnext, &ctx->vout, &ctx->kept, &ctx->difflist, &ctx->cre_lo, &ctx->cim_lo};
   for (DevBuf* b : bufs) b->release();
   if (ctx->side) cudaStreamSynchronize(ctx->side);
   for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -833,7 +857,9 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   if (!t->has_escape && t->M != t->N && cardioid_mode != NM_CARDIOID_ALL)
     return fail(ctx, NM_EINVAL, "nm_frame_deep: orbit shorter than N needs its escaped iterate (has_escape)");
   if (cardioid_mode == NM_CARDIOID_MASK && !cardioid_mask) return fail(ctx, NM_EINVAL, "cardioid mask missing");
-  if (mode != NM_MODE_REQUEUE && mode != NM_MODE_REBASE) return fail(ctx, NM_EINVAL, "bad mode");
+  if (mode != NM_MODE_REQUEUE && mode != NM_MODE_REBASE && mode != NM_MODE_DD) return fail(ctx, NM_EINVAL, "bad mode");
+  if (mode == NM_MODE_DD && (!pix_list || t->eps_re_exp || t->eps_im_exp))
+    return fail(ctx, NM_EINVAL, "NM_MODE_DD refines listed samples of frames with plain (not scaled) delta states");
   if (int rc = set_device(ctx)) return rc;
   // A pixel-list frame writes only the listed samples. On top of a deep frame of the same size the
   // others keep their values (secondary-reference rounds); otherwise (probe search: the candidate
@@ -921,6 +947,13 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
     NM_CUDA(ctx, cudaMemcpyAsync(ctx->cre_e.p, t->eps_re_exp, (size_t)nc * sizeof(int32_t), cudaMemcpyDefault, s));
     NM_CUDA(ctx, cudaMemcpyAsync(ctx->cim_e.p, t->eps_im_exp, (size_t)nr * sizeof(int32_t), cudaMemcpyDefault, s));
   }
+  ctx->have_eps_lo = mode == NM_MODE_DD && t->eps_re_lo && t->eps_im_lo;
+  if (ctx->have_eps_lo) {
+    NM_CUDA(ctx, ctx->cre_lo.ensure((size_t)nc * sizeof(double)));
+    NM_CUDA(ctx, ctx->cim_lo.ensure((size_t)nr * sizeof(double)));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->cre_lo.p, t->eps_re_lo, (size_t)nc * sizeof(double), cudaMemcpyDefault, s));
+    NM_CUDA(ctx, cudaMemcpyAsync(ctx->cim_lo.p, t->eps_im_lo, (size_t)nr * sizeof(double), cudaMemcpyDefault, s));
+  }
   if (cardioid_mode == NM_CARDIOID_MASK) {
     NM_CUDA(ctx, ctx->mask.ensure((size_t)ctx->pixels));
     NM_CUDA(ctx, cudaMemcpyAsync(ctx->mask.p, cardioid_mask, (size_t)ctx->pixels, cudaMemcpyDefault, s));
@@ -931,9 +964,11 @@ int nm_frame_deep(nm_ctx* ctx, const nm_deep_tables* t, const double* eps_re, in
   }
   {
     // K3 iterates against the orbit rounded to nearest (k_round_orbit); K2's phase 2 keeps the truncated hi/lo pair
-    k_round_orbit<<<(M + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>() + 1, ctx->xhi.as<double2>(), ctx->xlo.as<double2>(), M);
-    NM_CUDA(ctx, cudaGetLastError());
-    ctx->stats.kernel_launches++;
+    if (!(t->flags & NM_TABLES_ORBIT_TRUNCATED)) {   // (the exact mode's probe rendering keeps the truncated orbit)
+      k_round_orbit<<<(M + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>() + 1, ctx->xhi.as<double2>(), ctx->xlo.as<double2>(), M);
+      NM_CUDA(ctx, cudaGetLastError());
+      ctx->stats.kernel_launches++;
+    }
     int pad_n = J1 + 8;
     k_glitch_bounds<<<(pad_n + 255) / 256, 256, 0, s>>>(ctx->Z.as<double2>(), ctx->gb.as<double>(), ctx->ghi.as<int32_t>(),
                                                         ctx->Z2.as<double2>(), ctx->k3filt.as<K3Filt>(), ctx->esc_hi.as<int32_t>(), J1,
@@ -1005,6 +1040,44 @@ int nm_read_rows(nm_ctx* ctx, int r0, int r1, nm_escape* dst) {
   if (int rc = finish_frame(ctx)) return rc;
   NM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->out.as<nm_escape>() + (size_t)r0 * ctx->nc,
                                (size_t)(r1 - r0) * ctx->nc * sizeof(nm_escape), cudaMemcpyDefault, ctx->stream));
+  NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NM_OK;
+}
+
+int nm_raster_keep(nm_ctx* ctx) {
+  if (!ctx) return NM_EINVAL;
+  if (int rc = finish_frame(ctx)) return rc;
+  NM_CUDA(ctx, ctx->kept.ensure((size_t)ctx->pixels * sizeof(nm_escape)));
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->kept.p, ctx->out.p, (size_t)ctx->pixels * sizeof(nm_escape), cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->kept_pixels = ctx->pixels;
+  return NM_OK;
+}
+
+int64_t nm_raster_diff(nm_ctx* ctx, int32_t* pix, int64_t cap) {
+  if (!ctx) return NM_EINVAL;
+  if (int rc = finish_frame(ctx)) return rc;
+  if (ctx->kept_pixels != ctx->pixels || ctx->pixels == 0) return fail(ctx, NM_ESTATE, "nm_raster_diff: no raster of this size was kept");
+  unsigned long long* ctr = ctx->ctr.as<unsigned long long>();
+  NM_CUDA(ctx, ctx->difflist.ensure((size_t)ctx->pixels * sizeof(int32_t)));
+  NM_CUDA(ctx, cudaMemsetAsync(&ctr[CTR_Q_CUR], 0, sizeof(unsigned long long), ctx->stream));
+  long long blocks = (ctx->pixels + 255) / 256;
+  if (blocks > (long long)ctx->sm_count * 16) blocks = (long long)ctx->sm_count * 16;
+  k_raster_diff<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->kept.as<nm_escape>(), ctx->out.as<nm_escape>(), ctx->pixels,
+                                                           ctx->difflist.as<int32_t>(), &ctr[CTR_Q_CUR]);
+  NM_CUDA(ctx, cudaGetLastError());
+  unsigned long long n = 0;
+  if (int rc = read_back(ctx, &n, &ctr[CTR_Q_CUR], sizeof n)) return rc;
+  if (pix && n) {
+    const unsigned long long m = n < (unsigned long long)cap ? n : (unsigned long long)cap;
+    if (int rc = read_back(ctx, pix, ctx->difflist.p, (size_t)m * sizeof(int32_t))) return rc;
+  }
+  return (int64_t)n;
+}
+
+int nm_raster_restore(nm_ctx* ctx) {
+  if (!ctx) return NM_EINVAL;
+  if (ctx->kept_pixels != ctx->pixels || ctx->pixels == 0) return fail(ctx, NM_ESTATE, "nm_raster_restore: no raster of this size was kept");
+  NM_CUDA(ctx, cudaMemcpyAsync(ctx->out.p, ctx->kept.p, (size_t)ctx->pixels * sizeof(nm_escape), cudaMemcpyDeviceToDevice, ctx->stream));
   NM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NM_OK;
 }

@@ -51,6 +51,7 @@ void fill_info(const newman_b200::FrameInfo& f, nmv_frame_info* out) {
   out->ambiguous = f.ambiguous;
   out->host_precompute_s = f.host_precompute_s; out->device_ms = f.device_ms; out->frame_s = f.frame_s;
   out->probe_consistent = f.probe_consistent; out->cancelled = f.cancelled ? 1 : 0;
+  out->refined = f.refined; out->refine_ms = f.refine_ms;
 }
 
 newman_b200::ViewHP hp_of(nmv_view* v) {
@@ -356,6 +357,12 @@ int nmm_resolve(nmm_rank* rk, const uint8_t* pal_rgb, int n_pal, int sc, int smo
     l.return_band(bd, block_bytes, n_blocks, out_rgb, return_mode);
     return NM_OK;
   } catch (const std::exception& e) { rk->err = e.what(); return NM_ECUDA; }
+}
+
+int nmv_set_exact(nmv_view* v, int on) {
+  if (!v) return NM_EINVAL;
+  v->m.exact = on ? 1 : 0;
+  return NM_OK;
 }
 
 int nmv_cancel(nmv_view* v) {

@@ -65,7 +65,8 @@ class Device:
         self._ck(self.lib.nm_frame_hw(self.h, L.ptr(c_re), len(c_re), L.ptr(c_im), len(c_im), N))
 
     @staticmethod
-    def make_tables(x_hi, x_lo, a, b, c, N, tol, glitch_tol=1e-6, has_escape=None, exps=None, eps_exps=None):
+    def make_tables(x_hi, x_lo, a, b, c, N, tol, glitch_tol=1e-6, has_escape=None, exps=None, eps_exps=None, eps_lo=None,
+                    orbit_truncated=False):
         """exps = (a_exp, b_exp, c_exp) int32: floatexp series (a/b/c are then mantissas);
         eps_exps = (eps_re_exp, eps_im_exp) int32: floatexp eps => scaled delta states (the eps arrays
         given to frame_deep/render_deep are then mantissas)."""
@@ -76,11 +77,13 @@ class Device:
         pv = lambda x: None if x is None else L.ptr(x).value
         ex = exps or (None, None, None)
         ee = eps_exps or (None, None)
-        t = L.DeepTables(M=M, N=N, has_escape=has_escape, reserved=0, tol=tol, glitch_tol=glitch_tol,
+        el = [None if eps_lo is None else np.ascontiguousarray(x, dtype=np.float64) for x in (eps_lo or (None, None))]
+        t = L.DeepTables(M=M, N=N, has_escape=has_escape, flags=L.TABLES_ORBIT_TRUNCATED if orbit_truncated else 0, tol=tol,
+                         glitch_tol=glitch_tol, eps_re_lo=pv(el[0]), eps_im_lo=pv(el[1]),
                          x_hi=L.ptr(x_hi).value, x_lo=L.ptr(x_lo).value, a=L.ptr(a).value, b=L.ptr(b).value,
                          c=L.ptr(c).value, a_exp=pv(ex[0]), b_exp=pv(ex[1]), c_exp=pv(ex[2]),
                          eps_re_exp=pv(ee[0]), eps_im_exp=pv(ee[1]))
-        t._keep = (x_hi, x_lo, a, b, c, ex, ee)
+        t._keep = (x_hi, x_lo, a, b, c, ex, ee, el)
         return t
 
     def frame_deep(self, tables, eps_re, eps_im, cardioid_mode=L.CARDIOID_NONE, mask=None, pix_list=None,

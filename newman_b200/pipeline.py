@@ -56,7 +56,7 @@ class TableSet:
         """nm_deep_tables over these arrays; eps_im_e: the row-restricted exponent array (fe == 2)."""
         a = self.arr
         pv = lambda k: L.ptr(a[k]).value if k in a else None
-        t = L.DeepTables(M=self.M, N=self.N, has_escape=self.has_escape, reserved=0, tol=self.tol,
+        t = L.DeepTables(M=self.M, N=self.N, has_escape=self.has_escape, flags=0, tol=self.tol,
                          glitch_tol=self.glitch_tol, x_hi=pv("x_hi"), x_lo=pv("x_lo"), a=pv("a"), b=pv("b"), c=pv("c"),
                          a_exp=pv("a_e"), b_exp=pv("b_e"), c_exp=pv("c_e"), eps_re_exp=pv("eps_re_e"),
                          eps_im_exp=None if self.fe != 2 else L.ptr(a["eps_im_e"] if eps_im_e is None else eps_im_e).value)

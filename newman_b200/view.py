@@ -15,7 +15,8 @@ class FrameInfo(C.Structure):
                                            "fixups", "kernel_launches", "ambiguous")] +
                 [(n, C.c_double) for n in ("host_precompute_s", "device_ms", "frame_s")] +
                 [(n, C.c_uint64) for n in ("probe_iters", "probe_exact")] +
-                [(n, C.c_int32) for n in ("probe_consistent", "cancelled")])
+                [(n, C.c_int32) for n in ("probe_consistent", "cancelled")] +
+                [("refined", C.c_uint64), ("refine_ms", C.c_double)])
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -39,6 +40,7 @@ VIEW_API = {
     "nmv_precompute": (C.c_int, [C.c_void_p]),
     "nmv_compute_row": (C.c_int, [C.c_void_p, C.c_int]),
     "nmv_cancel": (C.c_int, [C.c_void_p]),
+    "nmv_set_exact": (C.c_int, [C.c_void_p, C.c_int]),
     "nmv_render": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nmv_read_grid": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nmv_write_grid": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -126,6 +128,10 @@ class Mandelbrot:
 
     def set_options(self, glitch_tol=-1.0, max_secondary=-1, device=-1, host_threads=-1):
         self.lib.nmv_set_options(self.h, glitch_tol, max_secondary, device, host_threads)
+
+    def set_exact(self, on=True):
+        """Mandelbrot::exact: repeat the samples FP64 perturbation cannot resolve in double-double arithmetic."""
+        self._ck(self.lib.nmv_set_exact(self.h, 1 if on else 0))
 
     def cancel(self):
         """Abandon the frame another thread is rendering through this view (nmv_cancel)."""

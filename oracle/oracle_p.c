@@ -315,7 +315,8 @@ int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, co
    * error of delta then grows linearly with the iteration count (5e-13 after 7 000 iterations of cfg2, against 5e-15
    * for unbiased roundings) — enough to move the escape count of the ~1 % of samples whose last few hundred iterations
    * are chaotic (tests/golden/k3_truth.json: adjudicated against the reference's own continuation at 2-4x its precision). */
-  for (int i = 0; i < 2 * M; i++) Z[2 + i] = t->x_hi[i] + t->x_lo[i];
+  if (!(t->flags & 1)) /* (flag: the exact mode's probe rendering keeps the truncated orbit) */
+    for (int i = 0; i < 2 * M; i++) Z[2 + i] = t->x_hi[i] + t->x_lo[i];
   for (int j = 1; j <= Jmax; j++) {
     if (t->has_escape && j == Jmax) { gb[j] = 0.0; continue; }
     gb[j] = (Z[2 * j] * Z[2 * j] + Z[2 * j + 1] * Z[2 * j + 1]) * t->glitch_tol;
@@ -408,6 +409,89 @@ int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, co
     st->glitched += (uint64_t)n_rq; st->rebased += rebased;
   }
   return n_rq;
+}
+
+/* ---- double-double continuation ("exact mode", newman_b200/csrc/k3_dd.cuh mirrors it one for one) ----------------
+ * FP64 perturbation carries a relative error of ~5e-15 in delta after a few thousand iterations, and samples whose last
+ * few hundred iterations are chaotic amplify that past 1. For the samples listed — the ones whose
+ * count depends on how the orbit table was rounded — phase 3 is repeated with delta, eps and the orbit in double-double
+ * (~106 bits): delta' = delta*(2Z + delta) + eps, z' = Z' + delta', escape test on the high parts, rebasing onto Z[0] = 0
+ * when the sample outlives the orbit. Phases 1-2 are the reference's double arithmetic and unchanged.
+ * Every operation below is a plain double operation or an explicit fma: no contraction (-ffp-contract=off). */
+typedef struct { double hi, lo; } dd_t;
+static dd_t dd_fast2sum(double a, double b) { dd_t r; r.hi = a + b; r.lo = b - (r.hi - a); return r; }
+static dd_t dd_2sum(double a, double b) {
+  dd_t r; r.hi = a + b; double bb = r.hi - a; r.lo = (a - (r.hi - bb)) + (b - bb); return r;
+}
+static dd_t dd_add(dd_t x, dd_t y) {
+  dd_t s = dd_2sum(x.hi, y.hi);
+  dd_t t = dd_2sum(x.lo, y.lo);
+  s.lo += t.hi;
+  s = dd_fast2sum(s.hi, s.lo);
+  s.lo += t.lo;
+  return dd_fast2sum(s.hi, s.lo);
+}
+static dd_t dd_mul(dd_t x, dd_t y) {
+  dd_t p; p.hi = x.hi * y.hi; p.lo = fma(x.hi, y.hi, -p.hi);
+  p.lo += x.hi * y.lo;
+  p.lo += x.lo * y.hi;
+  return dd_fast2sum(p.hi, p.lo);
+}
+static dd_t dd_neg(dd_t x) { x.hi = -x.hi; x.lo = -x.lo; return x; }
+static dd_t dd_dbl(dd_t x) { x.hi *= 2.0; x.lo *= 2.0; return x; }   /* exact */
+
+int64_t oraclep_refine_dd(const op_tables* t, const double* eps_re, const double* eps_re_lo, int nc, const double* eps_im,
+                          const double* eps_im_lo, int nr, const int32_t* pix_list, int64_t n_list, op_escape* out,
+                          op_stats* st) {
+  const int M = t->M, N = t->N;
+  const int Jmax = M + (t->has_escape ? 1 : 0);
+  uint64_t executed = 0, evals = 0, rebased = 0;
+  (void)nr;
+  if (t->eps_re_exp || t->eps_im_exp) return -1; /* scaled frames are not refined */
+  for (int64_t w = 0; w < n_list; w++) {
+    const int pix = pix_list[w];
+    op_escape* e = &out[pix];
+    const int r = pix / nc, c = pix - r * nc;
+    series_t s;
+    const fec_t eps = eps_of(t, eps_re, eps_im, r, c);
+    series_init(&s, t, eps, eps_re[c], eps_im[r]);
+    int L = series_scan(&s, &evals);
+    int found = L - 1;
+    double yr, yi;
+    if (bailed_mag(&s, found, &yr, &yi) > BAILOUT2) continue; /* phase 2 decided it: nothing to refine */
+    if (L >= N) continue;
+    cplx d0 = series_d(&s, found);
+    dd_t dr = {d0.re, 0.0}, di = {d0.im, 0.0};
+    const dd_t er = {eps_re[c], eps_re_lo ? eps_re_lo[c] : 0.0}, ei = {eps_im[r], eps_im_lo ? eps_im_lo[r] : 0.0};
+    int j = L, off = -1;
+    for (;;) {
+      /* Z[j] = X[j-1] as hi + lo (Z[0] = 0; the escaped iterate X[M] has no low part) */
+      dd_t xr = {0.0, 0.0}, xi = {0.0, 0.0};
+      if (j >= 1) {
+        xr.hi = t->x_hi[2 * (j - 1)]; xi.hi = t->x_hi[2 * (j - 1) + 1];
+        if (j - 1 < M) { xr.lo = t->x_lo[2 * (j - 1)]; xi.lo = t->x_lo[2 * (j - 1) + 1]; }
+      }
+      const dd_t wr = dd_add(dd_dbl(xr), dr), wi = dd_add(dd_dbl(xi), di);
+      const dd_t ndr = dd_add(dd_add(dd_mul(dr, wr), dd_neg(dd_mul(di, wi))), er);
+      const dd_t ndi = dd_add(dd_add(dd_mul(dr, wi), dd_mul(di, wr)), ei);
+      dr = ndr; di = ndi;
+      ++j;
+      executed++;
+      dd_t yr2 = {t->x_hi[2 * (j - 1)], 0.0}, yi2 = {t->x_hi[2 * (j - 1) + 1], 0.0};
+      if (j - 1 < M) { yr2.lo = t->x_lo[2 * (j - 1)]; yi2.lo = t->x_lo[2 * (j - 1) + 1]; }
+      const dd_t zr = dd_add(yr2, dr), zi = dd_add(yi2, di);
+      const double zmag = fma(zi.hi, zi.hi, zr.hi * zr.hi);
+      if (zmag > BAILOUT2) {
+        e->iterations = j + off;
+        e->smoothing = oraclep_smoothing(zr.hi * zr.hi + zi.hi * zi.hi);
+        break;
+      }
+      if (j + off + 1 >= N) { e->iterations = N; e->smoothing = 0.0f; break; }
+      if (j == Jmax) { rebased++; off = j + off; j = 0; dr = zr; di = zi; }
+    }
+  }
+  if (st) { st->executed_iters += executed; st->series_evals += evals; st->rebased += rebased; }
+  return 0;
 }
 
 int64_t oraclep_pick_reference(const int32_t* rq_pix, const int32_t* rq_iter, int64_t n) {

@@ -19,7 +19,7 @@
 typedef struct { int32_t iterations; float smoothing; } op_escape; /* grid.h:8-16 */
 
 typedef struct {
-  int32_t M, N, has_escape, reserved;
+  int32_t M, N, has_escape, flags; /* flags & 1: iterate against the truncated orbit (NM_TABLES_ORBIT_TRUNCATED) */
   double tol, glitch_tol;
   const double *x_hi, *x_lo, *a, *b, *c; /* same layout as nm_deep_tables */
   const int32_t *a_exp, *b_exp, *c_exp;  /* floatexp series: a/b/c are mantissas, these the exponents */
@@ -41,6 +41,13 @@ void oraclep_render_hw(const double* c_re, int nc, const double* c_im, int nr, i
 int64_t oraclep_render_deep(const op_tables* t, const double* eps_re, int nc, const double* eps_im, int nr,
                             int cardioid_mode, const uint8_t* mask, const int32_t* pix_list, int64_t n_list,
                             int mode, op_escape* out, int32_t* rq_pix, int32_t* rq_iter, op_stats* st);
+
+/* "Exact mode": phase 3 of the listed samples repeated in double-double arithmetic against the orbit as hi + lo, with
+ * rebasing at the end of the orbit; eps_*_lo (may be NULL) = low parts of the pixel offsets. Results overwrite out[pix].
+ * Mirrors newman_b200/csrc/k3_dd.cuh. Returns 0, or -1 for scaled frames (not refined). */
+int64_t oraclep_refine_dd(const op_tables* t, const double* eps_re, const double* eps_re_lo, int nc, const double* eps_im,
+                          const double* eps_im_lo, int nr, const int32_t* pix_list, int64_t n_list, op_escape* out,
+                          op_stats* st);
 
 /* Per-pixel probe of the series phase: returns L (d.size() after the scan, mandelbrot.cpp:165-181)
  * and d[L-1]. */

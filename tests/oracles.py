@@ -31,7 +31,7 @@ def sha(a):
 
 
 class OpTables(C.Structure):
-    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("has_escape", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("has_escape", C.c_int32), ("flags", C.c_int32),
                 ("tol", C.c_double), ("glitch_tol", C.c_double),
                 ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p),
                 ("a_exp", C.c_void_p), ("b_exp", C.c_void_p), ("c_exp", C.c_void_p),
@@ -63,6 +63,9 @@ def oraclep():
         _p.oraclep_pick_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         _p.oraclep_resolve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]
+        _p.oraclep_refine_dd.restype = C.c_int64
+        _p.oraclep_refine_dd.argtypes = [C.POINTER(OpTables), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(OpStats)]
         _p.oraclep_smoothing.restype = C.c_float
         _p.oraclep_smoothing.argtypes = [C.c_double]
         _p.oraclep_trunc_add3.restype = C.c_double
@@ -88,11 +91,12 @@ class Tables:
         self.N, self.tol, self.glitch_tol = N, tol, glitch_tol
         self.exps = None if exps is None else [np.ascontiguousarray(v, dtype=np.int32) for v in exps]
         self.eps_exps = None if eps_exps is None else [np.ascontiguousarray(v, dtype=np.int32) for v in eps_exps]
+        self.orbit_truncated = False   # True: K3 against the truncated orbit (the exact mode's probe rendering)
 
     def op(self):
         ex = [None] * 3 if self.exps is None else [v.ctypes.data for v in self.exps]
         ee = [None] * 2 if self.eps_exps is None else [v.ctypes.data for v in self.eps_exps]
-        return OpTables(M=self.M, N=self.N, has_escape=self.has_escape, reserved=0, tol=self.tol,
+        return OpTables(M=self.M, N=self.N, has_escape=self.has_escape, flags=1 if self.orbit_truncated else 0, tol=self.tol,
                         glitch_tol=self.glitch_tol, x_hi=self.x_hi.ctypes.data, x_lo=self.x_lo.ctypes.data,
                         a=self.a.ctypes.data, b=self.b.ctypes.data, c=self.c.ctypes.data,
                         a_exp=ex[0], b_exp=ex[1], c_exp=ex[2], eps_re_exp=ee[0], eps_im_exp=ee[1])
@@ -122,6 +126,21 @@ def p_render_deep(t, eps_re, eps_im, cardioid_mode=0, mask=None, pix_list=None, 
                                       vp(pix_list), 0 if pix_list is None else len(pix_list), mode, vp(out),
                                       vp(rq_pix), vp(rq_it), C.byref(st))
     return out, rq_pix[:n].copy(), rq_it[:n].copy(), {k: getattr(st, k) for k, _ in st._fields_}
+
+
+def p_refine_dd(t, eps_re, eps_im, pix_list, eps_lo=None, out=None):
+    """oraclep_refine_dd: phase 3 of the listed samples in double-double arithmetic (the exact mode's second pass)."""
+    nr, nc = len(eps_im), len(eps_re)
+    if out is None:
+        out = np.zeros((nr, nc), dtype=ESC)
+    pix = np.ascontiguousarray(pix_list, dtype=np.int32)
+    lo = [None, None] if eps_lo is None else [np.ascontiguousarray(x, dtype=np.float64) for x in eps_lo]
+    st = OpStats()
+    ot = t.op()
+    rc = oraclep().oraclep_refine_dd(C.byref(ot), vp(eps_re), vp(lo[0]), nc, vp(eps_im), vp(lo[1]), nr, vp(pix), len(pix), vp(out),
+                                     C.byref(st))
+    assert rc == 0, "scaled frames are not refined"
+    return out, {k: getattr(st, k) for k, _ in st._fields_}
 
 
 def p_render_hw(c_re, c_im, N, mask=None):

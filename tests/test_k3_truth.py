@@ -103,3 +103,33 @@ def test_cfg2_port_vs_truth_subsample():
     print("cfg2 (768 samples)", a)
     assert a["ref_wrong"] == 0
     assert a["port_agree"] >= 0.985 and a["port_max_abs_diff"] <= 400
+
+
+@needs_ref
+def test_exact_mode_on_the_cpu_oracle():
+    """The exact mode restated on the CPU (Oracle-P == the CUDA path bit for bit): the probe — the sample set rendered against
+    the rounded and against the truncated orbit — flags every sample the FP64 pass gets wrong, and the double-double pass
+    (oraclep_refine_dd) gives the flagged samples the count of the converged continuation, i.e. the compiled reference's."""
+    from newman_b200 import workloads
+    from oracles import p_refine_dd
+    cfg = workloads.config("cfg2")
+    z = load("k3_truth_cfg2.npz")
+    v = RefView(cfg["nr"], cfg["nc"], N=cfg["N"], sz=cfg["sz"], center=cfg["center"], tol=cfg["tol"])
+    v.precompute_at(*[int(x) for x in z["probe"]])
+    t = v.tables()
+    er, ei = v.eps()
+    sel = np.arange(0, len(z["pix"]), 3)
+    pix = np.ascontiguousarray(z["pix"][sel])
+    truth = z["t1b"]["iterations"][sel]
+    a, _, _, _ = p_render_deep(t, er, ei, pix_list=pix, mode=1)
+    t.orbit_truncated = True
+    b, _, _, _ = p_render_deep(t, er, ei, pix_list=pix, mode=1)
+    t.orbit_truncated = False
+    a, b = a.reshape(-1)[pix]["iterations"], b.reshape(-1)[pix]["iterations"]
+    wrong, flagged = a != truth, a != b
+    print("cfg2 (2 048 samples): FP64 wrong", int(wrong.sum()), " flagged by the probe", int(flagged.sum()))
+    assert wrong.sum() > 0 and not (wrong & ~flagged).any()
+    out, st = p_refine_dd(t, er, ei, pix[flagged])
+    fixed = a.copy()
+    fixed[flagged] = out.reshape(-1)[pix[flagged]]["iterations"]
+    assert np.array_equal(fixed, truth)
