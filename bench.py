@@ -1034,6 +1034,38 @@ def measure_view(env, args, workload, steps, y_mult=1, band=None):
             "timer": "wall clock around the call, barrier + synchronize on both sides; includes the host arbitrary-precision work"}
 
 
+def measure_exact_mode(env, args):
+    """The same frame through the drop-in class with Mandelbrot::exact = 1 (untimed region; its own frame time is reported):
+    after the frame, the samples whose escape count depends on how the orbit table was rounded are repeated in double-double
+    arithmetic (csrc/k3_dd.cuh). Compared on the adjudication fixture's sample with the reference's counts (which equal the
+    converged continuation there) — tests/golden/k3_truth_cfg2.npz, the sample bench.py's CPU legs use."""
+    from newman_b200 import workloads
+    fn = os.path.join(ROOT, "tests", "golden", "k3_truth_cfg2.npz")
+    if not os.path.exists(fn):
+        return None
+    z = np.load(fn)
+    cfg = workloads.config("cfg2")
+    v = view_for(cfg)
+    v.set_options(device=env.local)
+    v.set_exact(True)
+    v.render()                       # buffers of the refinement pass exist
+    t0 = time.perf_counter()
+    out = v.render()
+    secs = time.perf_counter() - t0
+    i = v.frame_info()
+    it = out.reshape(-1)[z["pix"]]["iterations"]
+    ref, truth = z["ref"]["iterations"], z["t1b"]["iterations"]
+    d = np.abs(it.astype(np.int64) - ref.astype(np.int64))
+    return {"equal_count_frac": float((it == ref).mean()), "n": int(len(it)), "n_diff": int((d != 0).sum()), "max_abs_diff": int(d.max()),
+            "truth_agree_gpu": float((it == truth).mean()), "refined_samples": int(i["refined"]),
+            "refined_frac_of_frame": i["refined"] / float(cfg["nr"] * cfg["nc"]),
+            "device_ms": i["device_ms"], "refine_device_ms": i["refine_ms"], "frame_s": secs,
+            "probe": [int(i["probe_row"]), int(i["probe_col"])], "probe_matches_fixture": [int(i["probe_row"]), int(i["probe_col"])] == [int(x) for x in z["probe"]],
+            "note": "Mandelbrot::exact = 1: the frame, a second rendering against the truncated orbit (the sensitivity probe), and the "
+                    "double-double pass over the samples whose count differed; reference counts from the fixture (== the compiled "
+                    "reference on this sample: ref_matches_fixture above)"}
+
+
 def measure_strong(env, args, steps):
     """N > 1: ONE frame of the north-star configuration (cfg3: 3840x2160, 4x multisampling => 8640 x 15360 samples, 1e-100,
     N = 2^20; reference viewer.cpp:186-253) split over the ranks inside libnewman_b200.so — strong scaling. Device time =
@@ -1120,6 +1152,8 @@ def run_ours(args):
         line = measure_frames(env, args, args.workload, args.steps, args.warmup, not args.no_cpu_baseline, y_mult)
     if not args.no_extras and args.scale == 1:
         xs = args.extra_steps
+        if env.rank == 0 and env.world == 1 and args.workload == "cfg2" and line is not None and "cpu_baseline" in line:
+            line["cpu_baseline"]["parity_on_sample"]["exact_mode"] = measure_exact_mode(env, args)
         if not main_is_video:
             ev = measure_view(env, args, args.workload, xs, y_mult=y_mult)
             if line is not None:

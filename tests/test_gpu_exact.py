@@ -74,6 +74,8 @@ def test_exact_mode_resolves_every_adjudicated_sample_of_cfg2():
     print("cfg2: plain frame %d of %d sampled counts differ from the truth; exact mode %d. refined %d samples (%.2f %% of the frame), "
           "device %.1f + %.1f ms" % ((p6 != truth).sum(), len(truth), (e6 != truth).sum(), i1["refined"],
                                      100.0 * i1["refined"] / plain.size, i1["device_ms"], i1["refine_ms"]))
+    bad = np.nonzero(e6 != truth)[0]
+    print("   still different (sample id, plain, exact, truth):", [(int(z["pix"][i]), int(p6[i]), int(e6[i]), int(truth[i])) for i in bad])
     assert (p6 != truth).sum() > 0
     assert np.array_equal(e6, truth)
     changed = int((plain["iterations"] != exact["iterations"]).sum())
