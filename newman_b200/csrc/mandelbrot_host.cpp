@@ -96,7 +96,8 @@ struct RoundParams {
 // earliest flag iteration (lowest id on ties), ...; after max_secondary such rounds the rest is
 // finished in one rebasing pass. T is overwritten by the secondary tables.
 void run_rounds(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp, DeepTablesHost& T, int cmode,
-                const std::vector<uint8_t>& mask, const std::vector<int32_t>* first_list, newman_b200::FrameInfo& info) {
+                const std::vector<uint8_t>& mask, const std::vector<int32_t>* first_list, newman_b200::FrameInfo& info,
+                std::vector<int32_t>* primary_glitched = nullptr) {
   nm_ctx* ctx = eng.ctx;
   std::vector<int32_t> rq_pix, rq_iter;
   if (first_list) rq_pix = *first_list;
@@ -138,6 +139,7 @@ void run_rounds(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp
     info.glitched += (unsigned long long)n_rq;
     rq_pix.resize((size_t)n_rq); rq_iter.resize((size_t)n_rq);
     nm_frame_requeue(ctx, rq_pix.data(), rq_iter.data(), n_rq);
+    if (round == 0 && primary_glitched) *primary_glitched = rq_pix;
     // next reference: the glitched sample flagged earliest, lowest pixel id on ties
     size_t best = 0;
     for (size_t i = 1; i < rq_pix.size(); i++)
@@ -285,7 +287,7 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
 // (k3_dd.cuh). On cfg2's 6 144-sample adjudication set the probe flags 72 samples, among them every one of the 26 the FP64
 // frame gets wrong, and the double-double pass reproduces the reference's count on all of them.
 void refine_exact(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp, const DeepTablesHost& T0, int cmode,
-                  const std::vector<uint8_t>& mask, newman_b200::FrameInfo& info) {
+                  const std::vector<uint8_t>& mask, const std::vector<int32_t>& primary_glitched, newman_b200::FrameInfo& info) {
   nm_ctx* ctx = eng.ctx;
   eng.check(nm_raster_keep(ctx), "nm_raster_keep");
   newman_b200::FrameInfo probe;
@@ -306,6 +308,14 @@ void refine_exact(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& 
     if (m != n) eng.check(m < 0 ? (int)m : NM_ESTATE, "nm_raster_diff");
   }
   eng.check(nm_raster_restore(ctx), "nm_raster_restore");
+  // ... plus every sample the primary round flagged as glitched: the frame finished those against a secondary reference
+  // or by rebasing, i.e. from ANOTHER series start than the reference's own algorithm takes (its series is relative to its
+  // probe = our primary reference), which both renderings do alike — the probe cannot see it. In double-double the
+  // cancellation behind the glitch flag is harmless, so they are repeated against the primary reference like the rest.
+  list.insert(list.end(), primary_glitched.begin(), primary_glitched.end());
+  std::sort(list.begin(), list.end());
+  list.erase(std::unique(list.begin(), list.end()), list.end());
+  n = (int64_t)list.size();
   info.refined = (unsigned long long)n;
   if (n == 0) return;
   const int fe = T0.finite ? (rp.force_floatexp == 1 ? 1 : 0) : 1;
@@ -783,10 +793,11 @@ void Mandelbrot::renderFrameImpl() {
     DeepTablesHost T0;
     const bool refine = exact != 0 && cmode != NM_CARDIOID_ALL;
     if (refine) T0 = T;   // run_rounds overwrites T with the secondary references
-    run_rounds(eng, v, rp, T, cmode, mask, nullptr, info_);
+    std::vector<int32_t> primary_glitched;
+    run_rounds(eng, v, rp, T, cmode, mask, nullptr, info_, &primary_glitched);
     tr.lap("rounds (GPU + secondary)");
     if (refine && info_.floatexp != 2) {
-      refine_exact(eng, v, rp, T0, cmode, mask, info_);
+      refine_exact(eng, v, rp, T0, cmode, mask, primary_glitched, info_);
       tr.lap("exact mode (probe + dd)");
     }
     eng.check(nm_read_rows(ctx, 0, v.nr, out), "nm_read_rows");
