@@ -1,5 +1,5 @@
 // Checked (one step at a time, exact double comparisons) form of the K3 iteration: used by K2 for the
-// <= 3 steps that bring a fresh pixel to an index that is a multiple of 4, and by k3_events to resolve
+// <= 3 steps that bring a fresh pixel to an index that is a multiple of 4, and (round 1) by k3_events to resolve
 // the pixels the branch-free kernel exported. Same operation order as k3_perturb.cuh / the oracle.
 // SCALED = true: the frame carries floatexp eps and (dr, di, e) states (floatexp.cuh "scaled
 // perturbation state"); SCALED = false compiles to exactly the plain-double code.
@@ -48,7 +48,7 @@ template <> struct EpsVal<true> {
   __device__ __forceinline__ double im_at(int e) const { return eps_scaled(i, i0, e); }
 };
 
-// Exact single step + decisions, shared by K2's alignment steps, k3_events and k3_finish. Returns:
+// Exact single step + decisions, shared by K2's alignment steps and the checked paths. Returns:
 //   0 continue, 1 escaped (r2 set), 2 glitched (MODE_REQUEUE), 3 |z|^2 < |delta|^2: rebase (MODE_REBASE).
 // State (dr, di, j) is advanced in place; (zr, zi) = z.
 // S = 2^e and (er, ei) = eps / 2^e of the state (1 and eps for a plain state).
@@ -80,7 +80,7 @@ __device__ __forceinline__ int checked_step(const double2* __restrict__ Z, const
   return 0;
 }
 
-struct CheckedParams {  // what the checked path needs (K2 alignment steps, k3_events)
+struct CheckedParams {  // what the checked path needs (K2 alignment steps, k3_finish)
   const double2* Z;
   const double* gb;
   int Jmax, N;

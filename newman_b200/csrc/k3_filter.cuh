@@ -1,7 +1,7 @@
 // K3 candidate filter — integer-only tests on the high words of delta that decide, per iteration,
 // whether the exact glitch / escape comparisons of k3_checked.cuh COULD fire. k3_fast runs the delta
 // recurrence alone (6 FP64 instructions per iteration: 2 DADD + 4 DFMA) and never forms z = Z + delta;
-// a block in which a filter fires is rolled back and replayed by k3_events with the exact doubles, so
+// a block in which a filter fires is rolled back and replayed by k3_finish<.., EVENTS> with the exact doubles, so
 // the decisions (and therefore the raster) are those of k3_perturb.cuh / the oracle. What has to hold is
 // only that the filters have NO FALSE NEGATIVES; tests/test_k3_filter.py attacks exactly that on the
 // host build of the functions below (nm_k3_filter_entry / nm_k3_filter_fires).

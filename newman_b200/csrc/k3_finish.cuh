@@ -1,7 +1,7 @@
 // K3 (run-to-completion form) — a frame, or the remainder of one, with so few states that the chunk-by-chunk
 // level launches of k3_perturb.cuh / k3_fast.cuh are nothing but launch latency: the glitch re-queue rounds
 // (a few hundred to a few thousand samples against a secondary reference), the final rebasing pass, the
-// probe-search frames, and what k3_events carries into a second sweep (samples that outlived the orbit).
+// probe-search frames, and — with EVENTS — every state a k3_fast sweep exported (k3_fast.cuh).
 // cfg2 spent ~800 of its launches and ~5 of its 41 ms per frame on such sweeps (profiles/r01l_*: every level
 // of the orbit is launched because the host cannot know where the last state dies).
 //

@@ -34,7 +34,7 @@ enum Counter {
   CTR_Q_CUR,          // K3: size of the current input queue
   CTR_DONE,           // K3: pixels finished
   CTR_CHECKED,        // K3 fast kernel: lane-steps taken in the checked (non-block) path
-  CTR_EVENTS,         // K3 fast kernel: exported pixels waiting for k3_events
+  CTR_EVENTS,         // K3 fast kernel: exported pixels waiting for k3_finish<.., EVENTS>
   CTR_CARRY,          // K3 fast path: states carried into the next sweep
   CTR_MINJ,           // lowest table index any K3 state of the coming sweep starts at (levels below are skipped)
   CTR_COUNT = 24

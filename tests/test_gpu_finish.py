@@ -47,7 +47,7 @@ def check(dev, tt, a, b, mode, base):
 @pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D90", "KAT-S", "KAT-B"])
 def test_finish_kernel_vs_oraclep(kat, finish_max):
     """finish_max = 65536: the whole frame in one launch. 300: the frame (1 200 .. 12 288 states) goes through
-    the level kernels and only what k3_events carries into a second sweep is run to completion."""
+    the level kernels and only the event queue of the sweep is run to completion."""
     t, er, ei = kat_inputs(kat)
     dev = newman_b200.Device(0)
     try:
