@@ -190,6 +190,8 @@ FP_LAT = 8           # DADD/DFMA -> dependent DADD/DFMA, as ptxas spaces them (m
 CAP_EDGE = 20        # distances to the block's entry / exit are preserved up to this many cycles
 MAX_WAIT = 0         # experiment: stall up to this many extra cycles for an instruction that can take an operand from the
                      # one before it (0 = only pair instructions that are ready anyway)
+STRICT_EXIT = False
+STRICT_ENTRY = False
 RENAME = True        # give the block's temporaries new registers for the designed order (reregister)
 RENAME_LEADS = (40, 32, 24, 16)   # loads this many FP64 instructions ahead of their first reader, first that fits
 FORCE = False        # experiment: accept a schedule whose per-warp issue time is longer than ptxas's
@@ -259,7 +261,7 @@ class Block(object):
             edge = {"entry": dict((r, min(self.cyc0[k], CAP_EDGE)) for r, k in first_use.items()),
                     "exit_w": dict((r, min(self.total0 - self.cyc0[k], CAP_EDGE)) for r, k in last_writer.items()),
                     "exit_r": dict((r, min(self.total0 - self.cyc0[k], 6)) for r, k in last_reader.items()),
-                    "total0": self.total0, "wait": 0}
+                    "total0": self.total0, "wait": 0, "own": True}
             for x in ins:
                 edge["wait"] |= x.ctrl["wait"]
         self.edge = edge
@@ -276,6 +278,8 @@ class Block(object):
                     m = max(m, edge["entry"].get(r, 0))
             self.entry_min[k] = m
             e = 2
+            if STRICT_EXIT:
+                e = min(self.cyc0[n] - self.cyc0[k], CAP_EDGE) if edge.get("own") else CAP_EDGE
             for r in x.dst:
                 if last_writer[r] == k:
                     e = max(e, edge["exit_w"].get(r, CAP_EDGE))
@@ -838,12 +842,13 @@ def live_after(ins, idx):
         if base == "EXIT":
             if x.pred and i + 1 < n:
                 sc.append(i + 1)
-        elif base == "BRA":
+        elif base in ("BRA", "WARPSYNC") and re.search(r"0x[0-9a-f]+", x.text):
             m = re.search(r"0x([0-9a-f]+)", x.text)
-            if not m or int(m.group(1), 16) not in addr_ix:
+            if int(m.group(1), 16) not in addr_ix:
                 return None
             sc.append(addr_ix[int(m.group(1), 16)])
-            if x.pred and i + 1 < n:
+            # only a plain, unpredicated BRA never falls through (BRA.DIV, BRA.U.ANY, WARPSYNC.COLLECTIVE may)
+            if (x.pred or x.op != "BRA") and i + 1 < n:
                 sc.append(i + 1)
         elif base == "BSYNC":
             sc += bssy
@@ -912,8 +917,7 @@ def recent_writes(ins, start, labels, horizon=24):
             return None
         x = ins[i]
         t = x.text[len(x.pred):].strip() if x.pred else x.text
-        m = re.match(r"\s*R(\d+)\b", t[len(x.op):])
-        if m:
+        for m in re.finditer(r"(?<![A-Za-z])R(\d+)", t[len(x.op):]):   # any of them may be a destination
             regs.update(range(int(m.group(1)), int(m.group(1)) + 4))
         acc += max(1, x.ctrl["stall"])
         i -= 1
@@ -1092,7 +1096,7 @@ def reschedule_cubin(cubin, only=("k3_fast",), tmp="/tmp"):
                     assert d >= FP_LAT, (name, key, d)
             blk = Block(seq)
             blk.live_out = live_after(ins, e)
-            recent = recent_writes(ins, s, labs)
+            recent = None if STRICT_ENTRY else recent_writes(ins, s, labs)
             if recent is not None:      # the entry constraint is only needed for registers written just before the block
                 blk.edge["entry"] = dict((r, c) for r, c in blk.edge["entry"].items() if r in recent)
                 blk = Block(seq, edge=blk.edge)
@@ -1197,7 +1201,10 @@ def process(src, dst, report=True, only=("k3_fast",), check=True):
 
 
 def main():
-    global MAX_WAIT, YIELD_EVERY, FORCE
+    global MAX_WAIT, YIELD_EVERY, FORCE, RENAME, STRICT_EXIT, STRICT_ENTRY
+    STRICT_EXIT = "--strict-exit" in sys.argv
+    STRICT_ENTRY = "--strict-entry" in sys.argv
+    RENAME = "--no-rename" not in sys.argv
     FORCE = "--force" in sys.argv
     for a in sys.argv[1:]:
         if a.startswith("--max-wait="):
