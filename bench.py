@@ -27,6 +27,7 @@ x N); rank r renders the interleaved rows r, r+N, ...; tables are computed on ra
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -55,17 +56,39 @@ K2_INST_PER_EVAL = 19   # 12 DMUL + 6 DADD + ... (k2_series.cuh phase-1 body inc
 
 
 def mix_ceiling(hw, simple, executed, k_ms, peak_dadd, peak_dfma3):
-    """What the measured instruction rates allow for k3_fast's instruction mix: per iteration 2 DADD at the DADD
-    rate + 4 DFMA whose three 64-bit operands are all different registers — such a DFMA issues at 2/3 of the
-    pipe rate (register read port; tools/issue_probe.py, nm_fp64_peak kind 12). Iterations/s as a fraction of
-    that ceiling says how close the kernel is to what the SM can deliver for THIS arithmetic; `frac` (against
-    the plain DADD rate) is the stricter, instruction-mix-agnostic number."""
+    """What the measured instruction rates allow for k3_fast's instruction mix. A warp-wide FP64 instruction reads one
+    64-bit register operand per cycle unless the operand-reuse cache of its slot already holds it, so a DFMA with three
+    fresh operands issues at 2/3 of the pipe rate (tools/issue_probe.py, nm_fp64_peak kinds 12/13). In the order
+    tools/sass_resched.py gives the quiet block — t1, t2, DADD, DADD, ndr, ndi — one DFMA per iteration reads three
+    fresh operands and three read two: per iteration 2 DADD + 1 DFMA(3 fresh) + 3 DFMA(2 fresh). (Round 1 / ptxas's own
+    order: 4 DFMA with three fresh operands, ceiling 1 / (2/dadd + 4/dfma3) = 2 320 Giter/s.) Iterations/s as a
+    fraction of that ceiling says how close the kernel is to what the SM can deliver for THIS arithmetic; `frac`
+    (against the plain DADD rate) is the stricter, instruction-mix-agnostic number."""
+    peak_dfma2 = None
+    if isinstance(peak_dfma3, tuple):
+        peak_dfma3, peak_dfma2 = peak_dfma3
     if hw or simple or not (k_ms > 0 and peak_dadd and peak_dfma3):
         return {}
-    ceiling = 1.0 / (2.0 / peak_dadd + 4.0 / peak_dfma3)       # iterations/s
     rate = executed / (k_ms * 1e-3)
-    return {"mix_ceiling_giter_s": ceiling / 1e9, "frac_of_mix_ceiling": rate / ceiling,
-            "peak_dfma_3_distinct_operands_ginst": peak_dfma3 / 1e9}
+    out = {"peak_dfma_3_distinct_operands_ginst": peak_dfma3 / 1e9}
+    if peak_dfma2:
+        ceiling = 1.0 / (2.0 / peak_dadd + 1.0 / peak_dfma3 + 3.0 / peak_dfma2)       # iterations/s
+        out["peak_dfma_2_distinct_operands_ginst"] = peak_dfma2 / 1e9
+        out["mix_ceiling_ptxas_order_giter_s"] = 1.0 / (2.0 / peak_dadd + 4.0 / peak_dfma3) / 1e9
+    else:
+        ceiling = 1.0 / (2.0 / peak_dadd + 4.0 / peak_dfma3)
+    out.update({"mix_ceiling_giter_s": ceiling / 1e9, "frac_of_mix_ceiling": rate / ceiling})
+    return out
+
+
+def resched_note():
+    """what tools/sass_resched.py did to the library that is loaded (written next to it at build time), or None"""
+    try:
+        from newman_b200 import _lib
+        rows = [l.strip() for l in open(_lib.LIB_PATH + ".resched.txt") if "k3_fastILi4" in l]
+        return [re.sub(r"^_ZN2nm7k3_fastILi(\d)ELb(\d)EEEvNS_8K3ParamsEPNS_8PixStateE", lambda m: "k3_fast<%s,%s>" % (m.group(1), "scaled" if m.group(2) == "1" else "plain"), l) for l in rows]
+    except (IOError, OSError):
+        return None
 
 
 METRIC = "executed pixel-iterations/sec"
@@ -422,7 +445,8 @@ class Env:
         """FP64 issue peaks measured live on this box (MEASURED_PEAKS.json has no FP64 entry), once per process."""
         if self.peaks is None:
             d = self.dev
-            self.peaks = (d.fp64_peak(0, 1 << 15)[0], d.fp64_peak(1, 1 << 15)[0], d.fp64_peak(12, 1 << 15)[0])
+            self.peaks = (d.fp64_peak(0, 1 << 15)[0], d.fp64_peak(1, 1 << 15)[0],
+                          (d.fp64_peak(12, 1 << 15)[0], d.fp64_peak(13, 1 << 15)[0]))
             d.sync()
         return self.peaks
 
@@ -752,7 +776,8 @@ def measure_frames(env, args, workload, steps, warmup, cpu_baseline, y_mult):
                          "fp64_tflops": executed / world * k3_flops_iter / (k3_ms * 1e-3) / 1e12 if (k3_ms > 0 and not hw) else None,
                          "fp64_tflops_peak_dfma": 2 * peak_dfma / 1e12,
                          "kernel_ms_per_step": k_ms / steps, "k2_ms_per_step": k2_ms / steps,
-                         "k3_ms_per_step": k3_ms / steps},
+                         "k3_ms_per_step": k3_ms / steps,
+                         "sass_resched": None if hw else resched_note()},
             "executed_iters_per_step": executed / steps, "series_evals_per_step": evals / steps,
             "effective_giter_s": effective / (ms / steps * 1e-3) / 1e9,
             "secondary_references": 0 if hw else len(refs), "glitched_per_step": st_dev.get("glitched", 0) / steps,

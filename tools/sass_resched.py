@@ -1193,6 +1193,11 @@ def process(src, dst, report=True, only=("k3_fast",), check=True):
         rows += summary
     if dst:
         open(dst, "wb").write(bytes(data))
+        if dst.endswith(".so"):     # a note next to the library: what was done to it (bench.py quotes it)
+            with open(dst + ".resched.txt", "w") as f:
+                for r in rows:
+                    f.write("%s block %s: %d instructions, reuse flags %d -> %d, operand cycles %d -> %d, %s\n"
+                            % (r[0], r[1], r[2], r[3], r[4], r[5], r[6], ("patched: " + r[11]) if r[10] else "left alone"))
     if report:
         for r in rows:
             print("%s block %s: %d instructions, reuse flags %d -> %d, operand cycles %d -> %d, issue cycles %d -> %d, model stalls %d, %s"
