@@ -750,6 +750,14 @@ int nm_create(int device, nm_ctx** out) {
   NM_K3_SETUP((k3_fast<4, false>), 4, ctx->occ_k3f[1]);
   NM_K3_SETUP((k3_fast<2, true>), 2, ctx->occ_k3fs[0]);
   NM_K3_SETUP((k3_fast<4, true>), 4, ctx->occ_k3fs[1]);
+  if (const char* e = getenv("NM_K3F_OCC")) {   // experiment: fewer resident CTAs per SM for k3_fast
+    const int cap = atoi(e);
+    if (cap >= 1)
+      for (int q = 0; q < 2; ++q) {
+        if (ctx->occ_k3f[q] > cap) ctx->occ_k3f[q] = cap;
+        if (ctx->occ_k3fs[q] > cap) ctx->occ_k3fs[q] = cap;
+      }
+  }
 #undef NM_K3_SETUP
   NM_CREATE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_k1, k1_escape, K1_THREADS, 0));
 #undef NM_CREATE_CUDA
