@@ -1,7 +1,8 @@
 #!/bin/bash
 # usage: gpurun --timeout 900 -- 'bash tools/gpu_resched_ab.sh <tag> [variants...]'
 # A/B of the instruction orders tools/sass_resched.py produces for k3_fast's quiet block: the libraries
-# newman_b200/libnewman_b200_<variant>.so (built here beforehand; "-" = the in-tree library) are benchmarked back to
+# newman_b200/libnewman_b200_<variant>.so (built here beforehand: `make -C newman_b200/csrc RESCHED=0 OUT=$PWD/newman_b200/libnewman_b200_plain.so`,
+# then `python tools/sass_resched.py ..._plain.so ..._<variant>.so [flags]`; "-" = the in-tree library) are benchmarked back to
 # back on the same box, and the parity tests that compare k3_fast with the oracle bit for bit run on each.
 T=${1:-ab}; shift; mkdir -p gpurun_out
 VARS=${@:-plain - plain -}
