@@ -96,3 +96,134 @@ def test_patched_blocks_verify_against_ptxas_output():
     assert match
     assert match[0] != orig, "the library holds ptxas's own order (built with RESCHED=0?)"
     assert S.check_cubin(orig, match[0]) >= 3
+
+
+# ---- the designed order and the re-registering on a synthetic block (no cuobjdump needed) ----------------------------
+
+def _enc(op, d, a, b=None, c=None, stall=2, wb=7, wait=0, off=0):
+    """an instruction whose encoding carries the same registers as its text (what field_regs checks)"""
+    x = S.Ins()
+    x.addr, x.pred, x.label = 0, None, None
+    x.op = op
+    if op == "DFMA":
+        x.text = "DFMA R%d, %s, R%d, R%d" % (d, ("-R%d" % -a) if a < 0 else "R%d" % a, b, c)
+        x.lo = (d << 16) | (abs(a) << 24) | (b << 32)
+        x.hi = c
+    elif op == "DADD":
+        x.text = "DADD R%d, R%d, R%d" % (d, a, c)
+        x.lo = (d << 16) | (a << 24)
+        x.hi = c
+    else:
+        x.text = "LDS.128 R%d, [R%d+0x%x]" % (d, a, off)
+        x.lo = (d << 16) | (a << 24) | (off << 40)
+        x.hi = 0
+    x.ctrl = {"stall": stall, "yield": 1, "wb": wb, "rb": 7, "wait": wait, "reuse": 0}
+    x.hi = S.set_ctrl(x.hi, x.ctrl)
+    x.dst = x.src = None
+    assert S.decode_operands(x), x.text
+    assert S.field_regs(x) is not None, x.text
+    return x
+
+
+def _synthetic_block(slots=4, depth=4):
+    """the perturbation recurrence for `slots` samples and `depth` iterations in a naive order, registers recycled the
+    way a compiler would for that order: dr/di of slot s in R(12+4s) / R(14+4s), er/ei in R(60+4s) / R(62+4s) (never
+    written), x of iteration t in the quad R(40 + 4 (t % 3)) loaded two iterations ahead, temporaries in R80..R143"""
+    ins = []
+    bar = 0
+    for t in range(depth):
+        q = 40 + 4 * (t % 3)
+        if t + 2 < depth:        # load x for iteration t + 2 into the quad iteration t - 1 used
+            ins.append(_enc("LDS.128", 40 + 4 * ((t + 2) % 3), 9, stall=1, wb=bar, off=16 * (t + 2)))
+            bar = (bar + 1) % 3
+        for s in range(slots):
+            dr, di, er, ei = 12 + 4 * s, 14 + 4 * s, 60 + 4 * s, 62 + 4 * s
+            wr, wi, t1, t2 = [80 + 8 * s + 32 * (t % 2) + 2 * j for j in range(4)]   # two sets of temporaries in rotation
+            w = 7 if t < 2 else (1 << ((t - 2) % 3))
+            ins.append(_enc("DADD", wr, dr, c=q, wait=0 if t < 2 else w))
+            ins.append(_enc("DADD", wi, di, c=q + 2, stall=8))
+            ins.append(_enc("DFMA", t1, dr, wr, er))
+            ins.append(_enc("DFMA", t2, dr, wi, ei, stall=8))
+            ins.append(_enc("DFMA", dr, -di, wi, t1, stall=2))
+            ins.append(_enc("DFMA", di, di, wr, t2, stall=8))
+    return ins
+
+
+def _free_entry(ins):
+    """a Block whose registers may be touched at once (nothing was written just before it: recent_writes)"""
+    edge = S.Block(ins).edge
+    edge["entry"] = {}
+    edge["exit_w"] = dict((r, min(v, 8)) for r, v in edge["exit_w"].items())   # results needed 8 cycles after the block at the earliest
+    return S.Block(ins, edge=edge)
+
+
+def test_template_and_reregistering_on_a_synthetic_block():
+    ins = _synthetic_block()
+    blk = _free_entry(ins)
+    ideal = blk.template()
+    assert ideal is not None and len(blk.units) == 16
+    assert [u["depth"] for u in blk.units] == [d for d in range(4) for _ in range(4)]
+    assert S.Block(_synthetic_block(slots=2, depth=4)).template() is None     # needs three samples or more
+    got = blk.renamed(8)
+    assert got is not None
+    nb, em = got
+    S.verify(nb, em)                                        # latency, scoreboard, reuse flags, edges
+    new = [nb.ins[k] for k, _ in em]
+    assert S.same_results(ins, new, None)                   # same final value in every register, none new written
+    before = S.operand_cycles([(x, x.ctrl) for x in ins])
+    after = S.operand_cycles([(nb.ins[k], c) for k, c in em])
+    assert before == 16 * 16 + 2                            # no reuse at all + 2 loads
+    assert after <= 16 * 13 + 2 + 6                         # the designed order, a few misses at the block's ends
+    # the encodings follow the new registers
+    for x in new:
+        assert S.field_regs(x) is not None
+
+
+def test_reregistering_respects_live_out_and_pool():
+    ins = _synthetic_block()
+    blk = _free_entry(ins)
+    written = set(r for x in ins for r in x.dst)
+    nb, em = blk.renamed(8)
+    assert set(r for x in nb.ins for r in x.dst) <= written
+    # with only dr/di live after the block the temporaries' last values need not be reproduced ...
+    blk2 = _free_entry(ins)
+    blk2.live_out = set(range(12, 28))
+    nb2, em2 = blk2.renamed(8)
+    new2 = [nb2.ins[k] for k, _ in em2]
+    assert S.same_results(ins, new2, blk2.live_out)
+    # ... and a sequence that gets one of the live values wrong is caught
+    bad = list(new2)
+    i = [k for k, x in enumerate(bad) if x.op == "DFMA"][-1]
+    bad[i], bad[i - 1] = bad[i - 1], bad[i]
+    wrong = _enc("DFMA", 12, 14, 80, 84)
+    assert not S.same_results(ins, bad[:-1] + [wrong], blk2.live_out)
+
+
+def test_liveness_and_recent_writes_are_conservative():
+    def I(addr, text, stall=2):
+        x = S.Ins()
+        x.addr, x.text, x.label, x.lo, x.hi = addr, text, None, 0, 0
+        x.pred = None
+        t = text
+        if t.startswith("@"):
+            x.pred, t = t.split(None, 1)
+        x.op = t.split()[0]
+        x.ctrl = {"stall": stall, "yield": 1, "wb": 7, "rb": 7, "wait": 0, "reuse": 0}
+        x.dst = x.src = None
+        return x
+    prog = [I(0x00, "DADD R10, R2, R4"),
+            I(0x10, "@P0 BRA 0x40"),
+            I(0x20, "DFMA R12, R10, R6, R8"),          # reads R10 on the fall-through path only
+            I(0x30, "BRA 0x50"),
+            I(0x40, "DADD R10, R20, R22"),             # the taken path overwrites R10 first
+            I(0x50, "LOP3.LUT P4, R28, R12, 0x1, RZ, 0xc0, !PT"),
+            I(0x60, "EXIT")]
+    live = S.live_after(prog, 1)
+    assert 10 in live and 6 in live and 20 in live          # live on SOME path
+    assert 40 not in live
+    live4 = S.live_after(prog, 4)
+    assert 10 not in live4 and 20 in live4 and 12 in live4  # R10 is written before any read from here on
+    # every register token before the block counts as possibly written (a destination may follow a predicate)
+    rec = S.recent_writes(prog, 6, set(), horizon=4)
+    assert rec is not None and 28 in rec and 12 in rec
+    assert S.recent_writes(prog, 6, {0x50}, horizon=8) is None   # another path joins inside the window

@@ -213,6 +213,10 @@ FORCE = False        # experiment: accept a schedule whose per-warp issue time i
 YIELD_EVERY = 0      # a yield hint on an instruction without reuse flags every N instructions (ptxas: about 7); 0 = none, which measured 0.5 % faster
 
 
+class Unschedulable(Exception):
+    """the order needs something the control word cannot express"""
+
+
 class Block(object):
     live_out = None      # registers that may be read after the block before they are written (None: all)
 
@@ -563,7 +567,8 @@ class Block(object):
         for u in U:
             u["slot"] = roots.index(u["root"])
         U.sort(key=lambda u: (u["depth"], u["slot"]))
-        S_ = len(roots)
+        if len(roots) < 3:
+            return None     # the DADDs hosted two units ahead would belong to the same sample as the unit hosting them
         seq = []
         lead = min(2, len(U))
         for u in U[:lead]:
@@ -610,7 +615,10 @@ class Block(object):
             return None
         nb = Block(new_ins, edge=self.edge)
         nb.schedule(dict((k, k) for k in range(nb.n)))
-        return nb, nb.emit()
+        try:
+            return nb, nb.emit()
+        except Unschedulable:
+            return None
 
     def emit(self):
         """control fields of the new order: [(orig index, ctrl dict)]"""
@@ -641,7 +649,8 @@ class Block(object):
             c = dict(ins[k].ctrl)
             nxt = cyc[order[pos + 1]] if pos + 1 < n else end_t
             st = nxt - cyc[k]
-            assert 1 <= st <= 15, (pos, k, st)
+            if not 1 <= st <= 15:
+                raise Unschedulable("stall count %d at position %d" % (st, pos))
             c["stall"] = st
             c["wait"] = self.new_waits.get(pos, 0) | (self.entry_wait if pos == 0 else 0)
             c["reuse"] = self.new_reuse.get(pos, 0)
@@ -1135,11 +1144,16 @@ def reschedule_cubin(cubin, only=("k3_fast",), tmp="/tmp"):
                     best = (cost_, [(nb.ins[k], c) for k, c in em_], tot_, nb.model_stalls, "re-registered, loads %d ahead" % lead)
             for ideal in (blk.template(), None):
                 blk.schedule(ideal)
-                em_ = blk.emit()
+                try:
+                    em_ = blk.emit()
+                except Unschedulable:
+                    continue
                 tot_ = verify(blk, em_)
                 cost_ = operand_cycles([(seq[k], c) for k, c in em_])
                 if best is None or cost_ < best[0]:
                     best = (cost_, [(seq[k], c) for k, c in em_], tot_, blk.model_stalls, "re-ordered")
+            if best is None:
+                continue
             after, em, new_total, blk.model_stalls, how = best
             before = operand_cycles([(x, x.ctrl) for x in seq])
             nre0 = sum(bin(x.ctrl["reuse"]).count("1") for x in seq)
