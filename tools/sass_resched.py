@@ -1230,7 +1230,18 @@ def process(src, dst, report=True, only=("k3_fast",), check=True):
     if dst:
         open(dst, "wb").write(bytes(data))
         if dst.endswith(".so"):     # a note next to the library: what was done to it (bench.py quotes it)
+            import hashlib
+            seen = set()
             with open(dst + ".resched.txt", "w") as f:
+                for r in rows:      # the code of the kernels the pass works on (their .text sections; reproducible)
+                    if r[0] not in seen:
+                        seen.add(r[0])
+                        for (off, size) in embedded_cubins(data):
+                            try:
+                                o, n = elf_text_offset(data[off:off + size], r[0])
+                            except KeyError:
+                                continue
+                            f.write("%s code sha256 %s (%d bytes)\n" % (r[0], hashlib.sha256(bytes(data[off + o:off + o + n])).hexdigest()[:16], n))
                 for r in rows:
                     f.write("%s block %s: %d instructions, reuse flags %d -> %d, operand cycles %d -> %d, %s\n"
                             % (r[0], r[1], r[2], r[3], r[4], r[5], r[6], ("patched: " + r[11]) if r[10] else "left alone"))
