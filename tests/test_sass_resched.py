@@ -2,7 +2,6 @@
 operand reuse. CPU-only: it works on the SASS inside the built library (cuobjdump), no GPU needed. What the pass
 does to the RESULTS is covered by the GPU parity tests, which run against the patched library."""
 import os
-import shutil
 import sys
 
 import pytest
@@ -13,7 +12,14 @@ import sass_resched as S  # noqa: E402
 
 LIB = os.path.join(ROOT, "newman_b200", "libnewman_b200.so")
 OBJ = os.path.join(ROOT, "newman_b200", "csrc", "_build", "nm_device.o")
-needs_tools = pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(LIB), reason="needs cuobjdump and the built library")
+def _have_cuobjdump():
+    try:
+        return bool(S.cuobjdump())
+    except RuntimeError:
+        return False
+
+
+needs_tools = pytest.mark.skipif(not _have_cuobjdump() or not os.path.exists(LIB), reason="needs cuobjdump and the built library")
 
 
 def test_control_word_roundtrip():

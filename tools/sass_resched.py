@@ -39,6 +39,16 @@ import struct
 import subprocess
 import sys
 
+def cuobjdump():
+    """the disassembler: on PATH, next to $CUDA_HOME's nvcc, or in the usual place"""
+    import os
+    import shutil
+    for c in (shutil.which("cuobjdump"), os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "cuobjdump"), "/usr/local/cuda/bin/cuobjdump"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("cuobjdump not found")
+
+
 def ctrl_fields(hi):
     c = (hi >> 41) & 0x1FFFFF
     return {"stall": c & 0xF, "yield": (c >> 4) & 1, "wb": (c >> 5) & 7, "rb": (c >> 8) & 7, "wait": (c >> 11) & 0x3F, "reuse": (c >> 17) & 0xF}
@@ -1105,7 +1115,7 @@ def reschedule_cubin(cubin, only=("k3_fast",), tmp="/tmp"):
     os.write(fd, bytes(cubin))
     os.close(fd)
     try:
-        sass = subprocess.check_output(["cuobjdump", "-sass", path]).decode()
+        sass = subprocess.check_output([cuobjdump(), "-sass", path]).decode()
     finally:
         os.unlink(path)
     funcs = parse_functions(sass)
@@ -1180,7 +1190,7 @@ def check_cubin(orig, patched, only=("k3_fast",)):
         os.write(fd, bytes(img))
         os.close(fd)
         try:
-            listings.append(parse_functions(subprocess.check_output(["cuobjdump", "-sass", path]).decode()))
+            listings.append(parse_functions(subprocess.check_output([cuobjdump(), "-sass", path]).decode()))
         finally:
             os.unlink(path)
     fo, fp = listings
