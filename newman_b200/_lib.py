@@ -116,12 +116,17 @@ def load():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C newman_b200/csrc`). newman_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    _lib = load_from(LIB_PATH)
+    return _lib
+
+
+def load_from(path):
+    """A separate handle on another build of the library (tests compare builds side by side); not cached."""
+    lib = C.CDLL(path)
     for name, (res, args) in DEVICE_API.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
     return lib
 
 

@@ -10,8 +10,8 @@ from . import _lib as L
 class Device:
     """One nm_ctx = one GPU + one stream. Mirrors include/newman_b200.h one to one."""
 
-    def __init__(self, device=0):
-        self.lib = L.load()
+    def __init__(self, device=0, lib=None):
+        self.lib = lib if lib is not None else L.load()
         h = C.c_void_p()
         rc = self.lib.nm_create(device, C.byref(h))
         if rc != L.NM_OK:

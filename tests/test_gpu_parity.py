@@ -183,3 +183,43 @@ def test_fp64_peak_probe(dev):
     per_sm_clk = ips / (info["sm_count"] * info["sm_clock_khz"] * 1e3)
     print("DFMA inst/s %.3e  => %.1f lanes/clk/SM at max clock" % (ips, per_sm_clk))
     assert 8 < per_sm_clk < 140
+
+
+@needs_ref
+@pytest.mark.parametrize("group", [4, 2])
+@pytest.mark.parametrize("kat", ["KAT-D30", "KAT-D90", "KAT-S"])
+def test_post_link_pass_changes_no_result(dev, kat, group):
+    """tools/sass_resched.py re-orders and re-registers k3_fast's FP64 blocks inside the shipped library; the same
+    objects linked without it (libnewman_b200_ptxas.so, ptxas's own instruction order) must give the same raster, the
+    same glitch list and the same counters on the same tables — every rounding is the same instruction."""
+    import os
+    from newman_b200 import _lib as L
+    from newman_b200.device import Device
+    other = os.path.join(os.path.dirname(L.LIB_PATH), "libnewman_b200_ptxas.so")
+    if not os.path.exists(other):
+        pytest.skip("libnewman_b200_ptxas.so not built")
+    k = KATS[kat]
+    v = RefView(**k)
+    v.precompute()
+    t = v.tables()
+    er, ei = v.eps()
+    got = []
+    for d in (dev, Device(0, lib=L.load_from(other))):
+        tabs = d.make_tables(t.x_hi, t.x_lo, t.a, t.b, t.c, t.N, t.tol, t.glitch_tol)
+        d.set_option(L.OPT_K3_GROUP, group)
+        try:
+            out = d.render_deep(tabs, er, ei)
+            gpix, git = d.requeue()
+            gs = d.stats()
+        finally:
+            d.set_option(L.OPT_K3_GROUP, 4)
+        o = np.argsort(gpix)
+        got.append((out["iterations"].copy(), bits(out["smoothing"]).copy(), gpix[o].copy(), git[o].copy(),
+                    gs["executed_iters"], gs["rebased"], gs["glitched"]))
+        if d is not dev:
+            d.close()
+    a, b = got
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    assert a[4:] == b[4:]
+    assert a[4] > 0
