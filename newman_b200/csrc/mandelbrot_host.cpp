@@ -162,9 +162,14 @@ void run_rounds(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp
 // the reference's rule (first longest in scan order) is applied to those exact lengths.
 // The winner is the exhaustive search's whenever that one is on the short-list (every fixture tested);
 // probe_search = 0 selects the exhaustive search.
+// `spec` (optional): the caller's next step is the reference build at the winner. The winner by the GPU's counts is,
+// more often than not, the winner by the exact lengths as well, so its build starts on a thread of its own next to the
+// exact check; if the check confirms that candidate, *spec holds its tables and *spec_valid is set (same function, same
+// inputs: the tables are what the caller would have built), else the speculative build is discarded.
 void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundParams& rp, int threads, int cmode,
                          const std::vector<uint8_t>& mask, int& row, int& col, int& length, int* n_exact,
-                         newman_b200::FrameInfo& info) {
+                         newman_b200::FrameInfo& info, DeepTablesHost* spec = nullptr, bool* spec_valid = nullptr) {
+  if (spec_valid) *spec_valid = false;
   std::vector<std::pair<int, int> > cand;
   newman_b200::probe_candidates(v, cand);
   const int n = (int)cand.size();
@@ -221,6 +226,36 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
     std::vector<int> keep;
     for (int i : which) if (i <= first_full && (got[i].iterations < rp.N || i == first_full)) keep.push_back(i);
     which.swap(keep);
+  }
+  struct SpecBuild {      // joined on every way out of this function
+    std::thread th;
+    DeepTablesHost T;
+    std::string fail;
+    int idx = -1;
+    ~SpecBuild() { if (th.joinable()) th.join(); }
+  } sb;
+  // A wrong guess costs the exact check some of its cores and the wait for the discarded build (measured: cfg3, whose
+  // ranking is ill-conditioned, +32 ms per frame; cfg2, where the guess holds, -6 ms): after a miss the next few frames
+  // of the process do not speculate.
+  static std::atomic<int> skip_after_miss(0);
+  bool speculate = spec && spec_valid && !which.empty() && getenv("NM_NO_SPECULATION") == nullptr;
+  if (speculate && skip_after_miss.load(std::memory_order_relaxed) > 0) {
+    skip_after_miss.fetch_sub(1, std::memory_order_relaxed);
+    speculate = false;
+  }
+  if (speculate) {
+    size_t b = 0;   // first longest in scan order, by the GPU's counts
+    for (size_t k = 1; k < which.size(); k++)
+      if (got[which[k]].iterations > got[which[b]].iterations) b = k;
+    sb.idx = which[b];
+    const int sr = cand[sb.idx].first, sc = cand[sb.idx].second;
+    SpecBuild* psb = &sb;
+    const ViewHP* pv = &v;
+    sb.th = std::thread([psb, pv, sr, sc, threads]() {
+      try { newman_b200::build_tables(*pv, sr, sc, psb->T, threads); }
+      catch (const std::exception& e) { psb->fail = e.what(); }
+      catch (...) { psb->fail = "speculative reference build failed"; }
+    });
   }
   std::vector<int> len;
   newman_b200::probe_lengths(v, cand, which, threads, len);
@@ -279,6 +314,15 @@ void find_probe_assisted(newman_b200::Engine& eng, const ViewHP& v, const RoundP
   row = cand[which[best]].first;
   col = cand[which[best]].second;
   length = len[best];
+  if (sb.th.joinable()) {
+    sb.th.join();
+    if (sb.idx == which[best] && sb.fail.empty()) {
+      *spec = std::move(sb.T);
+      *spec_valid = true;
+    }
+    if (!*spec_valid) skip_after_miss.store(8, std::memory_order_relaxed);
+    tr.lap(*spec_valid ? "speculative reference (kept)" : "speculative reference (discarded)");
+  }
 }
 // Exact mode (Mandelbrot::exact). After the frame: (1) keep its raster, (2) render the frame once more against the orbit
 // TRUNCATED to doubles instead of rounded to nearest — same probe, same rounds —, (3) the samples whose escape COUNT differs
@@ -780,10 +824,11 @@ void Mandelbrot::renderFrameImpl() {
     } else {
       int prow, pcol, plen;
       RoundParams rp0 = {N, max_secondary, force_floatexp, error_tolerance, glitch_tolerance, host_threads};
+      bool have = false;
       if (probe_search == 0) newman_b200::find_probe(v, host_threads, prow, pcol, plen);
-      else find_probe_assisted(eng, v, rp0, host_threads, cmode, mask, prow, pcol, plen, nullptr, info_);
+      else find_probe_assisted(eng, v, rp0, host_threads, cmode, mask, prow, pcol, plen, nullptr, info_, &T, &have);
       tr.lap("findProbe (total)");
-      newman_b200::build_tables(v, prow, pcol, T, host_threads);
+      if (!have) newman_b200::build_tables(v, prow, pcol, T, host_threads);
       tr.lap("primary reference");
     }
     info_.orbit_len = T.M; info_.probe_row = T.probe_row; info_.probe_col = T.probe_col;
